@@ -1,0 +1,274 @@
+#!/usr/bin/env python
+"""bench.py -- flowamok per-tick grid update on B200 (BASELINE.json metric: cell-updates/sec, GCUPS).
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path (one process per GPU)
+  python bench.py --impl reference --gpus N --steps K ...   the reference's CPU algorithm (oracle port,
+                                                            all host threads, bounded sample), rank 0 only
+
+A "step" is one tick (stepper_quick.step, steppers.fut:177-185) over the whole grid.  At N=1 the workload is
+BASELINE config 4: the synthetic road network at 16384 x 16384, seed 1, 10 % of road cells
+occupied, quick mode.  Prints ONE JSON line (see the keys below).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+B_ALG = 12.0  # algorithmic bytes per cell-update (SURVEY 8d / BASELINE.md): r+w of a u16 control word and a u32 colour
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (profiling recipe's clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_run(size_w, rows, ticks, warm, threads=None):
+    """The oracle port (reference layout: record of arrays, one full-grid Jacobi pass per fixpoint iteration,
+    count-based termination exactly as steppers.fut:160-163) on a band of the same synthetic network."""
+    from oracle import oracle as O
+    if threads:
+        O.set_threads(threads)
+    g = O.Grid(rows, size_w)
+    g.generate_synthetic(seed=1)
+    ch = O.Chooser(O.CHOOSE_RANDOM)
+    for _ in range(warm):
+        g.step_quick(ch)
+    t0 = time.perf_counter()
+    for _ in range(ticks):
+        g.step_quick(ch)
+    dt = time.perf_counter() - t0
+    return rows * size_w * ticks / dt / 1e9, dt, O.max_threads()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return 0
+    size = args.size
+    # calibrate on a thin band, then size the band so that (steps + warmup) ticks take about a minute
+    g1, dt1, thr = cpu_oracle_run(size, 64, 2, 1)
+    per_cell_tick = dt1 / (64 * size * 2)
+    budget = 60.0
+    rows = int(budget / (per_cell_tick * size * max(1, args.steps + args.warmup)))
+    rows = max(32, min(size, (rows // 16) * 16))
+    gcups, dt, thr = cpu_oracle_run(size, rows, args.steps, args.warmup)
+    sample = f"{rows}x{size} band of the synthetic-{size} network, {args.steps} ticks, quick mode"
+    line = {"impl": "reference", "metric": "cell-updates/sec", "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"synthetic-{size}x{size}-quick (SURVEY App. E, seed 1, 10% of road cells occupied)",
+                       "sample": sample},
+            "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": thr, "kind": "port", "sample": sample},
+            "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference is pure Futhark; no Futhark compiler in the image, so this is the C/OpenMP oracle port "
+                    "in the reference's layout and schedule (BASELINE.md plan B)"}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=16384)
+    ap.add_argument("--mode", default="quick", choices=["quick", "perfect"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import numpy as np
+    import torch
+    import flowamok_b200 as fa
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (flowamok_b200 has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.Stream()
+    perfect = args.mode == "perfect"
+    S = args.size
+    cells = S * S
+    with torch.cuda.stream(stream):
+        ctx = fa.Context(local_rank, stream.cuda_stream)
+        g = ctx.grid(S, S)
+        g.generate_synthetic(seed=1 + rank, density16=6554, ring_full16=2)
+        n_rings, _ = g.cycle_count()
+        g.step(perfect, args.warmup, leaks=False)
+        ctx.sync()
+        g.stats()
+
+        def barrier():
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        # ---- device-resident throughput: K ticks, inputs already in HBM, CUDA events on the launching stream
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        g.step(perfect, args.steps, leaks=False)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop()
+        st = g.stats()
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        value = world * cells * args.steps / (ms * 1e-3) / 1e9
+
+        # ---- per-kernel device time (events between the launches, same stream)
+        prof_ticks = min(50, args.steps)
+        prof = g.step_profile(perfect, prof_ticks)
+        prof_total = sum(prof.values())
+
+        # ---- end to end through the C ABI with HOST buffers: upload + K ticks + leak count + download
+        e2e = None
+        if not args.no_e2e:
+            host = g.download()
+            pin = {}
+            for k in ("uy", "ux", "dy", "dx", "color", "pref", "rng_state"):
+                tt = torch.from_numpy(host[k]).pin_memory()
+                pin[k] = tt.numpy()
+            out = {k: torch.empty_like(torch.from_numpy(host[k])).pin_memory().numpy()
+                   for k in ("dy", "dx", "color", "pref", "rng_state")}
+            del host
+            h2d = sum(v.nbytes for v in pin.values())
+            d2h = sum(v.nbytes for v in out.values()) + 8
+            import ctypes as C
+            barrier()
+            t0 = time.perf_counter()
+            g.upload(**pin, rng_inc=fa.PCG_INC)
+            leaks = g.step(perfect, args.steps, leaks=True)
+            inc = C.c_uint64()
+            ctx.check(ctx.L.flowamok_grid_download(ctx.h, g.h, None, None, out["dy"].ctypes.data, out["dx"].ctypes.data,
+                                                   out["color"].ctypes.data, out["pref"].ctypes.data,
+                                                   out["rng_state"].ctypes.data, C.byref(inc)))
+            barrier()
+            dt = time.perf_counter() - t0
+            if dist is not None:
+                t = torch.tensor([dt], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            e2e = {"value": world * cells * args.steps / dt / 1e9, "unit": "GCUPS",
+                   "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
+                   "seconds": dt, "leaks": int(leaks),
+                   "what": "flowamok_grid_upload (pinned host record-of-arrays) + flowamok_step_quick x steps "
+                           "+ leak count + flowamok_grid_download, wall clock"}
+            del pin, out
+
+    peak, peak_src = measured_peak()
+    per_gpu_gcups = value / world
+    achieved = per_gpu_gcups * B_ALG  # GB/s of algorithmic traffic per GPU
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src,
+                "what": "whole tick (k_u_first + k_u_fix + k_move), 12 algorithmic B per cell-update (SURVEY 8d)",
+                "kernel_ms_per_tick": {k: v / prof_ticks for k, v in prof.items()},
+                "dominant_kernel": max(prof, key=prof.get),
+                "dominant_share": max(prof.values()) / prof_total if prof_total else None}
+    line = {"metric": "cell-updates/sec", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32 bit-planes (32 cells per word) + u32 colour payload",
+            "data": "synthetic",
+            "config": {"workload": f"synthetic-{S}x{S}-{args.mode} (SURVEY App. E, seed 1, 10% of road cells occupied)",
+                       "grid": [S, S], "mode": args.mode, "rings": int(n_rings),
+                       "parallelism": "1 grid" if world == 1 else f"{world} independent {S}x{S} grids (one per GPU)",
+                       "l2": f"state {cells * 9.75 / 1e9:.2f} GB per tick >> 126 MB L2: inputs larger than L2, no flush"},
+            "fixpoint": {"passes_per_tick": st["passes"] / max(1, st["ticks"]),
+                         "sweeps_per_tile_visit": st["sweeps"] / max(1, st["passes"]) / max(1, (S // 48 + 1) * (S // 1024))},
+            "roofline": roofline, "clocks": clocks, "gpu_launches": (3 + (1 if perfect and n_rings else 0)) * args.steps,
+            "e2e": e2e}
+    if rank == 0 and not args.no_cpu and world >= 1:
+        try:
+            g1, dt1, thr = cpu_oracle_run(S, 64, 2, 1)
+            rows = int(15.0 / (dt1 / (64 * S * 2) * S * 6))
+            rows = max(32, min(S, (rows // 16) * 16))
+            gc, dt, thr = cpu_oracle_run(S, rows, 5, 1)
+            line["cpu_baseline"] = {"value": gc, "unit": "GCUPS", "cores": thr, "kind": "port",
+                                    "sample": f"{rows}x{S} band of the same network, 5 ticks, quick mode, {dt:.1f} s"}
+        except Exception as e:  # the oracle is only a reported baseline
+            line["cpu_baseline"] = {"value": None, "unit": "GCUPS", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,70 @@
+"""ctypes binding of include/flowamok.h -- the same stub a reference-side maintainer would write
+(see INTEGRATION.md).  Nothing here computes: every call goes to libflowamok_b200.so, and a missing
+library or a missing CUDA device is a hard error (there is no CPU path)."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+from . import _build
+
+_lib = None
+
+I64, I32, U64, U32, I8, U8 = C.c_int64, C.c_int32, C.c_uint64, C.c_uint32, C.c_int8, C.c_uint8
+P = C.c_void_p
+
+
+class FlowamokError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the in-tree CUDA library (building it first if sources are newer and nvcc exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    so = _build.SO
+    if _build.needs_build():
+        try:
+            _build.build()
+        except Exception as e:  # pragma: no cover
+            if not so.exists():
+                raise FlowamokError(f"libflowamok_b200.so is missing and could not be built: {e}") from e
+    L = C.CDLL(str(so))
+    sig = {
+        "flowamok_context_new": (C.c_int, [C.POINTER(P), C.c_int, P]),
+        "flowamok_context_free": (C.c_int, [P]),
+        "flowamok_context_sync": (C.c_int, [P]),
+        "flowamok_context_get_error": (P, [P]),
+        "flowamok_context_device": (C.c_int, [P]),
+        "flowamok_grid_new": (C.c_int, [P, C.POINTER(P), I64, I64]),
+        "flowamok_grid_free": (C.c_int, [P, P]),
+        "flowamok_grid_shape": (C.c_int, [P, P, C.POINTER(I64), C.POINTER(I64)]),
+        "flowamok_create_grid": (C.c_int, [P, P, I32, C.POINTER(U64), C.POINTER(U64)]),
+        "flowamok_grid_upload": (C.c_int, [P, P, P, P, P, P, P, P, P, U64]),
+        "flowamok_grid_download": (C.c_int, [P, P, P, P, P, P, P, P, P, C.POINTER(U64)]),
+        "flowamok_add_line_vertical": (C.c_int, [P, P, I64, I64, I64, I8]),
+        "flowamok_add_line_horizontal": (C.c_int, [P, P, I64, I64, I64, I8]),
+        "flowamok_add_cell": (C.c_int, [P, P, I64, I64, U32, I8, I8]),
+        "flowamok_set_chooser": (C.c_int, [P, P, C.c_int, P, I64]),
+        "flowamok_set_cycles": (C.c_int, [P, P, I64, P, P, P, P, P, P]),
+        "flowamok_find_cycles": (C.c_int, [P, P, I64, C.POINTER(I64)]),
+        "flowamok_cycle_count": (C.c_int, [P, P, C.POINTER(I64), C.POINTER(I64)]),
+        "flowamok_get_cycles_dense": (C.c_int, [P, P, P]),
+        "flowamok_step_quick": (C.c_int, [P, P, I64, C.POINTER(I64)]),
+        "flowamok_step_perfect": (C.c_int, [P, P, I64, C.POINTER(I64)]),
+        "flowamok_step_profile": (C.c_int, [P, P, C.c_int, I64, C.POINTER(C.c_double)]),
+        "flowamok_step_leaks": (C.c_int, [P, P, C.c_int, I64, P, C.POINTER(I64)]),
+        "flowamok_render": (C.c_int, [P, P, I64, P]),
+        "flowamok_stats": (C.c_int, [P, P, C.POINTER(I64), C.POINTER(I64), C.POINTER(I64)]),
+        "flowamok_generate_synthetic": (C.c_int, [P, P, U64, U32, U32]),
+        "flowamok_version": (C.c_char_p, []),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    L._libc = C.CDLL(None)
+    L._libc.free.argtypes = [P]
+    _lib = L
+    return L

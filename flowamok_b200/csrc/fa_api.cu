@@ -1,0 +1,687 @@
+// flowamok_b200 -- C ABI (include/flowamok.h) over the CUDA kernels.  Host-side state management,
+// packing, the sparse find_cycles and the per-tick launch sequence.  No CPU compute fallback exists:
+// every stepping call needs a CUDA device.
+#include "../../include/flowamok.h"
+
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+#include "fa_kernels.cuh"
+
+using namespace fa;
+
+struct flowamok_context {
+  int device;
+  cudaStream_t stream;
+  bool own_stream;
+  int num_sms;
+  int fix_blocks;  // co-resident CTAs of k_u_fix
+  std::string err;
+};
+
+struct flowamok_grid {
+  flowamok_context *ctx;
+  int gh, gw, pitch, wvalid;
+  size_t nwords, ncells_p;  // plane words, pitched cells
+  U4 *road, *head[2];
+  u32 *pref[2], *calc, *my, *mx, *color[2], *leak_plane;
+  u64 *rng;
+  u64 rng_inc;
+  int cur;
+  int chooser;
+  std::vector<uint8_t> tape;
+  long long tick;
+  // cycles (sparse)
+  unsigned long long *ring_cells, *ring_off;
+  long long n_rings, n_ring_cells;
+  int ring_stride;  // >0: uniform rings, ring_off == nullptr
+  std::vector<int64_t> h_off, h_y, h_x;  // host copy for flowamok_get_cycles_dense
+  std::vector<int8_t> h_cy, h_cx;
+  // per-tick machinery
+  FixState *fs;
+  Diag *diag;
+  Diag *h_diag;  // pinned
+  unsigned int *pend[2];
+  int ntx, nty, mtx, mty;
+  Diag base;  // diag values already reported
+};
+
+static int fail(flowamok_context *ctx, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return 1;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+static inline unsigned int nblk(long long n, int b) { return (unsigned int)((n + b - 1) / b); }
+
+extern "C" {
+
+const char *flowamok_version(void) { return "flowamok_b200 0.1 (sm_100a)"; }
+
+int flowamok_context_new(flowamok_context **out, int device, void *stream) {
+  if (!out) return 1;
+  flowamok_context *ctx = new flowamok_context();
+  *out = ctx;
+  ctx->own_stream = false;
+  ctx->stream = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    ctx->device = -1;
+    return fail(ctx, "no CUDA device: flowamok_b200 has no CPU path (%s)", cudaGetErrorString(e));
+  }
+  if (device < 0) CU(cudaGetDevice(&device));
+  ctx->device = device;
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  ctx->num_sms = prop.multiProcessorCount;
+  if (stream) ctx->stream = (cudaStream_t)stream;
+  else { CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+  CU(cudaFuncSetAttribute(k_u_first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UT::Smem)));
+  CU(cudaFuncSetAttribute(k_u_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UT::Smem)));
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_u_fix, U_THREADS, sizeof(UT::Smem)));
+  if (per_sm < 1) return fail(ctx, "k_u_fix does not fit on an SM");
+  ctx->fix_blocks = per_sm * ctx->num_sms;
+  return 0;
+}
+
+int flowamok_context_free(flowamok_context *ctx) {
+  if (!ctx) return 0;
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return 0;
+}
+int flowamok_context_sync(flowamok_context *ctx) {
+  if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+char *flowamok_context_get_error(flowamok_context *ctx) {
+  if (!ctx || ctx->err.empty()) return nullptr;
+  char *s = (char *)malloc(ctx->err.size() + 1);
+  memcpy(s, ctx->err.c_str(), ctx->err.size() + 1);
+  ctx->err.clear();
+  return s;
+}
+int flowamok_context_device(flowamok_context *ctx) { return ctx ? ctx->device : -1; }
+
+// ---------------------------------------------------------------------------------------------
+int flowamok_grid_new(flowamok_context *ctx, flowamok_grid **out, int64_t gh, int64_t gw) {
+  if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
+  if (gh < 1 || gw < 1 || gh > (1 << 20) || gw > (1 << 20)) return fail(ctx, "grid shape out of range");
+  CU(cudaSetDevice(ctx->device));
+  flowamok_grid *g = new flowamok_grid();
+  g->ctx = ctx;
+  g->gh = (int)gh; g->gw = (int)gw;
+  g->wvalid = (int)((gw + 31) / 32);
+  g->pitch = ((g->wvalid + 3) / 4) * 4;
+  g->nwords = (size_t)g->gh * g->pitch;
+  g->ncells_p = g->nwords * 32;
+  if (g->nwords >= (1ull << 32)) { delete g; return fail(ctx, "grid too large for 32-bit word indices"); }
+  g->cur = 0; g->chooser = CHOOSE_RANDOM; g->tick = 0;
+  g->rng_inc = (0xda3e39cb94b95bdbULL << 1) | 1ULL;
+  g->ring_cells = g->ring_off = nullptr; g->n_rings = g->n_ring_cells = 0; g->ring_stride = 0;
+  g->leak_plane = nullptr;
+  *out = g;
+  CU(cudaMalloc(&g->road, g->nwords * sizeof(U4)));
+  for (int k = 0; k < 2; k++) {
+    CU(cudaMalloc(&g->head[k], g->nwords * sizeof(U4)));
+    CU(cudaMalloc(&g->pref[k], g->nwords * 4));
+    CU(cudaMalloc(&g->color[k], g->ncells_p * 4));
+  }
+  CU(cudaMalloc(&g->calc, g->nwords * 4));
+  CU(cudaMalloc(&g->my, g->nwords * 4));
+  CU(cudaMalloc(&g->mx, g->nwords * 4));
+  CU(cudaMalloc(&g->rng, g->ncells_p * 8));
+  g->ntx = (g->pitch + UT::TW - 1) / UT::TW; g->nty = (g->gh + UT::TR - 1) / UT::TR;
+  g->mtx = (g->pitch + MT::TW - 1) / MT::TW; g->mty = (g->gh + MT::TR - 1) / MT::TR;
+  size_t ntiles = (size_t)g->ntx * g->nty;
+  CU(cudaMalloc(&g->pend[0], ntiles * 4));
+  CU(cudaMalloc(&g->pend[1], ntiles * 4));
+  CU(cudaMalloc(&g->fs, sizeof(FixState)));
+  CU(cudaMalloc(&g->diag, sizeof(Diag)));
+  CU(cudaMallocHost(&g->h_diag, sizeof(Diag)));
+  memset(&g->base, 0, sizeof(Diag));
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemsetAsync(g->road, 0, g->nwords * sizeof(U4), st));
+  for (int k = 0; k < 2; k++) {
+    CU(cudaMemsetAsync(g->head[k], 0, g->nwords * sizeof(U4), st));
+    CU(cudaMemsetAsync(g->pref[k], 0, g->nwords * 4, st));
+    CU(cudaMemsetAsync(g->color[k], 0, g->ncells_p * 4, st));
+  }
+  CU(cudaMemsetAsync(g->calc, 0, g->nwords * 4, st));
+  CU(cudaMemsetAsync(g->my, 0, g->nwords * 4, st));
+  CU(cudaMemsetAsync(g->mx, 0, g->nwords * 4, st));
+  CU(cudaMemsetAsync(g->rng, 0, g->ncells_p * 8, st));
+  CU(cudaMemsetAsync(g->fs, 0, sizeof(FixState), st));
+  CU(cudaMemsetAsync(g->diag, 0, sizeof(Diag), st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int flowamok_grid_free(flowamok_context *ctx, flowamok_grid *g) {
+  if (!g) return 0;
+  if (ctx && ctx->device >= 0) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(g->road);
+  for (int k = 0; k < 2; k++) { cudaFree(g->head[k]); cudaFree(g->pref[k]); cudaFree(g->color[k]); cudaFree(g->pend[k]); }
+  cudaFree(g->calc); cudaFree(g->my); cudaFree(g->mx); cudaFree(g->rng); cudaFree(g->fs); cudaFree(g->diag);
+  cudaFree(g->ring_cells); cudaFree(g->ring_off); cudaFree(g->leak_plane);
+  cudaFreeHost(g->h_diag);
+  delete g;
+  return 0;
+}
+
+int flowamok_grid_shape(flowamok_context *ctx, const flowamok_grid *g, int64_t *gh, int64_t *gw) {
+  if (!g) return fail(ctx, "null grid");
+  if (gh) *gh = g->gh;
+  if (gw) *gw = g->gw;
+  return 0;
+}
+
+int flowamok_create_grid(flowamok_context *ctx, flowamok_grid *g, int32_t seed, uint64_t *joined_state, uint64_t *joined_inc) {
+  if (!g) return fail(ctx, "null grid");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  u64 s0, inc;
+  pcg32_from_seed(seed, s0, inc);
+  g->rng_inc = inc;
+  CU(cudaMemsetAsync(g->road, 0, g->nwords * sizeof(U4), st));
+  CU(cudaMemsetAsync(g->head[g->cur], 0, g->nwords * sizeof(U4), st));
+  CU(cudaMemsetAsync(g->pref[g->cur], 0, g->nwords * 4, st));
+  CU(cudaMemsetAsync(g->color[g->cur], 0, g->ncells_p * 4, st));
+  CU(cudaMemsetAsync(g->rng, 0, g->ncells_p * 8, st));
+  long long n = (long long)g->gh * g->gw;
+  k_create<<<nblk(n, 256), 256, 0, st>>>(g->gh, g->gw, g->pitch, g->color[g->cur], g->rng, s0, inc);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(st));
+  if (joined_state || joined_inc) {  // join_rng (utils.fut:17): product of states, OR of incs
+    u64 js = 1;
+    for (long long i = 0; i < n; i++) js *= pcg32_split_state(s0, inc, i);
+    if (joined_state) *joined_state = js;
+    if (joined_inc) *joined_inc = inc;
+  }
+  g->tick = 0;
+  return 0;
+}
+
+int flowamok_grid_upload(flowamok_context *ctx, flowamok_grid *g, const int8_t *uy, const int8_t *ux,
+                         const int8_t *dy, const int8_t *dx, const uint32_t *color, const uint8_t *pref,
+                         const uint64_t *rng_state, uint64_t rng_inc) {
+  if (!g) return fail(ctx, "null grid");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  size_t n = (size_t)g->gh * g->gw;
+  int8_t *tmp = nullptr;
+  CU(cudaMalloc(&tmp, n * 5));
+  const void *src[5] = {uy, ux, dy, dx, pref};
+  int8_t *dptr[5];
+  for (int k = 0; k < 5; k++) {
+    dptr[k] = src[k] ? tmp + n * k : nullptr;
+    if (src[k]) CU(cudaMemcpyAsync(dptr[k], src[k], n, cudaMemcpyHostToDevice, st));
+  }
+  k_pack<<<nblk((long long)g->nwords * 32, 256), 256, 0, st>>>(g->gh, g->gw, g->pitch, dptr[0], dptr[1], dptr[2],
+                                                              dptr[3], (const uint8_t *)dptr[4], g->road,
+                                                              g->head[g->cur], g->pref[g->cur]);
+  CU(cudaGetLastError());
+  size_t cp = (size_t)g->pitch * 32;
+  if (color)
+    CU(cudaMemcpy2DAsync(g->color[g->cur], cp * 4, color, (size_t)g->gw * 4, (size_t)g->gw * 4, g->gh, cudaMemcpyHostToDevice, st));
+  else
+    CU(cudaMemsetAsync(g->color[g->cur], 0xFF, g->ncells_p * 4, st));
+  if (rng_state)
+    CU(cudaMemcpy2DAsync(g->rng, cp * 8, rng_state, (size_t)g->gw * 8, (size_t)g->gw * 8, g->gh, cudaMemcpyHostToDevice, st));
+  else
+    CU(cudaMemsetAsync(g->rng, 0, g->ncells_p * 8, st));
+  g->rng_inc = rng_inc;
+  CU(cudaStreamSynchronize(st));
+  CU(cudaFree(tmp));
+  return 0;
+}
+
+int flowamok_grid_download(flowamok_context *ctx, const flowamok_grid *g, int8_t *uy, int8_t *ux, int8_t *dy,
+                           int8_t *dx, uint32_t *color, uint8_t *pref, uint64_t *rng_state, uint64_t *rng_inc) {
+  if (!g) return fail(ctx, "null grid");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  size_t n = (size_t)g->gh * g->gw;
+  void *dst[5] = {uy, ux, dy, dx, pref};
+  bool any = false;
+  for (int k = 0; k < 5; k++) any |= dst[k] != nullptr;
+  int8_t *tmp = nullptr;
+  if (any) {
+    CU(cudaMalloc(&tmp, n * 5));
+    k_unpack<<<nblk((long long)n, 256), 256, 0, st>>>(g->gh, g->gw, g->pitch, g->road, g->head[g->cur], g->pref[g->cur],
+                                                      uy ? tmp : nullptr, ux ? tmp + n : nullptr, dy ? tmp + 2 * n : nullptr,
+                                                      dx ? tmp + 3 * n : nullptr, pref ? (uint8_t *)(tmp + 4 * n) : nullptr);
+    CU(cudaGetLastError());
+    for (int k = 0; k < 5; k++)
+      if (dst[k]) CU(cudaMemcpyAsync(dst[k], tmp + n * k, n, cudaMemcpyDeviceToHost, st));
+  }
+  size_t cp = (size_t)g->pitch * 32;
+  if (color)
+    CU(cudaMemcpy2DAsync(color, (size_t)g->gw * 4, g->color[g->cur], cp * 4, (size_t)g->gw * 4, g->gh, cudaMemcpyDeviceToHost, st));
+  if (rng_state)
+    CU(cudaMemcpy2DAsync(rng_state, (size_t)g->gw * 8, g->rng, cp * 8, (size_t)g->gw * 8, g->gh, cudaMemcpyDeviceToHost, st));
+  if (rng_inc) *rng_inc = g->rng_inc;
+  CU(cudaStreamSynchronize(st));
+  if (tmp) CU(cudaFree(tmp));
+  return 0;
+}
+
+int flowamok_add_line_vertical(flowamok_context *ctx, flowamok_grid *g, int64_t y0, int64_t y1, int64_t x, int8_t flow) {
+  if (!g) return fail(ctx, "null grid");
+  if (y1 < y0) return 0;  // n <= 0: the reference loop body never runs (utils.fut:21-23)
+  if (y0 < 0 || y1 >= g->gh || x < 0 || x >= g->gw) return fail(ctx, "add_line_vertical: index out of bounds");
+  CU(cudaSetDevice(ctx->device));
+  int n = (int)(y1 - y0 + 1);
+  k_line_v<<<nblk(n, 128), 128, 0, ctx->stream>>>(g->pitch, g->road, (int)y0, n, (int)x, flow);
+  CU(cudaGetLastError());
+  return 0;
+}
+int flowamok_add_line_horizontal(flowamok_context *ctx, flowamok_grid *g, int64_t y, int64_t x0, int64_t x1, int8_t flow) {
+  if (!g) return fail(ctx, "null grid");
+  if (x1 < x0) return 0;
+  if (x0 < 0 || x1 >= g->gw || y < 0 || y >= g->gh) return fail(ctx, "add_line_horizontal: index out of bounds");
+  CU(cudaSetDevice(ctx->device));
+  int nw = (int)((x1 >> 5) - (x0 >> 5) + 1);
+  k_line_h<<<nblk(nw, 128), 128, 0, ctx->stream>>>(g->pitch, g->road, (int)y, (int)x0, (int)x1, flow);
+  CU(cudaGetLastError());
+  return 0;
+}
+int flowamok_add_cell(flowamok_context *ctx, flowamok_grid *g, int64_t y, int64_t x, uint32_t color, int8_t dy, int8_t dx) {
+  if (!g) return fail(ctx, "null grid");
+  if (y < 0 || y >= g->gh || x < 0 || x >= g->gw) return fail(ctx, "add_cell: index out of bounds");
+  CU(cudaSetDevice(ctx->device));
+  k_add_cell<<<1, 1, 0, ctx->stream>>>(g->pitch, g->head[g->cur], g->color[g->cur], (int)y, (int)x, color, dy, dx);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int flowamok_set_chooser(flowamok_context *ctx, flowamok_grid *g, int mode, const uint8_t *tape, int64_t tape_len) {
+  if (!g) return fail(ctx, "null grid");
+  if (mode < 0 || mode > 3) return fail(ctx, "unknown chooser mode %d", mode);
+  if (mode == CHOOSE_TAPE && (!tape || tape_len <= 0)) return fail(ctx, "tape chooser needs a tape");
+  g->chooser = mode;
+  g->tape.clear();
+  if (mode == CHOOSE_TAPE) g->tape.assign(tape, tape + tape_len);
+  g->tick = 0;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cycles
+// ---------------------------------------------------------------------------------------------
+static int install_rings(flowamok_context *ctx, flowamok_grid *g, int64_t n, const int64_t *off, const int64_t *y,
+                         const int64_t *x, const int8_t *cy, const int8_t *cx, const uint8_t *grant) {
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaFree(g->ring_cells)); CU(cudaFree(g->ring_off));
+  g->ring_cells = g->ring_off = nullptr; g->n_rings = 0; g->n_ring_cells = 0; g->ring_stride = 0;
+  g->h_off.clear(); g->h_y.clear(); g->h_x.clear(); g->h_cy.clear(); g->h_cx.clear();
+  if (n <= 0) return 0;
+  int64_t tot = off[n];
+  std::vector<unsigned long long> cells((size_t)tot), offs((size_t)n + 1);
+  for (int64_t k = 0; k <= n; k++) offs[(size_t)k] = (unsigned long long)off[k];
+  for (int64_t t = 0; t < tot; t++) {
+    if (y[t] < 0 || y[t] >= g->gh || x[t] < 0 || x[t] >= g->gw) return fail(ctx, "cycle cell out of bounds");
+    bool single = (cy[t] != 0) != (cx[t] != 0);
+    if (!single) return fail(ctx, "cycle check direction must be single-axis (steppers.fut:239-294)");
+    unsigned int dir = cy[t] < 0 ? 0u : cy[t] > 0 ? 1u : cx[t] < 0 ? 2u : 3u;
+    if (grant[t] != 1 && grant[t] != 2) return fail(ctx, "grant must be 1 (y) or 2 (x)");
+    cells[(size_t)t] = (unsigned long long)((size_t)y[t] * g->pitch + (x[t] >> 5)) | ((unsigned long long)(x[t] & 31) << 32) |
+                       ((unsigned long long)dir << 37) | ((unsigned long long)(grant[t] == 2 ? 1 : 0) << 39);
+  }
+  CU(cudaMalloc(&g->ring_cells, std::max<size_t>(1, (size_t)tot) * 8));
+  CU(cudaMalloc(&g->ring_off, ((size_t)n + 1) * 8));
+  CU(cudaMemcpy(g->ring_cells, cells.data(), (size_t)tot * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(g->ring_off, offs.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice));
+  g->n_rings = n; g->n_ring_cells = tot;
+  g->h_off.assign(off, off + n + 1); g->h_y.assign(y, y + tot); g->h_x.assign(x, x + tot);
+  g->h_cy.assign(cy, cy + tot); g->h_cx.assign(cx, cx + tot);
+  return 0;
+}
+
+int flowamok_set_cycles(flowamok_context *ctx, flowamok_grid *g, int64_t n, const int64_t *off, const int64_t *y,
+                        const int64_t *x, const int8_t *cy, const int8_t *cx, const uint8_t *grant) {
+  if (!g) return fail(ctx, "null grid");
+  return install_rings(ctx, g, n, off, y, x, cy, cx, grant);
+}
+
+// stepper_perfect.find_cycles (steppers.fut:233-300) with sparse path sets instead of dense masks.
+// Same worklist discipline (in-place continuation on the y branch, x branch appended, :281-285), so
+// the surviving cycles come out in the reference's order; nub_2d (:299) keeps the first of equals.
+namespace {
+struct Path {
+  std::vector<int64_t> idx;   // cells in visiting order
+  std::vector<int8_t> cy, cx;
+  std::unordered_set<int64_t> seen;
+  int64_t y, x, ys, xs;
+  void add(int64_t i, int8_t a, int8_t b) { idx.push_back(i); cy.push_back(a); cx.push_back(b); seen.insert(i); }
+};
+}  // namespace
+
+int flowamok_find_cycles(flowamok_context *ctx, flowamok_grid *g, int64_t max_paths, int64_t *n_cycles) {
+  if (!g) return fail(ctx, "null grid");
+  if (max_paths <= 0) max_paths = 1 << 16;
+  const int64_t gh = g->gh, gw = g->gw;
+  std::vector<int8_t> uy((size_t)gh * gw), ux((size_t)gh * gw);
+  if (flowamok_grid_download(ctx, g, uy.data(), ux.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr)) return 1;
+  auto inb = [&](int64_t y, int64_t x) { return y >= 0 && y < gh && x >= 0 && x < gw; };
+  std::vector<Path> ps;
+  for (int64_t y = 0; y < gh; y++)
+    for (int64_t x = 0; x < gw; x++) {
+      int64_t i = y * gw + x;
+      int8_t cy = uy[i], cx = ux[i];
+      if (!(cy != 0 && cx != 0)) continue;
+      int64_t yn = y + cy, xn = x + cx;
+      bool y_ok = inb(yn, x) && uy[yn * gw + x] == cy, x_ok = inb(y, xn) && ux[y * gw + xn] == cx;
+      if (y_ok) { Path p; p.add(i, cy, 0); p.y = yn; p.x = x; p.ys = y; p.xs = x; ps.push_back(std::move(p)); }
+      if (x_ok) { Path p; p.add(i, 0, cx); p.y = y; p.x = xn; p.ys = y; p.xs = x; ps.push_back(std::move(p)); }
+      if ((int64_t)ps.size() > max_paths) return fail(ctx, "find_cycles: more than %lld paths", (long long)max_paths);
+    }
+  size_t cur = 0;
+  while (cur < ps.size()) {
+    Path &p = ps[cur];
+    int64_t y = p.y, x = p.x;
+    if (y == p.ys && x == p.xs) { cur++; continue; }
+    if (!inb(y, x)) { p.y = p.x = -1; cur++; continue; }  // the reference would fault indexing here (:266)
+    int64_t i = y * gw + x;
+    if (p.seen.count(i)) { p.y = p.x = -1; cur++; continue; }
+    int8_t cy = uy[i], cx = ux[i];
+    if (cy != 0 && cx != 0) {
+      int64_t yn = y + cy, xn = x + cx;
+      bool y_ok = inb(yn, x) && uy[yn * gw + x] == cy, x_ok = inb(y, xn) && ux[y * gw + xn] == cx;
+      if (y_ok && x_ok) {
+        if ((int64_t)ps.size() >= max_paths) return fail(ctx, "find_cycles: more than %lld paths", (long long)max_paths);
+        Path b = p;
+        p.add(i, cy, 0); p.y = yn; p.x = x;
+        b.add(i, 0, cx); b.y = y; b.x = xn;
+        ps.push_back(std::move(b));  // may reallocate: p is not used afterwards
+      } else if (y_ok) { p.add(i, cy, 0); p.y = yn; p.x = x; }
+      else { p.add(i, 0, cx); p.y = y; p.x = xn; }
+    } else if (cy != 0 || cx != 0) {
+      p.add(i, cy, cx); p.y = y + cy; p.x = x + cx;
+    } else { p.y = p.x = -1; cur++; }
+  }
+  // keep cycles, drop duplicates (same cell set with the same directions), first occurrence wins
+  struct Canon { std::vector<std::pair<int64_t, int>> v; };
+  std::vector<Canon> canon;
+  std::vector<size_t> keep;
+  for (size_t a = 0; a < ps.size(); a++) {
+    if (ps[a].y == -1) continue;
+    Canon c;
+    for (size_t t = 0; t < ps[a].idx.size(); t++) c.v.push_back({ps[a].idx[t], (ps[a].cy[t] + 1) * 3 + (ps[a].cx[t] + 1)});
+    std::sort(c.v.begin(), c.v.end());
+    bool dup = false;
+    for (auto &o : canon) if (o.v == c.v) { dup = true; break; }
+    if (!dup) { canon.push_back(std::move(c)); keep.push_back(a); }
+  }
+  std::vector<int64_t> off{0}, ry, rx;
+  std::vector<int8_t> rcy, rcx;
+  std::vector<uint8_t> grant;
+  for (size_t a : keep) {
+    const Path &p = ps[a];
+    for (size_t t = 0; t < p.idx.size(); t++) {
+      int64_t i = p.idx[t], y = i / gw, x = i % gw;
+      ry.push_back(y); rx.push_back(x); rcy.push_back(p.cy[t]); rcx.push_back(p.cx[t]);
+      uint8_t gr;
+      if (uy[i] != 0 && ux[i] != 0) {  // steppers.fut:206-209: is the ring cell at y - u.y heading {u.y, 0}?
+        int64_t yp = y - uy[i];
+        bool isy = false;
+        if (inb(yp, x)) {
+          int64_t j = yp * gw + x;
+          for (size_t q = 0; q < p.idx.size(); q++)
+            if (p.idx[q] == j) { isy = p.cy[q] == uy[i] && p.cx[q] == 0; break; }
+        }
+        gr = isy ? 1 : 2;
+      } else gr = uy[i] != 0 ? 1 : 2;
+      grant.push_back(gr);
+    }
+    off.push_back((int64_t)ry.size());
+  }
+  int64_t n = (int64_t)keep.size();
+  if (n_cycles) *n_cycles = n;
+  return install_rings(ctx, g, n, off.data(), ry.data(), rx.data(), rcy.data(), rcx.data(), grant.data());
+}
+
+int flowamok_cycle_count(flowamok_context *ctx, const flowamok_grid *g, int64_t *n_cycles, int64_t *n_cells) {
+  if (!g) return fail(ctx, "null grid");
+  if (n_cycles) *n_cycles = g->n_rings;
+  if (n_cells) *n_cells = g->n_ring_cells;
+  return 0;
+}
+int flowamok_get_cycles_dense(flowamok_context *ctx, const flowamok_grid *g, int8_t *masks) {
+  if (!g) return fail(ctx, "null grid");
+  if (g->n_rings > 0 && g->h_off.empty()) return fail(ctx, "cycle list was generated on the device; dense form unavailable");
+  size_t per = (size_t)g->gh * g->gw * 2;
+  memset(masks, 0, per * (size_t)g->n_rings);
+  for (int64_t k = 0; k < g->n_rings; k++)
+    for (int64_t t = g->h_off[k]; t < g->h_off[k + 1]; t++) {
+      size_t o = per * (size_t)k + ((size_t)g->h_y[t] * g->gw + g->h_x[t]) * 2;
+      masks[o] = g->h_cy[t]; masks[o + 1] = g->h_cx[t];
+    }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stepping
+// ---------------------------------------------------------------------------------------------
+static GridView make_view(flowamok_grid *g) {
+  GridView v;
+  v.gh = g->gh; v.gw = g->gw; v.pitch = g->pitch; v.wvalid = g->wvalid;
+  v.road = g->road;
+  v.head_in = g->head[g->cur]; v.head_out = g->head[g->cur ^ 1];
+  v.pref_in = g->pref[g->cur]; v.pref_out = g->pref[g->cur ^ 1];
+  v.calc = g->calc; v.my = g->my; v.mx = g->mx;
+  v.color_in = g->color[g->cur]; v.color_out = g->color[g->cur ^ 1];
+  v.rng = g->rng; v.rng_inc = g->rng_inc;
+  v.chooser = g->chooser;
+  v.tape_bit = (g->chooser == CHOOSE_TAPE) ? (g->tape[(size_t)(g->tick % (long long)g->tape.size())] != 0) : 0u;
+  return v;
+}
+
+static int enqueue_tick(flowamok_context *ctx, flowamok_grid *g, bool perfect, u32 *leak_plane, cudaEvent_t *ev = nullptr) {
+  cudaStream_t st = ctx->stream;
+  GridView v = make_view(g);
+  int ntiles = g->ntx * g->nty;
+  if (ev) CU(cudaEventRecord(ev[0], st));
+  k_u_first<<<ntiles, U_THREADS, sizeof(UT::Smem), st>>>(v, g->ntx, g->diag, g->fs, g->pend[0]);
+  CU(cudaGetLastError());
+  {
+    int fixb = std::min(ctx->fix_blocks, std::max(1, ntiles));
+    int ntx = g->ntx;
+    void *args[] = {(void *)&v, (void *)&ntx, (void *)&g->diag, (void *)&g->fs, (void *)&g->pend[0], (void *)&g->pend[1]};
+    if (ev) CU(cudaEventRecord(ev[1], st));
+    CU(cudaLaunchCooperativeKernel((void *)k_u_fix, dim3(fixb), dim3(U_THREADS), args, sizeof(UT::Smem), st));
+    if (ev) CU(cudaEventRecord(ev[2], st));
+  }
+  if (perfect && g->n_rings > 0) {
+    k_rings<<<nblk(g->n_rings, 128), 128, 0, st>>>(v, g->ring_cells, g->ring_off, g->n_rings, g->ring_stride);
+    CU(cudaGetLastError());
+  }
+  if (ev) CU(cudaEventRecord(ev[3], st));
+  k_move<<<g->mtx * g->mty, M_THREADS, 0, st>>>(v, g->mtx, g->diag, leak_plane);
+  CU(cudaGetLastError());
+  if (ev) CU(cudaEventRecord(ev[4], st));
+  g->cur ^= 1;
+  g->tick++;
+  return 0;
+}
+
+static int read_diag(flowamok_context *ctx, flowamok_grid *g, Diag *d) {
+  CU(cudaMemcpyAsync(g->h_diag, g->diag, sizeof(Diag), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *d = *g->h_diag;
+  unsigned int err = 0;
+  CU(cudaMemcpy(&err, &g->fs->error, 4, cudaMemcpyDeviceToHost));
+  if (err) return fail(ctx, "grid barrier watchdog tripped in k_u_fix");
+  return 0;
+}
+
+static int step_n(flowamok_context *ctx, flowamok_grid *g, bool perfect, int64_t n_ticks, int64_t *n_leaks) {
+  if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device: flowamok_b200 has no CPU path");
+  if (!g) return fail(ctx, "null grid");
+  CU(cudaSetDevice(ctx->device));
+  unsigned long long before = 0;
+  if (n_leaks) {
+    Diag d;
+    if (read_diag(ctx, g, &d)) return 1;
+    before = d.leaks;
+  }
+  for (int64_t t = 0; t < n_ticks; t++)
+    if (enqueue_tick(ctx, g, perfect, nullptr)) return 1;
+  if (n_leaks) {
+    Diag d;
+    if (read_diag(ctx, g, &d)) return 1;
+    *n_leaks = (int64_t)(d.leaks - before);
+  }
+  return 0;
+}
+
+int flowamok_step_quick(flowamok_context *ctx, flowamok_grid *g, int64_t n_ticks, int64_t *n_leaks) {
+  return step_n(ctx, g, false, n_ticks, n_leaks);
+}
+int flowamok_step_perfect(flowamok_context *ctx, flowamok_grid *g, int64_t n_ticks, int64_t *n_leaks) {
+  return step_n(ctx, g, true, n_ticks, n_leaks);
+}
+
+int flowamok_step_profile(flowamok_context *ctx, flowamok_grid *g, int perfect, int64_t n_ticks, double *ms) {
+  if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
+  if (!g || !ms || n_ticks < 1 || n_ticks > 4096) return fail(ctx, "bad profile arguments");
+  CU(cudaSetDevice(ctx->device));
+  std::vector<cudaEvent_t> ev((size_t)n_ticks * 5);
+  for (auto &e : ev) CU(cudaEventCreate(&e));
+  for (int64_t t = 0; t < n_ticks; t++)
+    if (enqueue_tick(ctx, g, perfect != 0, nullptr, &ev[(size_t)t * 5])) return 1;
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < 4; k++) ms[k] = 0.0;
+  for (int64_t t = 0; t < n_ticks; t++)
+    for (int k = 0; k < 4; k++) {
+      float f = 0.f;
+      CU(cudaEventElapsedTime(&f, ev[(size_t)t * 5 + k], ev[(size_t)t * 5 + k + 1]));
+      ms[k] += f;
+    }
+  for (auto &e : ev) cudaEventDestroy(e);
+  return 0;
+}
+
+int flowamok_step_leaks(flowamok_context *ctx, flowamok_grid *g, int perfect, int64_t cap, int64_t *leaks, int64_t *n_leaks) {
+  if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
+  if (!g) return fail(ctx, "null grid");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (!g->leak_plane) CU(cudaMalloc(&g->leak_plane, g->nwords * 4));
+  int old = g->cur;
+  if (enqueue_tick(ctx, g, perfect != 0, g->leak_plane)) return 1;
+  unsigned int *counts = nullptr, *offs = nullptr;
+  CU(cudaMalloc(&counts, (g->nwords + 1) * 4));
+  CU(cudaMalloc(&offs, (g->nwords + 1) * 4));
+  CU(cudaMemsetAsync(counts, 0, (g->nwords + 1) * 4, st));
+  k_leak_counts<<<nblk((long long)g->nwords, 256), 256, 0, st>>>((long long)g->nwords, g->leak_plane, counts);
+  CU(cudaGetLastError());
+  void *tmp = nullptr;
+  size_t tmpb = 0;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, tmpb, counts, offs, (int)(g->nwords + 1), st));
+  CU(cudaMalloc(&tmp, tmpb));
+  CU(cub::DeviceScan::ExclusiveSum(tmp, tmpb, counts, offs, (int)(g->nwords + 1), st));
+  unsigned int total = 0;
+  CU(cudaMemcpyAsync(&total, offs + g->nwords, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  long long emit = std::min<long long>(total, cap);
+  if (emit > 0 && leaks) {
+    long long *dout = nullptr;
+    CU(cudaMalloc(&dout, (size_t)emit * 64));
+    k_leak_emit<<<nblk((long long)g->nwords, 256), 256, 0, st>>>(g->gh, g->gw, g->pitch, g->leak_plane, offs, g->head[old],
+                                                                g->pref[old], g->color[old], emit, dout);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(leaks, dout, (size_t)emit * 64, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaFree(dout));
+  }
+  if (n_leaks) *n_leaks = total;
+  CU(cudaFree(tmp)); CU(cudaFree(counts)); CU(cudaFree(offs));
+  return 0;
+}
+
+int flowamok_render(flowamok_context *ctx, const flowamok_grid *g, int64_t scale, uint32_t *pixels) {
+  if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
+  if (!g || scale < 1) return fail(ctx, "bad render arguments");
+  CU(cudaSetDevice(ctx->device));
+  long long n = (long long)g->gh * scale * g->gw * scale;
+  u32 *d = nullptr;
+  CU(cudaMalloc(&d, (size_t)n * 4));
+  k_render<<<nblk(n, 256), 256, 0, ctx->stream>>>(g->gh, g->gw, g->pitch, scale, g->road, g->head[g->cur], g->color[g->cur], d);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(pixels, d, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaFree(d));
+  return 0;
+}
+
+int flowamok_stats(flowamok_context *ctx, flowamok_grid *g, int64_t *ticks, int64_t *passes, int64_t *sweeps) {
+  if (!g) return fail(ctx, "null grid");
+  CU(cudaSetDevice(ctx->device));
+  Diag d;
+  if (read_diag(ctx, g, &d)) return 1;
+  if (ticks) *ticks = (int64_t)(d.ticks - g->base.ticks);
+  if (passes) *passes = (int64_t)(d.passes - g->base.passes);
+  if (sweeps) *sweeps = (int64_t)(d.sweeps - g->base.sweeps);
+  g->base = d;
+  return 0;
+}
+
+int flowamok_generate_synthetic(flowamok_context *ctx, flowamok_grid *g, uint64_t seed, uint32_t density16, uint32_t ring_full16) {
+  if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
+  if (!g) return fail(ctx, "null grid");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CU(cudaStreamSynchronize(st));
+  k_synth<<<nblk((long long)g->nwords * 32, 256), 256, 0, st>>>(g->gh, g->gw, g->pitch, seed, density16, ring_full16, g->road,
+                                                               g->head[g->cur], g->pref[g->cur], g->color[g->cur], g->rng);
+  CU(cudaGetLastError());
+  g->rng_inc = (0xda3e39cb94b95bdbULL << 1) | 1ULL;
+  CU(cudaFree(g->ring_cells)); CU(cudaFree(g->ring_off));
+  g->ring_cells = g->ring_off = nullptr; g->n_rings = g->n_ring_cells = 0; g->ring_stride = 0;
+  g->h_off.clear(); g->h_y.clear(); g->h_x.clear(); g->h_cy.clear(); g->h_cx.clear();
+  int nby = g->gh >= 15 ? (g->gh - 15) / 16 + 1 : 0, nbx = g->gw >= 23 ? (g->gw - 23) / 16 + 1 : 0;
+  if (nby > 0 && nbx > 0) {
+    unsigned int *cnt = nullptr;
+    CU(cudaMalloc(&cnt, 4));
+    CU(cudaMemsetAsync(cnt, 0, 4, st));
+    CU(cudaMalloc(&g->ring_cells, (size_t)nby * nbx * 48 * 8));
+    k_synth_rings<<<nblk((long long)nby * nbx, 128), 128, 0, st>>>(g->gh, g->gw, g->pitch, seed, nby, nbx, g->ring_cells, cnt);
+    CU(cudaGetLastError());
+    unsigned int n = 0;
+    CU(cudaMemcpyAsync(&n, cnt, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(cudaFree(cnt));
+    g->n_rings = n; g->n_ring_cells = (long long)n * 48; g->ring_stride = 48;
+  }
+  CU(cudaStreamSynchronize(st));
+  g->tick = 0;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,476 @@
+// flowamok_b200 -- CUDA kernels (sm_100a) of the per-tick grid update.
+//
+// Kernel list (one tick = k_u_first, k_u_fix, [k_rings], k_move):
+//   k_u_first : one CTA per U tile, local least fixpoint of update_can_be_moved_to_from
+//               (steppers.fut:9-56, :147-164) on bit planes staged in shared memory; tiles whose
+//               waiting chains leave their halo are queued.
+//   k_u_fix   : cooperative persistent kernel; iterates the queued tiles under a grid-wide barrier
+//               and a device-side changed/pending flag until the global fixpoint -- no host round
+//               trip per iteration.  Returns immediately when nothing was queued.
+//   k_rings   : resolve_cycles (steppers.fut:189-224) on the sparse ring list, one thread per ring.
+//   k_move    : move_cell + reset_cells (steppers.fut:58-145): new car planes, colour payload
+//               gather with 128-bit accesses, per-cell pcg32 draws at forks, leak count.
+// plus packing / unpacking / generator / render helpers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "fa_tiles.h"
+
+namespace fa {
+
+// production tile shapes (tests/emul variant 0 uses the same)
+typedef UTile<48, 32, 4> UT;
+typedef MTile<16, 32> MT;
+constexpr int U_THREADS = 512;
+constexpr int M_THREADS = 512;
+
+struct FixState {
+  unsigned int npend[2];    // queue lengths (ping-pong)
+  unsigned int changed[2];  // progress flags (ping-pong)
+  unsigned int bar[2];      // grid barrier: arrivals, generation
+  unsigned int error;       // barrier watchdog tripped
+  unsigned int pad;
+};
+
+struct Diag {
+  unsigned long long leaks;    // summed cell leaks
+  unsigned long long passes;   // fixpoint passes (1 per tick + extra rounds)
+  unsigned long long sweeps;   // local relaxation sweeps over all tiles
+  unsigned long long ticks;
+};
+
+// ---------------------------------------------------------------------------------------------
+// U tile driver shared by both fixpoint kernels
+// ---------------------------------------------------------------------------------------------
+template <bool FIRST>
+__device__ __forceinline__ void run_u_tile(const GridView &g, UT::Smem &s, int tile_id, int ntx, Diag *diag,
+                                           unsigned int *pend_out, unsigned int *npend_out,
+                                           unsigned int *changed_out) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  UT t(g, s, tile_id / ntx, tile_id % ntx, FIRST);
+  t.p0(tid, nt);
+  __syncthreads();
+  t.p1(tid, nt);
+  __syncthreads();
+  t.p2(tid, nt);
+  __syncthreads();
+  unsigned int sweeps = 0;
+  for (;;) {
+    bool ch = t.p3(tid, nt);
+    sweeps++;
+    if (!__syncthreads_or(ch)) break;
+  }
+  int res = t.p4(tid, nt);
+  int unready = __syncthreads_or(res & 1);
+  int differs = FIRST ? 0 : __syncthreads_or(res & 2);
+  int pending = 0;
+  if (unready) {
+    t.p5a(tid, nt);
+    __syncthreads();
+    for (;;) {
+      bool ch = t.p5b(tid, nt);
+      if (!__syncthreads_or(ch)) break;
+    }
+    pending = __syncthreads_or(t.p5c(tid, nt));
+  }
+  if (tid == 0) {
+    if (pending) pend_out[atomicAdd(npend_out, 1u)] = (unsigned int)tile_id;
+    if (differs) atomicExch(changed_out, 1u);
+    atomicAdd(&diag->sweeps, (unsigned long long)sweeps);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(U_THREADS, 2)
+k_u_first(const __grid_constant__ GridView g, int ntx, Diag *diag, FixState *fs, unsigned int *pend0) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  UT::Smem &s = *reinterpret_cast<UT::Smem *>(smem_raw);
+  run_u_tile<true>(g, s, blockIdx.x, ntx, diag, pend0, &fs->npend[0], &fs->changed[0]);
+}
+
+// Sense-reversing grid barrier; co-residency is guaranteed by the cooperative launch.  A watchdog
+// turns a would-be hang into an error flag.
+__device__ __forceinline__ bool grid_barrier(FixState *fs, unsigned int nblocks) {
+  __shared__ int ok;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ok = 1;
+    volatile unsigned int *vgen = &fs->bar[1];
+    unsigned int gen = *vgen;
+    __threadfence();
+    unsigned int prev = atomicAdd(&fs->bar[0], 1u);
+    if (prev == nblocks - 1) {
+      atomicExch(&fs->bar[0], 0u);
+      __threadfence();
+      atomicAdd(&fs->bar[1], 1u);
+    } else {
+      long long spins = 0;
+      while (*vgen == gen) {
+        if (++spins > (1LL << 25)) { atomicExch(&fs->error, 1u); ok = 0; break; }
+        __nanosleep(200);
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  return ok != 0;
+}
+
+__global__ void __launch_bounds__(U_THREADS, 2)
+k_u_fix(const __grid_constant__ GridView g, int ntx, Diag *diag, FixState *fs, unsigned int *pend0,
+        unsigned int *pend1) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  UT::Smem &s = *reinterpret_cast<UT::Smem *>(smem_raw);
+  volatile FixState *vfs = fs;
+  unsigned int *lists[2] = {pend0, pend1};
+  int in = 0;
+  unsigned long long extra = 0;
+  for (;;) {
+    unsigned int n = vfs->npend[in];
+    if (n == 0) break;
+    const int out = in ^ 1;
+    for (unsigned int t = blockIdx.x; t < n; t += gridDim.x)
+      run_u_tile<false>(g, s, (int)lists[in][t], ntx, diag, lists[out], &fs->npend[out], &fs->changed[out]);
+    extra++;
+    if (!grid_barrier(fs, gridDim.x)) return;
+    unsigned int ch = vfs->changed[out];
+    if (!grid_barrier(fs, gridDim.x)) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      fs->npend[in] = 0;
+      fs->changed[in] = 0;
+      if (!ch) { fs->npend[out] = 0; fs->changed[out] = 0; }
+      __threadfence();
+    }
+    if (!grid_barrier(fs, gridDim.x)) return;
+    if (!ch) break;  // a whole pass without progress: global fixpoint (cars queued behind a full ring)
+    in = out;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    // nobody reads the flags outside a round; leave them clean for the next tick
+    fs->npend[0] = 0; fs->npend[1] = 0; fs->changed[0] = 0; fs->changed[1] = 0;
+    atomicAdd(&diag->passes, 1ull + extra);
+    atomicAdd(&diag->ticks, 1ull);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// resolve_cycles on sparse rings (steppers.fut:189-224; disjointness argument SURVEY 8a-R)
+// ring cell encoding: [31:0] plane word index, [36:32] bit, [38:37] check direction
+// (0 N, 1 S, 2 W, 3 E), [39] grant (0: direction.y, 1: direction.x)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool ring_cell_ok(const GridView &g, unsigned long long e) {
+  unsigned int wi = (unsigned int)e, bit = 1u << ((e >> 32) & 31u), dir = (unsigned int)(e >> 37) & 3u;
+  if (g.calc[wi] & bit) return false;
+  U4 h = g.head_in[wi];
+  bool dyn = h.x & bit, dys = h.y & bit, dxn = h.z & bit, dxs = h.w & bit;
+  switch (dir) {
+  case 0: return dyn && dys && !dxn;
+  case 1: return dyn && !dys && !dxn;
+  case 2: return dxn && dxs && !dyn;
+  default: return dxn && !dxs && !dyn;
+  }
+}
+__global__ void k_rings(const __grid_constant__ GridView g, const unsigned long long *cells,
+                        const unsigned long long *off, long long n, int stride) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  unsigned long long b = off ? off[k] : (unsigned long long)k * stride;
+  unsigned long long e = off ? off[k + 1] : b + stride;
+  for (unsigned long long t = b; t < e; t++)
+    if (!ring_cell_ok(g, cells[t])) return;
+  for (unsigned long long t = b; t < e; t++) {
+    unsigned long long c = cells[t];
+    unsigned int wi = (unsigned int)c, bit = 1u << ((c >> 32) & 31u);
+    atomicOr(((c >> 39) & 1ull) ? &g.mx[wi] : &g.my[wi], bit);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// move + reset
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(M_THREADS, 2)
+k_move(const __grid_constant__ GridView g, int mtx, Diag *diag, unsigned int *leak_plane) {
+  __shared__ MT::Smem s;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  MT t(g, s, blockIdx.x / mtx, blockIdx.x % mtx);
+  t.p0(tid, nt);
+  __syncthreads();
+  t.p1(tid, nt, leak_plane);
+  __syncthreads();
+  t.p2(tid, nt);
+  if (tid == 0 && s.leaks) atomicAdd(&diag->leaks, (unsigned long long)s.leaks);
+}
+
+// ---------------------------------------------------------------------------------------------
+// packing helpers: one warp builds one plane word with __ballot_sync
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pack(int gh, int gw, int pitch, const int8_t *uy, const int8_t *ux, const int8_t *dy,
+                       const int8_t *dx, const uint8_t *pref, U4 *road, U4 *head, u32 *prefp) {
+  long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  long long nwords = (long long)gh * pitch;
+  if (warp >= nwords) return;
+  int y = (int)(warp / pitch), w = (int)(warp % pitch);
+  int x = w * 32 + lane;
+  bool in = x < gw;
+  size_t i = (size_t)y * gw + x;
+  int vuy = (in && uy) ? uy[i] : 0, vux = (in && ux) ? ux[i] : 0;
+  int vdy = (in && dy) ? dy[i] : 0, vdx = (in && dx) ? dx[i] : 0;
+  int vp = (in && pref) ? pref[i] : 0;
+  U4 r, h;
+  r.x = __ballot_sync(0xFFFFFFFFu, vuy != 0); r.y = __ballot_sync(0xFFFFFFFFu, vuy < 0);
+  r.z = __ballot_sync(0xFFFFFFFFu, vux != 0); r.w = __ballot_sync(0xFFFFFFFFu, vux < 0);
+  h.x = __ballot_sync(0xFFFFFFFFu, vdy != 0); h.y = __ballot_sync(0xFFFFFFFFu, vdy < 0);
+  h.z = __ballot_sync(0xFFFFFFFFu, vdx != 0); h.w = __ballot_sync(0xFFFFFFFFu, vdx < 0);
+  u32 p = __ballot_sync(0xFFFFFFFFu, vp != 0);
+  if (lane == 0) {
+    if (road) road[warp] = r;
+    if (head) head[warp] = h;
+    if (prefp) prefp[warp] = p;
+  }
+}
+
+__global__ void k_unpack(int gh, int gw, int pitch, const U4 *road, const U4 *head, const u32 *prefp, int8_t *uy,
+                         int8_t *ux, int8_t *dy, int8_t *dx, uint8_t *pref) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)gh * gw) return;
+  int y = (int)(i / gw), x = (int)(i % gw);
+  size_t o = (size_t)y * pitch + (x >> 5);
+  u32 bit = 1u << (x & 31);
+  U4 r = road[o], h = head[o];
+  if (uy) uy[i] = (r.x & bit) ? ((r.y & bit) ? -1 : 1) : 0;
+  if (ux) ux[i] = (r.z & bit) ? ((r.w & bit) ? -1 : 1) : 0;
+  if (dy) dy[i] = (h.x & bit) ? ((h.y & bit) ? -1 : 1) : 0;
+  if (dx) dx[i] = (h.z & bit) ? ((h.w & bit) ? -1 : 1) : 0;
+  if (pref) pref[i] = (prefp[o] & bit) ? 1 : 0;
+}
+
+// create_grid (utils.fut:7-17): white, empty; rng_i = split_rng element i
+__global__ void k_create(int gh, int gw, int pitch, u32 *color, u64 *rng, u64 state0, u64 inc) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)gh * gw) return;
+  int y = (int)(i / gw), x = (int)(i % gw);
+  size_t c = (size_t)y * pitch * 32 + x;
+  color[c] = 0xFFFFFFFFu;
+  rng[c] = pcg32_split_state(state0, inc, i);
+}
+
+// point edits (utils.fut:19-38)
+__global__ void k_line_v(int pitch, U4 *road, int y0, int n, int x, int flow) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  size_t o = (size_t)(y0 + k) * pitch + (x >> 5);
+  u32 bit = 1u << (x & 31);
+  // distinct rows -> distinct words, but other columns of the word may be edited concurrently: atomics
+  if (flow != 0) atomicOr(&road[o].x, bit); else atomicAnd(&road[o].x, ~bit);
+  if (flow < 0) atomicOr(&road[o].y, bit); else atomicAnd(&road[o].y, ~bit);
+}
+__global__ void k_line_h(int pitch, U4 *road, int y, int x0, int x1, int flow) {
+  int w = (x0 >> 5) + blockIdx.x * blockDim.x + threadIdx.x;
+  if (w > (x1 >> 5)) return;
+  int lo = max(x0, w * 32) - w * 32, hi = min(x1, w * 32 + 31) - w * 32;
+  u32 m = (hi == 31 ? 0xFFFFFFFFu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+  size_t o = (size_t)y * pitch + w;
+  if (flow != 0) road[o].z |= m; else road[o].z &= ~m;
+  if (flow < 0) road[o].w |= m; else road[o].w &= ~m;
+}
+__global__ void k_add_cell(int pitch, U4 *head, u32 *color, int y, int x, u32 col, int dy, int dx) {
+  size_t o = (size_t)y * pitch + (x >> 5);
+  u32 bit = 1u << (x & 31);
+  U4 h = head[o];
+  h.x = dy != 0 ? (h.x | bit) : (h.x & ~bit); h.y = dy < 0 ? (h.y | bit) : (h.y & ~bit);
+  h.z = dx != 0 ? (h.z | bit) : (h.z & ~bit); h.w = dx < 0 ? (h.w | bit) : (h.w & ~bit);
+  head[o] = h;
+  color[(size_t)y * pitch * 32 + x] = col;
+}
+
+// ---------------------------------------------------------------------------------------------
+// synthetic road network: monotone avenue lattice + ring tiles.  One warp per word.
+// The same rule is restated independently in tests/synth_ref.py.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline u64 synth_hash(u64 seed, u64 tag, u64 a, u64 b) {
+  u64 k = splitmix64(seed ^ (tag * 0xD6E8FEB86659FD93ULL));
+  k = splitmix64(k ^ a);
+  return splitmix64(k ^ b);
+}
+struct SynthCell {
+  int uy, ux, dy, dx;
+  u32 color;
+  u64 rng;
+};
+__host__ __device__ inline SynthCell synth_cell(int gh, int gw, int y, int x, u64 seed, u32 density16, u32 ring_full16) {
+  SynthCell c = {0, 0, 0, 0, 0xFFFFFFFFu, 0};
+  u64 hc = synth_hash(seed, 2, (u64)y, (u64)x);
+  bool car_draw = (u32)(hc & 0xFFFFu) < density16;
+  bool arow = (y % 16) == 0, acol = (x % 16) == 8;
+  if (arow) c.ux = 1;
+  if (acol) c.uy = 1;
+  if (arow || acol) {
+    if (car_draw) {
+      bool alongx = arow && (!acol || ((hc >> 16) & 1));
+      if (alongx) c.dx = 1; else c.dy = 1;
+    }
+  } else if (y >= 2 && x >= 10) {
+    int by = (y - 2) / 16, bx = (x - 10) / 16;
+    int ly = (y - 2) - by * 16, lx = (x - 10) - bx * 16;
+    bool fits = (16 * by + 14 <= gh - 1) && (16 * bx + 22 <= gw - 1);
+    if (fits && ly <= 12 && lx <= 12 && (ly == 0 || ly == 12 || lx == 0 || lx == 12)) {
+      u64 hb = synth_hash(seed, 1, (u64)by, (u64)bx);
+      if (hb & 1) {
+        bool cw = (hb >> 1) & 1;
+        bool full = (u32)((hb >> 8) & 15u) < ring_full16;
+        int s = cw ? 1 : -1;  // cw: top row +x, right col +y, bottom row -x, left col -y
+        if (ly == 0) c.ux = s;
+        if (ly == 12) c.ux = -s;
+        if (lx == 12) c.uy = s;
+        if (lx == 0) c.uy = -s;
+        if (full || car_draw) {
+          // heading = outgoing travel direction (as explorer/scenarios.fut:121-125 places them)
+          int hy = 0, hx = 0;
+          if (cw) {
+            if (ly == 0 && lx < 12) hx = 1; else if (lx == 12 && ly < 12) hy = 1;
+            else if (ly == 12 && lx > 0) hx = -1; else hy = -1;
+          } else {
+            if (ly == 0 && lx > 0) hx = -1; else if (lx == 0 && ly < 12) hy = 1;
+            else if (ly == 12 && lx < 12) hx = 1; else hy = -1;
+          }
+          c.dy = hy; c.dx = hx;
+        }
+      }
+    }
+  }
+  if (c.dy != 0 || c.dx != 0) c.color = 0xFF000000u | (u32)(synth_hash(seed, 3, (u64)y, (u64)x) & 0xFFFFFFu);
+  c.rng = synth_hash(seed, 4, (u64)y, (u64)x);
+  return c;
+}
+__global__ void k_synth(int gh, int gw, int pitch, u64 seed, u32 density16, u32 ring_full16, U4 *road, U4 *head,
+                        u32 *prefp, u32 *color, u64 *rng) {
+  long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= (long long)gh * pitch) return;
+  int y = (int)(warp / pitch), w = (int)(warp % pitch), x = w * 32 + lane;
+  SynthCell c = {0, 0, 0, 0, 0, 0};
+  if (x < gw) c = synth_cell(gh, gw, y, x, seed, density16, ring_full16);
+  U4 r, h;
+  r.x = __ballot_sync(0xFFFFFFFFu, c.uy != 0); r.y = __ballot_sync(0xFFFFFFFFu, c.uy < 0);
+  r.z = __ballot_sync(0xFFFFFFFFu, c.ux != 0); r.w = __ballot_sync(0xFFFFFFFFu, c.ux < 0);
+  h.x = __ballot_sync(0xFFFFFFFFu, c.dy != 0); h.y = __ballot_sync(0xFFFFFFFFu, c.dy < 0);
+  h.z = __ballot_sync(0xFFFFFFFFu, c.dx != 0); h.w = __ballot_sync(0xFFFFFFFFu, c.dx < 0);
+  if (lane == 0) { road[warp] = r; head[warp] = h; prefp[warp] = 0; }
+  size_t ci = (size_t)y * pitch * 32 + x;
+  color[ci] = c.color;   // pad cells get 0
+  rng[ci] = c.rng;
+}
+// analytic ring list of the generator: every ring has exactly 48 cells
+__global__ void k_synth_rings(int gh, int gw, int pitch, u64 seed, int nby, int nbx, unsigned long long *cells,
+                              unsigned int *nrings) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nby * nbx) return;
+  int by = b / nbx, bx = b % nbx;
+  if (!((16 * by + 14 <= gh - 1) && (16 * bx + 22 <= gw - 1))) return;
+  u64 hb = synth_hash(seed, 1, (u64)by, (u64)bx);
+  if (!(hb & 1)) return;
+  bool cw = (hb >> 1) & 1;
+  unsigned int slot = atomicAdd(nrings, 1u);
+  unsigned long long *out = cells + (size_t)slot * 48;
+  int n = 0;
+  for (int ly = 0; ly <= 12; ly++)
+    for (int lx = 0; lx <= 12; lx++) {
+      if (!(ly == 0 || ly == 12 || lx == 0 || lx == 12)) continue;
+      int y = 16 * by + 2 + ly, x = 16 * bx + 10 + lx;
+      int hy = 0, hx = 0;
+      if (cw) {
+        if (ly == 0 && lx < 12) hx = 1; else if (lx == 12 && ly < 12) hy = 1;
+        else if (ly == 12 && lx > 0) hx = -1; else hy = -1;
+      } else {
+        if (ly == 0 && lx > 0) hx = -1; else if (lx == 0 && ly < 12) hy = 1;
+        else if (ly == 12 && lx < 12) hx = 1; else hy = -1;
+      }
+      // grant (steppers.fut:206-211): a corner is entered along the axis it does NOT leave on
+      bool corner = (ly == 0 || ly == 12) && (lx == 0 || lx == 12);
+      bool grant_x = corner ? (hy != 0) : (hx != 0);
+      unsigned int dir = hy < 0 ? 0u : hy > 0 ? 1u : hx < 0 ? 2u : 3u;
+      unsigned long long e = (unsigned long long)((size_t)y * pitch + (x >> 5)) | ((unsigned long long)(x & 31) << 32) |
+                             ((unsigned long long)dir << 37) | ((unsigned long long)(grant_x ? 1 : 0) << 39);
+      out[n++] = e;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// render (flowamok.fut:16-64); matte gray/mix restated from memory (unpinned)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 d_from_rgba(float r, float g, float b, float a) {
+  u32 R = (u32)__fmul_rn(fminf(1.0f, fmaxf(0.0f, r)), 255.0f), G = (u32)__fmul_rn(fminf(1.0f, fmaxf(0.0f, g)), 255.0f);
+  u32 B = (u32)__fmul_rn(fminf(1.0f, fmaxf(0.0f, b)), 255.0f), A = (u32)__fmul_rn(fminf(1.0f, fmaxf(0.0f, a)), 255.0f);
+  return (A << 24) | (R << 16) | (G << 8) | B;
+}
+__device__ __forceinline__ float d_mix_ch(float w1, float c1, float w2, float c2) {
+  return sqrtf(__fadd_rn(__fmul_rn(__fmul_rn(w1, c1), c1), __fmul_rn(__fmul_rn(w2, c2), c2)));
+}
+__device__ __forceinline__ u32 d_mix(float m1, u32 c1, float m2, u32 c2) {
+  float r1 = __fdiv_rn((float)((c1 >> 16) & 255u), 255.0f), g1 = __fdiv_rn((float)((c1 >> 8) & 255u), 255.0f);
+  float b1 = __fdiv_rn((float)(c1 & 255u), 255.0f), a1 = __fdiv_rn((float)(c1 >> 24), 255.0f);
+  float r2 = __fdiv_rn((float)((c2 >> 16) & 255u), 255.0f), g2 = __fdiv_rn((float)((c2 >> 8) & 255u), 255.0f);
+  float b2 = __fdiv_rn((float)(c2 & 255u), 255.0f), a2 = __fdiv_rn((float)(c2 >> 24), 255.0f);
+  float m12 = __fadd_rn(m1, m2), w1 = __fdiv_rn(m1, m12), w2 = __fdiv_rn(m2, m12);
+  float a = __fdiv_rn(__fadd_rn(__fmul_rn(m1, a1), __fmul_rn(m2, a2)), m12);
+  return d_from_rgba(d_mix_ch(w1, r1, w2, r2), d_mix_ch(w1, g1, w2, g2), d_mix_ch(w1, b1, w2, b2), a);
+}
+__global__ void k_render(int gh, int gw, int pitch, long long scale, const U4 *road, const U4 *head,
+                         const u32 *color, u32 *pixels) {
+  long long h = gh * scale, w = gw * scale;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= h * w) return;
+  long long y = i / w, x = i % w;
+  int yg = (int)(y / scale), xg = (int)(x / scale);
+  size_t o = (size_t)yg * pitch + (xg >> 5);
+  u32 bit = 1u << (xg & 31);
+  U4 r = road[o], hd = head[o];
+  int fy = (r.x & bit) ? ((r.y & bit) ? -1 : 1) : 0, fx = (r.z & bit) ? ((r.w & bit) ? -1 : 1) : 0;
+  bool occupied = ((hd.x | hd.z) & bit) != 0;
+  u32 px = 0xFF000000u;
+  if (fy != 0 || fx != 0) {
+    u32 base = occupied ? color[(size_t)yg * pitch * 32 + xg] : 0xFFFFFFFFu;
+    long long yi = y % scale, xi = x % scale;
+    long long d2 = scale / 2, m2 = scale % 2;
+    long long yy = yi - d2, xx = xi - d2;
+    if (m2 == 0) { yy += (yy >= 0); xx += (xx >= 0); }
+    long long d = d2 - m2;
+    long long ya = yy < 0 ? -yy : yy, xa = xx < 0 ? -xx : xx;
+    bool y_draw = (fy * yy == d - xa) && xa <= d, x_draw = (fx * xx == d - ya) && ya <= d;
+    bool draw = (fx == 0 && y_draw) || (fy == 0 && x_draw) || (fy != 0 && fx != 0 && (y_draw || x_draw));
+    const u32 grey = d_from_rgba(0.3f, 0.3f, 0.3f, 1.0f);
+    px = draw ? (occupied ? d_mix(0.5f, grey, 0.5f, base) : grey) : base;
+  }
+  pixels[i] = px;
+}
+
+// leak list compaction helpers (flowamok_step_leaks)
+__global__ void k_leak_counts(long long nwords, const u32 *leak_plane, unsigned int *counts) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nwords) counts[i] = __popc(leak_plane[i]);
+}
+__global__ void k_leak_emit(int gh, int gw, int pitch, const u32 *leak_plane, const unsigned int *offs,
+                            const U4 *head_old, const u32 *pref_old, const u32 *color_old, long long cap,
+                            long long *out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)gh * pitch) return;
+  u32 m = leak_plane[i];
+  long long k = offs[i];
+  int y = (int)(i / pitch), w = (int)(i % pitch);
+  U4 h = head_old[i];
+  u32 pr = pref_old[i];
+  while (m && k < cap) {
+    int b = __ffs(m) - 1;
+    m &= m - 1;
+    u32 bit = 1u << b;
+    int x = w * 32 + b;
+    int dy = (h.x & bit) ? ((h.y & bit) ? -1 : 1) : 0, dx = (h.z & bit) ? ((h.w & bit) ? -1 : 1) : 0;
+    long long *o = out + k * 8;
+    o[0] = y + dy; o[1] = x + dx; o[2] = y; o[3] = x; o[4] = dy; o[5] = dx;
+    o[6] = color_old[(size_t)y * pitch * 32 + x]; o[7] = (pr & bit) ? 1 : 0;
+    k++;
+  }
+}
+
+}  // namespace fa

@@ -1,0 +1,120 @@
+/*
+ * flowamok_b200 -- C ABI of the B200-native per-tick grid update of nqpz/flowamok.
+ *
+ * Two layers, both plain C (pointers and sizes only, no torch / C++ types):
+ *
+ *  1. flowamok_*  : the OPERATOR surface.  One entry point per reference operator on the hot path
+ *                   (SURVEY.md 8b "inner" boundary); citations are /root/reference/<file>:<line>.
+ *  2. futhark_*   : the surface the Futhark compiler emits for README.fut's two entry points
+ *                   (`init`, `step`, README.fut:12-13), so a frontend written against the generated
+ *                   library links against this one unchanged (SURVEY.md 8b "outer" boundary).
+ *                   Declared in include/flowamok_futhark.h.
+ *
+ * Conventions (same as a Futhark-generated library): every function returns 0 on success and
+ * non-zero on failure; the message is available from flowamok_context_get_error (malloc'd, caller
+ * frees).  Handles are opaque; grids live in device memory (B200 HBM) between calls, exactly like
+ * Futhark's opaque values on its GPU backends.  A context is single-threaded.  Work is enqueued on
+ * the context's CUDA stream; results are valid after flowamok_context_sync or any call documented
+ * as synchronous.  There is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef FLOWAMOK_H
+#define FLOWAMOK_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct flowamok_context flowamok_context;
+typedef struct flowamok_grid flowamok_grid;
+
+/* choose_direction parameter of both steppers (src/steppers.fut:180, :305) */
+enum flowamok_chooser {
+  FLOWAMOK_CHOOSE_RANDOM = 0, /* flowamok.fut:10-14 choose_direction_random (per-cell pcg32, src/random.fut:4-5) */
+  FLOWAMOK_CHOOSE_Y = 1,      /* always {y = u.y, x = 0} */
+  FLOWAMOK_CHOOSE_X = 2,      /* always {y = 0, x = u.x} */
+  FLOWAMOK_CHOOSE_TAPE = 3    /* every draw of tick t returns tape[t % tape_len] (README GIF replay) */
+};
+
+/* ---- context (replaces futhark_context_config_new / futhark_context_new / _free / _sync / _get_error) ---- */
+/* device < 0: current device.  stream: a cudaStream_t to enqueue on, or NULL for a private stream. */
+int flowamok_context_new(flowamok_context **out, int device, void *stream);
+int flowamok_context_free(flowamok_context *ctx);
+int flowamok_context_sync(flowamok_context *ctx);
+char *flowamok_context_get_error(flowamok_context *ctx);
+int flowamok_context_device(flowamok_context *ctx);
+
+/* ---- grid values: `[gh][gw](cell ())` of src/model.fut:19-24 as an opaque device value ---- */
+int flowamok_grid_new(flowamok_context *ctx, flowamok_grid **out, int64_t gh, int64_t gw);
+int flowamok_grid_free(flowamok_context *ctx, flowamok_grid *g);
+int flowamok_grid_shape(flowamok_context *ctx, const flowamok_grid *g, int64_t *gh, int64_t *gw);
+
+/* create_grid (src/utils.fut:14-17): every cell white, empty, no road, rng_i = split_rng(gh*gw, rng_from_seed [seed])[i].
+ * joined_state/joined_inc (may be NULL) receive join_rng of the per-cell rngs (utils.fut:17).  Synchronous. */
+int flowamok_create_grid(flowamok_context *ctx, flowamok_grid *g, int32_t seed, uint64_t *joined_state, uint64_t *joined_inc);
+
+/* Host arrays in the reference's record-of-arrays layout, row-major [gh][gw].  Any pointer may be
+ * NULL: on upload the field is zeroed (colour: white, rng: state 0); on download it is skipped.
+ * The per-tick fields calculated/direction.{y,x} are always false between ticks (steppers.fut:140-145)
+ * and are therefore not part of the value.  rng_inc is shared by all cells (utils.fut:15).  Synchronous. */
+int flowamok_grid_upload(flowamok_context *ctx, flowamok_grid *g, const int8_t *uy, const int8_t *ux,
+                         const int8_t *dy, const int8_t *dx, const uint32_t *color, const uint8_t *pref,
+                         const uint64_t *rng_state, uint64_t rng_inc);
+int flowamok_grid_download(flowamok_context *ctx, const flowamok_grid *g, int8_t *uy, int8_t *ux, int8_t *dy,
+                           int8_t *dx, uint32_t *color, uint8_t *pref, uint64_t *rng_state, uint64_t *rng_inc);
+
+/* point edits between ticks: src/utils.fut:19-25, :27-33, :35-38 */
+int flowamok_add_line_vertical(flowamok_context *ctx, flowamok_grid *g, int64_t y_start, int64_t y_end, int64_t x, int8_t flow);
+int flowamok_add_line_horizontal(flowamok_context *ctx, flowamok_grid *g, int64_t y, int64_t x_start, int64_t x_end, int8_t flow);
+int flowamok_add_cell(flowamok_context *ctx, flowamok_grid *g, int64_t y, int64_t x, uint32_t color, int8_t dy, int8_t dx);
+
+/* chooser: tape (host bytes, copied) only for FLOWAMOK_CHOOSE_TAPE */
+int flowamok_set_chooser(flowamok_context *ctx, flowamok_grid *g, int mode, const uint8_t *tape, int64_t tape_len);
+
+/* cycle_checks of stepper_perfect.step (src/steppers.fut:305) in sparse form: ring k is the cells
+ * [off[k], off[k+1]) with position (y,x), check direction (cy,cx) and grant (1: direction.y, 2: direction.x,
+ * i.e. the outcome of steppers.fut:206-211 for that cell).  Host arrays, copied.  n = 0 clears. */
+int flowamok_set_cycles(flowamok_context *ctx, flowamok_grid *g, int64_t n, const int64_t *off, const int64_t *y,
+                        const int64_t *x, const int8_t *cy, const int8_t *cx, const uint8_t *grant);
+/* stepper_perfect.find_cycles (src/steppers.fut:233-300) on the grid's roads; stores the result as
+ * the grid's cycle_checks and returns how many were found.  max_paths bounds the worklist (0: default). */
+int flowamok_find_cycles(flowamok_context *ctx, flowamok_grid *g, int64_t max_paths, int64_t *n_cycles);
+int flowamok_cycle_count(flowamok_context *ctx, const flowamok_grid *g, int64_t *n_cycles, int64_t *n_cells);
+/* dense masks [n][gh][gw][2] (y,x) as the reference returns them; n from flowamok_cycle_count */
+int flowamok_get_cycles_dense(flowamok_context *ctx, const flowamok_grid *g, int8_t *masks);
+
+/* stepper_quick.step (src/steppers.fut:177-185) / stepper_perfect.step (:302-312), n_ticks times, the
+ * grid being consumed and replaced like the reference's unique `*[gh][gw]` argument.  Enqueues only;
+ * if n_leaks is non-NULL the call synchronises and stores the summed number of cell leaks
+ * (explorer/explorer.fut:125). */
+int flowamok_step_quick(flowamok_context *ctx, flowamok_grid *g, int64_t n_ticks, int64_t *n_leaks);
+int flowamok_step_perfect(flowamok_context *ctx, flowamok_grid *g, int64_t n_ticks, int64_t *n_leaks);
+
+/* Like flowamok_step_*, but brackets every kernel of every tick with CUDA events on the context's stream
+ * and returns the summed device time in milliseconds of {k_u_first, k_u_fix, k_rings, k_move}.  Synchronous;
+ * n_ticks <= 4096.  Measurement aid for bench.py's roofline object, not a reference operator. */
+int flowamok_step_profile(flowamok_context *ctx, flowamok_grid *g, int perfect, int64_t n_ticks, double *ms);
+
+/* Ordered cell_leak list of ONE tick (src/model.fut:26, option.fut:3-12): runs one tick and returns up
+ * to cap leaks in row-major order of the source cell as 8 int64 per leak:
+ * {y_next, x_next, y_src, x_src, dy, dx, color, pref}.  Synchronous. */
+int flowamok_step_leaks(flowamok_context *ctx, flowamok_grid *g, int perfect, int64_t cap, int64_t *leaks, int64_t *n_leaks);
+
+/* render (flowamok.fut:16-64) into a host buffer [gh*scale][gw*scale] of argb.  Synchronous. */
+int flowamok_render(flowamok_context *ctx, const flowamok_grid *g, int64_t scale, uint32_t *pixels);
+
+/* diagnostics of the ticks since the last call: fixpoint passes, local relaxation sweeps, ticks */
+int flowamok_stats(flowamok_context *ctx, flowamok_grid *g, int64_t *ticks, int64_t *passes, int64_t *sweeps);
+
+/* Synthetic road network of SURVEY.md App. E (monotone avenue lattice + ring tiles), generated on the
+ * device; density16 = car probability per road cell in 1/65536, ring_full16 = share of rings that start
+ * completely full in 1/16.  Also installs the analytic cycle list.  Synchronous. */
+int flowamok_generate_synthetic(flowamok_context *ctx, flowamok_grid *g, uint64_t seed, uint32_t density16, uint32_t ring_full16);
+
+/* library identification */
+const char *flowamok_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

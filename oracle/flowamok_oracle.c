@@ -731,3 +731,95 @@ void fo_render(const fo_grid *g, int64_t h, int64_t w, int64_t scale, uint32_t *
       pixels[y * w + x] = px;
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * synthetic road network (rule documented in DESIGN.md):
+ *  - avenues: rows y%16==0 carry u.x=+1, columns x%16==8 carry u.y=+1 (monotone: no cycles)
+ *  - ring tiles: block (by,bx) owns rows 16by+2..16by+14, cols 16bx+10..16bx+22; if hash bit 0 is set it
+ *    holds a one-way 13x13 rectangular ring built like scenarios.fut:117-120 (bit 1: clockwise)
+ *  - cars: probability density16/65536 per road cell; a ring is completely full with prob ring_full16/16
+ * ---------------------------------------------------------------------------------------- */
+static uint64_t sm64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ULL;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+  return x ^ (x >> 31);
+}
+static uint64_t shash(uint64_t seed, uint64_t tag, uint64_t a, uint64_t b) {
+  uint64_t k = sm64(seed ^ (tag * 0xD6E8FEB86659FD93ULL));
+  k = sm64(k ^ a);
+  return sm64(k ^ b);
+}
+static void ring_dir(int cw, int ly, int lx, int *hy, int *hx) {
+  *hy = 0; *hx = 0;
+  if (cw) {
+    if (ly == 0 && lx < 12) *hx = 1; else if (lx == 12 && ly < 12) *hy = 1;
+    else if (ly == 12 && lx > 0) *hx = -1; else *hy = -1;
+  } else {
+    if (ly == 0 && lx > 0) *hx = -1; else if (lx == 0 && ly < 12) *hy = 1;
+    else if (ly == 12 && lx < 12) *hx = 1; else *hy = -1;
+  }
+}
+int64_t fo_generate_synthetic(fo_grid *g, uint64_t seed, uint32_t density16, uint32_t ring_full16,
+                              int64_t **off_o, int64_t **idx_o, int8_t **cy_o, int8_t **cx_o, uint8_t **grant_o) {
+  const int64_t gh = g->gh, gw = g->gw;
+  const uint64_t inc = (0xda3e39cb94b95bdbULL << 1) | 1ULL;
+#pragma omp parallel for schedule(static)
+  for (int64_t y = 0; y < gh; y++)
+    for (int64_t x = 0; x < gw; x++) {
+      int64_t i = y * gw + x;
+      uint64_t hc = shash(seed, 2, (uint64_t)y, (uint64_t)x);
+      int car = (uint32_t)(hc & 0xFFFF) < density16;
+      int arow = (y % 16) == 0, acol = (x % 16) == 8;
+      g->uy[i] = acol ? 1 : 0; g->ux[i] = arow ? 1 : 0; g->dy[i] = 0; g->dx[i] = 0;
+      if ((arow || acol) && car) {
+        int alongx = arow && (!acol || ((hc >> 16) & 1));
+        if (alongx) g->dx[i] = 1; else g->dy[i] = 1;
+      }
+      g->pref[i] = 0; g->calc[i] = g->my[i] = g->mx[i] = 0;
+      g->rng_state[i] = shash(seed, 4, (uint64_t)y, (uint64_t)x); g->rng_inc[i] = inc;
+      g->color[i] = 0xFFFFFFFFu;
+    }
+  int64_t nby = gh >= 15 ? (gh - 15) / 16 + 1 : 0, nbx = gw >= 23 ? (gw - 23) / 16 + 1 : 0;
+  int64_t nr = 0;
+  for (int64_t by = 0; by < nby; by++)
+    for (int64_t bx = 0; bx < nbx; bx++) nr += (int64_t)(shash(seed, 1, (uint64_t)by, (uint64_t)bx) & 1);
+  int64_t *off = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nr + 1));
+  int64_t *idx = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nr * 48 + 1));
+  int8_t *cy = (int8_t *)malloc((size_t)(nr * 48 + 1)), *cx = (int8_t *)malloc((size_t)(nr * 48 + 1));
+  uint8_t *grant = (uint8_t *)malloc((size_t)(nr * 48 + 1));
+  int64_t k = 0, t = 0;
+  for (int64_t by = 0; by < nby; by++)
+    for (int64_t bx = 0; bx < nbx; bx++) {
+      uint64_t hb = shash(seed, 1, (uint64_t)by, (uint64_t)bx);
+      if (!(hb & 1)) continue;
+      int cw = (int)((hb >> 1) & 1), full = (uint32_t)((hb >> 8) & 15) < ring_full16;
+      int s = cw ? 1 : -1;
+      off[k++] = t;
+      for (int ly = 0; ly <= 12; ly++)
+        for (int lx = 0; lx <= 12; lx++) {
+          if (!(ly == 0 || ly == 12 || lx == 0 || lx == 12)) continue;
+          int64_t y = 16 * by + 2 + ly, x = 16 * bx + 10 + lx, i = y * gw + x;
+          if (ly == 0) g->ux[i] = (int8_t)s;
+          if (ly == 12) g->ux[i] = (int8_t)-s;
+          if (lx == 12) g->uy[i] = (int8_t)s;
+          if (lx == 0) g->uy[i] = (int8_t)-s;
+          int hy, hx;
+          ring_dir(cw, ly, lx, &hy, &hx);
+          uint64_t hc = shash(seed, 2, (uint64_t)y, (uint64_t)x);
+          if (full || (uint32_t)(hc & 0xFFFF) < density16) { g->dy[i] = (int8_t)hy; g->dx[i] = (int8_t)hx; }
+          idx[t] = i; cy[t] = (int8_t)hy; cx[t] = (int8_t)hx;
+          int corner = (ly == 0 || ly == 12) && (lx == 0 || lx == 12);
+          /* steppers.fut:206-211: a corner is granted along the axis it is ENTERED on = not its heading */
+          grant[t] = (uint8_t)(corner ? (hy != 0 ? 2 : 1) : (hx != 0 ? 2 : 1));
+          t++;
+        }
+    }
+  off[k] = t;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < gh * gw; i++)
+    if (g->dy[i] != 0 || g->dx[i] != 0)
+      g->color[i] = 0xFF000000u | (uint32_t)(shash(seed, 3, (uint64_t)(i / gw), (uint64_t)(i % gw)) & 0xFFFFFFu);
+  *off_o = off; *idx_o = idx; *cy_o = cy; *cx_o = cx; *grant_o = grant;
+  return nr;
+}

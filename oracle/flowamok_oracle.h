@@ -113,6 +113,12 @@ int  fo_scenario_step(int sid, fo_grid *g, int64_t steps, fo_rng *rng);
 /* ---- render: flowamok.fut:16-64 ---- */
 void fo_render(const fo_grid *g, int64_t h, int64_t w, int64_t scale, uint32_t *pixels);
 
+/* ---- synthetic road network of SURVEY.md App. E (the reference has no generator; this restates the
+ * rule documented in DESIGN.md independently of the device generator) ----
+ * fills g; returns the number of rings and malloc'd sparse ring arrays (as fo_cycles_dense_to_sparse). */
+int64_t fo_generate_synthetic(fo_grid *g, uint64_t seed, uint32_t density16, uint32_t ring_full16,
+                              int64_t **off, int64_t **idx, int8_t **cy, int8_t **cx, uint8_t **grant);
+
 /* ---- misc ---- */
 void fo_set_threads(int n);    /* OpenMP threads for the map-shaped passes (cpu baseline) */
 int  fo_get_max_threads(void);

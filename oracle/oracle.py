@@ -102,6 +102,8 @@ def lib():
     L.fo_resolve_cycles_sparse.argtypes = [GP, C.c_int64] + [C.c_void_p] * 5
     L.fo_step_perfect_sparse.restype = C.c_int64
     L.fo_step_perfect_sparse.argtypes = [GP, C.POINTER(_Chooser), C.c_int64] + [C.c_void_p] * 5 + [LPP]
+    L.fo_generate_synthetic.restype = C.c_int64
+    L.fo_generate_synthetic.argtypes = [GP, C.c_uint64, C.c_uint32, C.c_uint32] + [C.POINTER(C.c_void_p)] * 5
     L.fo_scenario_name.restype = C.c_char_p
     L.fo_scenario_name.argtypes = [C.c_int]
     L.fo_scenario_init.argtypes = [C.c_int, GP]
@@ -305,6 +307,19 @@ class Grid:
             off.append(len(idx))
         return (np.asarray(off, np.int64), np.asarray(idx, np.int64), np.asarray(cy, np.int8),
                 np.asarray(cx, np.int8), np.asarray(grant, np.uint8))
+
+    def generate_synthetic(self, seed=1, density16=6554, ring_full16=2):
+        """fills the grid with the synthetic network; returns the sparse ring arrays"""
+        ptrs = [C.c_void_p() for _ in range(5)]
+        n = int(self.L.fo_generate_synthetic(self.p, seed, density16, ring_full16, *[C.byref(p) for p in ptrs]))
+        tot = n * 48
+        def take(p, dt, cnt):
+            a = np.frombuffer((C.c_char * (cnt * np.dtype(dt).itemsize)).from_address(p.value), dtype=dt).copy()
+            self.L._libc.free(p)
+            return a
+        return (take(ptrs[0], np.int64, n + 1), take(ptrs[1], np.int64, max(tot, 1))[:tot],
+                take(ptrs[2], np.int8, max(tot, 1))[:tot], take(ptrs[3], np.int8, max(tot, 1))[:tot],
+                take(ptrs[4], np.uint8, max(tot, 1))[:tot])
 
     # --- scenarios / render ---
     def scenario_init(self, sid):

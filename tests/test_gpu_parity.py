@@ -1,0 +1,234 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (flowamok_b200 -> libflowamok_b200.so),
+against the CPU oracle on the same inputs -- bit-exact, full state, every tick -- plus the committed
+golden fixture and size-independent properties at BASELINE.json's full sizes."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import synth_ref
+from util import O, ROOT, STATE_FIELDS, assert_state_equal, oracle_grid, random_grid, state_of
+
+pytestmark = pytest.mark.gpu
+
+
+def dev_state(g):
+    d = g.download()
+    return {k: d[k] for k in STATE_FIELDS}
+
+
+def rings_to_api(gw, rings):
+    off, idx, cy, cx, grant = rings
+    return off, idx // gw, idx % gw, cy, cx, grant
+
+
+SHAPES = [(5, 7), (17, 31), (30, 32), (33, 33), (64, 65), (70, 100), (1, 40), (40, 1), (97, 130), (200, 1100),
+          (130, 2100)]
+
+
+def test_upload_download_roundtrip(ctx):
+    for seed, (gh, gw) in enumerate(SHAPES):
+        arrs = random_grid(seed, gh, gw)
+        g = ctx.grid_from_arrays(**arrs)
+        d = g.download()
+        for k in ("uy", "ux", "dy", "dx", "color", "pref", "rng_state"):
+            assert np.array_equal(d[k], arrs[k]), (k, gh, gw)
+
+
+def test_quick_random_grids_every_tick(ctx):
+    for seed, (gh, gw) in enumerate(SHAPES):
+        arrs = random_grid(300 + seed, gh, gw)
+        og, ch = oracle_grid(arrs), O.Chooser(O.CHOOSE_RANDOM)
+        g = ctx.grid_from_arrays(**arrs)
+        for t in range(12):
+            nl, _ = og.step_quick(ch)
+            assert g.step(False, 1) == nl, f"leaks {gh}x{gw} tick {t}"
+            assert_state_equal(state_of(og), dev_state(g), f"{gh}x{gw} tick {t}")
+
+
+def test_dense_jam_multi_pass(ctx):
+    """long queues crossing tile borders: exercises k_u_fix (extra device-side fixpoint passes)"""
+    arrs = random_grid(7, 300, 2200, n_lines=400, car_p=0.93, weird_p=0.0, offroad_p=0.0)
+    og, ch = oracle_grid(arrs), O.Chooser(O.CHOOSE_RANDOM)
+    g = ctx.grid_from_arrays(**arrs)
+    g.stats()
+    for t in range(6):
+        nl, _ = og.step_quick(ch)
+        assert g.step(False, 1) == nl
+        assert_state_equal(state_of(og), dev_state(g), f"tick {t}")
+    st = g.stats()
+    assert st["ticks"] == 6 and st["passes"] > 6, st
+
+
+@pytest.mark.parametrize("mode", [O.CHOOSE_Y, O.CHOOSE_X, O.CHOOSE_TAPE])
+def test_choosers(ctx, mode):
+    arrs = random_grid(11, 40, 70, car_p=0.5)
+    tape = np.array([1, 0, 0, 1, 1, 0, 1], np.uint8)
+    og = oracle_grid(arrs)
+    ch = O.Chooser(mode, tape if mode == O.CHOOSE_TAPE else None)
+    g = ctx.grid_from_arrays(**arrs)
+    g.set_chooser(mode, tape if mode == O.CHOOSE_TAPE else None)
+    for t in range(14):
+        nl, _ = og.step_quick(ch)
+        assert g.step(False, 1) == nl
+        assert_state_equal(state_of(og), dev_state(g), f"tick {t}")
+
+
+def test_readme_gif_replay_cuda(ctx):
+    """BASELINE config 1 through the C ABI only (no oracle): create_grid 30 30 seed 123, scenario 8 via the
+    point-edit API, find_cycles, 400 perfect ticks with the tape chooser; every frame vs the GIF fixture."""
+    import flowamok_b200 as fa
+    from flowamok_b200 import scenarios as S
+    from test_oracle_golden import TAPE, classes
+    gold = np.load(ROOT / "tests/golden/readme_gif_classes.npz")["frames"]
+    g = ctx.create_grid(30, 30, 123)
+    S.init(8, g)
+    assert g.find_cycles() == 2
+    g.set_chooser(fa.CHOOSE_TAPE, np.array([int(c) for c in TAPE] + [0, 0], np.uint8))
+    for k in range(400):
+        assert np.array_equal(classes(g.download()), gold[k]), f"frame {k}"
+        fa.stepper_perfect.step(g, 1)
+
+
+@pytest.mark.parametrize("sid", list(range(14)))
+def test_explorer_scenarios_perfect(ctx, sid):
+    """BASELINE config 2: every explorer scenario, 108x192, perfect mode, stepping exactly as
+    explorer.fut:113-125 (device ticks + host scenario.step edits through the point-edit API)."""
+    from flowamok_b200 import scenarios as S
+    ox = O.Explorer(123, sid, perfect=True)
+    dx = S.Explorer(ctx, 123, sid, perfect=True)
+    assert_state_equal(state_of(ox.grid), dev_state(dx.grid), f"sid {sid} init")
+    assert np.array_equal(dx.grid.cycles_dense(), ox.cycles), "find_cycles differs from the oracle"
+    n_ticks = 1000 if sid in (1, 4, 5, 8) else 250
+    for t in range(n_ticks):
+        lo = ox.step(1)
+        ld = dx.step(1)
+        assert lo == ld, f"sid {sid} tick {t} leaks"
+        if t < 60 or t % 25 == 0 or t == n_ticks - 1:
+            assert_state_equal(state_of(ox.grid), dev_state(dx.grid), f"sid {sid} tick {t}")
+    assert np.array_equal(dx.grid.cycles_dense(), ox.cycles)
+
+
+def test_find_cycles_matches_oracle(ctx):
+    import synth_ref
+    arrs, rings = synth_ref.generate(50, 60, seed=4)
+    og = oracle_grid(arrs)
+    g = ctx.grid_from_arrays(**arrs)
+    n = g.find_cycles()
+    masks = og.find_cycles()
+    assert n == masks.shape[0] > 0
+    assert np.array_equal(g.cycles_dense(), masks)
+
+
+def test_point_edits_and_create_grid(ctx):
+    og = O.Grid(50, 70)
+    joined = og.create(O.Rng.from_seed([-77]))
+    g = ctx.grid(50, 70)
+    g.create(-77, want_joined=True)
+    assert g.joined_rng == (joined.state, joined.inc)
+    r = np.random.default_rng(5)
+    for _ in range(60):
+        kind = r.integers(0, 3)
+        flow = int(r.choice([-1, 1]))
+        if kind == 0:
+            a, b = sorted(r.integers(0, 50, 2).tolist()); x = int(r.integers(0, 70))
+            og.add_line_vertical(a, b, x, flow); g.add_line_vertical(a, b, x, flow)
+        elif kind == 1:
+            a, b = sorted(r.integers(0, 70, 2).tolist()); y = int(r.integers(0, 50))
+            og.add_line_horizontal(y, a, b, flow); g.add_line_horizontal(y, a, b, flow)
+        else:
+            y, x = int(r.integers(0, 50)), int(r.integers(0, 70))
+            c, dy, dx = int(r.integers(0, 2**32)), int(r.integers(-1, 2)), int(r.integers(-1, 2))
+            og.add_cell(y, x, c, dy, dx); g.add_cell(y, x, c, dy, dx)
+    d = g.download()
+    a = og.arrays()
+    for k in ("uy", "ux", "dy", "dx", "color", "pref", "rng_state"):
+        assert np.array_equal(d[k], a[k]), k
+    assert d["rng_inc"] == int(a["rng_inc"][0, 0])
+
+
+def test_leak_list_order_and_content(ctx):
+    arrs = random_grid(21, 80, 120, car_p=0.5, weird_p=0.05, offroad_p=0.03)
+    og, ch = oracle_grid(arrs), O.Chooser(O.CHOOSE_RANDOM)
+    g = ctx.grid_from_arrays(**arrs)
+    total = 0
+    for t in range(6):
+        nl, leaks = og.step_quick(ch, leaks=True)
+        n, rec = g.step_leaks(False)
+        assert n == nl
+        exp = [[l["y_next"], l["x_next"], l["y_src"], l["x_src"], l["dy"], l["dx"], l["color"], l["pref"]] for l in leaks]
+        assert rec.tolist() == exp, f"tick {t}"
+        total += n
+        assert_state_equal(state_of(og), dev_state(g), f"tick {t}")
+    assert total > 0
+
+
+def test_render_matches_oracle(ctx):
+    for scale in (1, 4, 5, 10):
+        arrs = random_grid(31, 30, 45, car_p=0.5)
+        og = oracle_grid(arrs)
+        g = ctx.grid_from_arrays(**arrs)
+        assert np.array_equal(g.render(scale), og.render(scale)), scale
+
+
+@pytest.mark.parametrize("perfect", [False, True])
+def test_synthetic_network_vs_oracle(ctx, perfect):
+    """BASELINE configs 3/4 generator at a size the oracle finishes in seconds; device generator vs the
+    numpy restatement, then every tick vs the oracle."""
+    gh, gw = 600, 1300
+    arrs, rings = synth_ref.generate(gh, gw, seed=1)
+    g = ctx.grid(gh, gw)
+    g.generate_synthetic(seed=1)
+    d = g.download()
+    for k in ("uy", "ux", "dy", "dx", "color", "pref", "rng_state"):
+        assert np.array_equal(d[k], arrs[k]), f"generator field {k}"
+    assert g.cycle_count()[0] == len(rings[0]) - 1
+    og, ch = oracle_grid(arrs), O.Chooser(O.CHOOSE_RANDOM)
+    for t in range(40):
+        if perfect:
+            nl, _ = og.step_perfect_sparse(ch, rings)
+        else:
+            nl, _ = og.step_quick(ch)
+        assert g.step(perfect, 1) == nl
+        if t < 10 or t % 10 == 9:
+            assert_state_equal(state_of(og), dev_state(g), f"perfect={perfect} tick {t}")
+
+
+def _plane_digest(g):
+    d = g.download(fields=("dy", "dx", "color", "pref"))
+    h = hashlib.sha256()
+    for k in ("dy", "dx", "color", "pref"):
+        h.update(d[k].tobytes())
+    occ = (d["dy"] != 0) | (d["dx"] != 0)
+    return h.hexdigest(), int(occ.sum())
+
+
+def test_full_size_properties_4096(ctx):
+    """BASELINE config 3 (4096^2, 10 % density): determinism, car conservation (cars only disappear by
+    leaving the grid: the lattice has no leaks), batch == single-tick stepping."""
+    a = ctx.grid(4096, 4096)
+    a.generate_synthetic(seed=1)
+    b = ctx.grid(4096, 4096)
+    b.generate_synthetic(seed=1)
+    _, cars0 = _plane_digest(a)
+    la = a.step(True, 200)
+    lb = sum(b.step(True, 1) for _ in range(200))
+    da, cars_a = _plane_digest(a)
+    db, cars_b = _plane_digest(b)
+    assert da == db and la == lb == 0
+    assert cars_a <= cars0 and cars0 - cars_a < cars0 * 0.2
+    st = a.stats()
+    assert st["ticks"] == 200 and st["passes"] >= 200
+
+
+def test_band_of_16384_vs_oracle(ctx):
+    """BASELINE config 4 generator on a 512 x 16384 band: 30 ticks vs the oracle."""
+    gh, gw = 512, 16384
+    arrs, rings = synth_ref.generate(gh, gw, seed=1)
+    g = ctx.grid(gh, gw)
+    g.generate_synthetic(seed=1)
+    og, ch = oracle_grid(arrs), O.Chooser(O.CHOOSE_RANDOM)
+    for t in range(30):
+        nl, _ = og.step_quick(ch)
+        assert g.step(False, 1) == nl
+    assert_state_equal(state_of(og), dev_state(g), "band tick 30")
