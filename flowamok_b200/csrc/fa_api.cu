@@ -97,6 +97,7 @@ int flowamok_context_new(flowamok_context **out, int device, void *stream) {
   else { CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
   CU(cudaFuncSetAttribute(k_u_first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UT::Smem)));
   CU(cudaFuncSetAttribute(k_u_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UT::Smem)));
+  CU(cudaFuncSetAttribute(k_move, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MoveSmem)));
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_u_fix, U_THREADS, sizeof(UT::Smem)));
   if (per_sm < 1) return fail(ctx, "k_u_fix does not fit on an SM");
@@ -522,7 +523,7 @@ static int enqueue_tick(flowamok_context *ctx, flowamok_grid *g, bool perfect, u
     CU(cudaGetLastError());
   }
   if (ev) CU(cudaEventRecord(ev[3], st));
-  k_move<<<g->mtx * g->mty, M_THREADS, 0, st>>>(v, g->mtx, g->diag, leak_plane);
+  k_move<<<g->mtx * g->mty, M_THREADS, sizeof(MoveSmem), st>>>(v, g->mtx, g->diag, leak_plane);
   CU(cudaGetLastError());
   if (ev) CU(cudaEventRecord(ev[4], st));
   g->cur ^= 1;
@@ -613,8 +614,10 @@ int flowamok_step_leaks(flowamok_context *ctx, flowamok_grid *g, int perfect, in
   if (emit > 0 && leaks) {
     long long *dout = nullptr;
     CU(cudaMalloc(&dout, (size_t)emit * 64));
+    // the tuple copies the cell as move_cell saw it (steppers.fut:122): heading/colour of the old state,
+    // next_preference_flow_x already updated by the fixpoint (written by U into the new buffer)
     k_leak_emit<<<nblk((long long)g->nwords, 256), 256, 0, st>>>(g->gh, g->gw, g->pitch, g->leak_plane, offs, g->head[old],
-                                                                g->pref[old], g->color[old], emit, dout);
+                                                                g->pref[old ^ 1], g->color[old], emit, dout);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(leaks, dout, (size_t)emit * 64, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));

@@ -55,23 +55,45 @@ __device__ __forceinline__ void run_u_tile(const GridView &g, UT::Smem &s, int t
   t.p2(tid, nt);
   __syncthreads();
   unsigned int sweeps = 0;
-  for (;;) {
-    bool ch = t.p3(tid, nt);
+  int cur = 0;
+  for (;;) {  // relaxation sweeps over the worklist of words that still hold a waiting car
+    const int n = (int)s.wn[cur];
+    if (n == 0) break;
+    bool ch = false;
+    for (int base = 0; base < n; base += nt) {
+      UT::Pend pd;
+      t.p3a(tid, cur, base, pd);
+      __syncthreads();
+      ch |= t.p3b(cur, pd);
+      __syncthreads();
+    }
     sweeps++;
-    if (!__syncthreads_or(ch)) break;
+    int any = __syncthreads_or(ch);
+    if (tid == 0) s.wn[cur] = 0;
+    cur ^= 1;
+    __syncthreads();
+    if (!any) break;
   }
   int res = t.p4(tid, nt);
   int unready = __syncthreads_or(res & 1);
   int differs = FIRST ? 0 : __syncthreads_or(res & 2);
   int pending = 0;
-  if (unready) {
+  if (unready && s.wn[cur] != 0) {
     t.p5a(tid, nt);
     __syncthreads();
+    const int n = (int)s.wn[cur];
     for (;;) {
-      bool ch = t.p5b(tid, nt);
+      bool ch = false;
+      for (int base = 0; base < n; base += nt) {
+        int iw;
+        u32 x = t.p5b_compute(tid, cur, base, iw);
+        __syncthreads();
+        ch |= t.p5b_commit(iw, x);
+        __syncthreads();
+      }
       if (!__syncthreads_or(ch)) break;
     }
-    pending = __syncthreads_or(t.p5c(tid, nt));
+    pending = __syncthreads_or(t.p5c(tid, nt, cur));
   }
   if (tid == 0) {
     if (pending) pend_out[atomicAdd(npend_out, 1u)] = (unsigned int)tile_id;
@@ -186,18 +208,99 @@ __global__ void k_rings(const __grid_constant__ GridView g, const unsigned long 
 }
 
 // ---------------------------------------------------------------------------------------------
+// TMA (bulk async copy) + mbarrier wrappers.  The colour payload is pure data movement, so it is
+// handed to the copy engine: global -> shared -> global in 4 KB rows, no per-thread LDG/STG.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done = 0;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(dst_gmem), "r"(smem_addr(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_all() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
 // move + reset
 // ---------------------------------------------------------------------------------------------
+struct MoveSmem {
+  MT::Smem m;
+  alignas(128) u32 color[MT::TR][MT::TW * 32];  // the tile's colour payload, staged by TMA
+  alignas(8) uint64_t bar;
+};
+
 __global__ void __launch_bounds__(M_THREADS, 2)
 k_move(const __grid_constant__ GridView g, int mtx, Diag *diag, unsigned int *leak_plane) {
-  __shared__ MT::Smem s;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  MoveSmem &sm = *reinterpret_cast<MoveSmem *>(smem_raw);
+  MT::Smem &s = sm.m;
   const int tid = threadIdx.x, nt = blockDim.x;
-  MT t(g, s, blockIdx.x / mtx, blockIdx.x % mtx);
+  const int ty = blockIdx.x / mtx, tx = blockIdx.x % mtx;
+  const int y0 = ty * MT::TR, w0 = tx * MT::TW;
+  const int rows = min(MT::TR, g.gh - y0), words = min(MT::TW, g.pitch - w0);
+  const size_t cpitch = (size_t)g.pitch * 32;
+  const uint32_t row_bytes = (uint32_t)words * 128u;
+  // 1. kick off the colour tile: one bulk copy per row, completion counted on the mbarrier
+  if (tid == 0) mbar_init(&sm.bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&sm.bar, row_bytes * (uint32_t)rows);
+    for (int r = 0; r < rows; r++)
+      bulk_g2s(&sm.color[r][0], g.color_in + (size_t)(y0 + r) * cpitch + (size_t)w0 * 32, row_bytes, &sm.bar);
+  }
+  // 2. control planes while the payload is in flight
+  MT t(g, s, ty, tx);
   t.p0(tid, nt);
   __syncthreads();
   t.p1(tid, nt, leak_plane);
   __syncthreads();
-  t.p2(tid, nt);
+  // 3. payload landed -> stream it out unchanged, then overwrite the few cells a car arrived in
+  mbar_wait(&sm.bar, 0);
+  if (tid == 0) {
+    for (int r = 0; r < rows; r++)
+      bulk_s2g(g.color_out + (size_t)(y0 + r) * cpitch + (size_t)w0 * 32, &sm.color[r][0], row_bytes);
+    bulk_commit_wait_all();   // writes performed before any patch store is issued
+  }
+  __syncthreads();
+  for (int i = tid; i < MT::TR * MT::TW; i += nt) {
+    u32 ay = s.AY[i], ax = s.AX[i];
+    u32 m = ay | ax;
+    if (!m) continue;
+    int tr = i / MT::TW, tc = i - tr * MT::TW;
+    int si = MT::idx(tr + 1, tc + 1);
+    u32 uys = s.UYS[si], uxs = s.UXS[si];
+    size_t base = (size_t)(y0 + tr) * cpitch + (size_t)(w0 + tc) * 32;
+    while (m) {  // steppers.fut:109: the arriving car brings its colour
+      int b = __ffs(m) - 1;
+      u32 bit = 1u << b;
+      m &= m - 1;
+      int sr = tr, sx = tc * 32 + b;  // source cell in tile coordinates
+      if (ay & bit) sr += (uys & bit) ? 1 : -1; else sx += (uxs & bit) ? 1 : -1;
+      u32 col;
+      if (sr >= 0 && sr < rows && sx >= 0 && sx < words * 32) col = sm.color[sr][sx];
+      else col = g.color_in[(size_t)(y0 + sr) * cpitch + (size_t)w0 * 32 + sx];
+      g.color_out[base + b] = col;
+    }
+  }
   if (tid == 0 && s.leaks) atomicAdd(&diag->leaks, (unsigned long long)s.leaks);
 }
 

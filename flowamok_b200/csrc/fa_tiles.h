@@ -87,7 +87,39 @@ FA_HD int ffs32(u32 v) {  // index of lowest set bit, v != 0
 
 // =============================================================================================
 // U tile: local least fixpoint of update_can_be_moved_to_from (steppers.fut:9-56, :147-164)
+//
+// Only words that hold a waiting car ("link" cells: occupied, successor in bounds and on a road) can
+// ever change after initialisation, so they are compacted into a worklist in shared memory and the
+// relaxation sweeps touch nothing else.  A sweep is compute -> barrier -> commit -> barrier, which
+// makes every committed word a consistent (R, MY, MX) triple: a cell with R = 1 has final MY/MX.
 // =============================================================================================
+FA_HD void fa_fence_block() {
+#if defined(__CUDA_ARCH__)
+  __threadfence_block();
+#endif
+}
+FA_HD void fa_fence_device() {
+#if defined(__CUDA_ARCH__)
+  __threadfence();
+#endif
+}
+// append v to list if pred (warp-aggregated on the device)
+FA_HD void wl_push(unsigned short *list, unsigned int *cnt, bool pred, unsigned short v) {
+#if defined(__CUDA_ARCH__)
+  unsigned act = __activemask();
+  unsigned m = __ballot_sync(act, pred);
+  if (m) {
+    int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(cnt, (unsigned)__popc(m));
+    base = __shfl_sync(act, base, leader);
+    if (pred) list[base + __popc(m & ((1u << lane) - 1u))] = v;
+  }
+#else
+  if (pred) list[(*cnt)++] = v;
+#endif
+}
+
 template <int TR_, int TW_, int H_>
 struct UTile {
   static constexpr int TR = TR_, TW = TW_, H = H_;
@@ -98,7 +130,13 @@ struct UTile {
     u32 DYN[NW], DYS[NW], DXN[NW], DXS[NW];
     u32 T[NW], GY[NW], GX[NW];
     u32 R[NW], MY[NW], MX[NW];   // R doubles as ROAD staging during p0/p1; MY as the taint plane in p5
-    int flag;                    // block-wide vote scratch for the host emulation
+    unsigned short wl[2][NW];    // worklists of active words (ping-pong)
+    unsigned int wn[2];
+  };
+  struct Pend {  // a thread's computed-but-uncommitted word of the current sweep
+    int i;
+    u32 R, MY, MX;
+    bool changed;
   };
 
   const GridView &g;
@@ -133,6 +171,7 @@ struct UTile {
 
   // p0: stage car planes and the road-presence plane of the whole smem region
   FA_HD void p0(int tid, int nt) {
+    if (tid == 0) { s.wn[0] = 0; s.wn[1] = 0; }
     for (int i = tid; i < NW; i += nt) {
       int r = i / SW, c = i - r * SW;
       U4 hd = {0, 0, 0, 0};
@@ -166,20 +205,29 @@ struct UTile {
       s.T[i] = T; s.GY[i] = GY; s.GX[i] = GX;
     }
   }
-  // p2: initial state: computed bits start from the terminals, outer bits come from the global planes
+  // p2: initial state (computed bits start from the terminals, outer bits come from the global planes)
+  //     and the first worklist: every word holding a link cell
   FA_HD void p2(int tid, int nt) {
-    for (int i = tid; i < NW; i += nt) {
-      int r = i / SW, c = i - r * SW;
-      u32 cm = cmask(r, c);
-      u32 oR = 0, oMY = 0, oMX = 0;
-      if (!first_pass && cm != 0xFFFFFFFFu && in_grid(r, c)) {
-        size_t o = (size_t)grow(r) * g.pitch + gword(c);
-        oR = g.calc[o]; oMY = g.my[o]; oMX = g.mx[o];
+    for (int i0 = 0; i0 < NW; i0 += nt) {
+      int i = i0 + tid;
+      bool act = false;
+      if (i < NW) {
+        int r = i / SW, c = i - r * SW;
+        u32 cm = cmask(r, c);
+        u32 oR = 0, oMY = 0, oMX = 0;
+        if (!first_pass && cm != 0xFFFFFFFFu && in_grid(r, c)) {
+          size_t o = (size_t)grow(r) * g.pitch + gword(c);
+          oR = g.calc[o];       // calc BEFORE my/mx: the writer publishes my/mx first (p4)
+          fa_fence_device();
+          oMY = g.my[o]; oMX = g.mx[o];
+        }
+        u32 T = s.T[i];
+        s.R[i] = (cm & T) | (~cm & oR);
+        s.MY[i] = (cm & T & s.GY[i]) | (~cm & oMY);
+        s.MX[i] = (cm & T & s.GX[i]) | (~cm & oMX);
+        act = (~T & cm) != 0u;
       }
-      u32 T = s.T[i];
-      s.R[i] = (cm & T) | (~cm & oR);
-      s.MY[i] = (cm & T & s.GY[i]) | (~cm & oMY);
-      s.MX[i] = (cm & T & s.GX[i]) | (~cm & oMX);
+      wl_push(s.wl[0], &s.wn[0], act, (unsigned short)i);
     }
   }
   FA_HD UStatic links(int i) const {
@@ -192,27 +240,33 @@ struct UTile {
     st.GYr = s.GY[i]; st.GXr = s.GX[i];
     return st;
   }
-  // p3: one relaxation sweep; returns true if this thread changed anything
-  FA_HD bool p3(int tid, int nt) {
-    bool changed = false;
-    for (int i = tid; i < NW; i += nt) {
-      int r = i / SW, c = i - r * SW;
-      u32 cm = cmask(r, c);
-      if (cm == 0u) continue;
-      u32 T = s.T[i];
-      if ((~T & cm) == 0u) continue;  // no waiting car in this word: state is final since p2
-      UStatic st = links(i);
-      UState n = u_relax(st, w3(s.R, r - 1, c), w3(s.R, r, c), w3(s.R, r + 1, c), w3(s.MY, r - 1, c),
-                         w3(s.MY, r + 1, c), w3(s.MX, r, c), w3(s.MX, r - 1, c), w3(s.MX, r + 1, c));
-      u32 nR = (cm & n.R) | (~cm & s.R[i]);
-      u32 nMY = (cm & n.MY) | (~cm & s.MY[i]);
-      u32 nMX = (cm & n.MX) | (~cm & s.MX[i]);
-      if (nR != s.R[i] || nMY != s.MY[i] || nMX != s.MX[i]) {
-        s.R[i] = nR; s.MY[i] = nMY; s.MX[i] = nMX;
-        changed = true;
-      }
+  // p3a: compute the new state of worklist entry (base + tid) of list `cur` (no smem writes)
+  FA_HD void p3a(int tid, int cur, int base, Pend &pd) const {
+    pd.i = -1; pd.changed = false;
+    int k = base + tid;
+    if (k >= (int)s.wn[cur]) return;
+    int i = s.wl[cur][k];
+    int r = i / SW, c = i - r * SW;
+    u32 cm = cmask(r, c);
+    UStatic st = links(i);
+    UState n = u_relax(st, w3(s.R, r - 1, c), w3(s.R, r, c), w3(s.R, r + 1, c), w3(s.MY, r - 1, c),
+                       w3(s.MY, r + 1, c), w3(s.MX, r, c), w3(s.MX, r - 1, c), w3(s.MX, r + 1, c));
+    pd.i = i;
+    pd.R = (cm & n.R) | (~cm & s.R[i]);
+    pd.MY = (cm & n.MY) | (~cm & s.MY[i]);
+    pd.MX = (cm & n.MX) | (~cm & s.MX[i]);
+    pd.changed = pd.R != s.R[i] || pd.MY != s.MY[i] || pd.MX != s.MX[i];
+  }
+  // p3b: commit, and keep the word on the next list while it still holds an uncalculated link cell
+  FA_HD bool p3b(int cur, const Pend &pd) {
+    bool keep = false;
+    if (pd.i >= 0) {
+      if (pd.changed) { s.R[pd.i] = pd.R; s.MY[pd.i] = pd.MY; s.MX[pd.i] = pd.MX; }
+      int r = pd.i / SW, c = pd.i - r * SW;
+      keep = (~pd.R & ~s.T[pd.i] & cmask(r, c)) != 0u;
     }
-    return changed;
+    wl_push(s.wl[cur ^ 1], &s.wn[cur ^ 1], keep, (unsigned short)(pd.i >= 0 ? pd.i : 0));
+    return pd.changed;
   }
   // p4: write the tile's own words; returns bit0 = some owned cell is still uncalculated,
   //     bit1 = the written planes differ from what the previous pass left in global memory
@@ -228,7 +282,9 @@ struct UTile {
       Edge e = edge_masks(y, w, g.gh, g.gw);
       u32 R = s.R[si] & e.valid, MY = s.MY[si] & e.valid, MX = s.MX[si] & e.valid;
       if (!first_pass && (g.calc[o] != R || g.my[o] != MY || g.mx[o] != MX)) res |= 2;
-      g.calc[o] = R; g.my[o] = MY; g.mx[o] = MX;
+      g.my[o] = MY; g.mx[o] = MX;
+      if (!first_pass) fa_fence_device();   // concurrent readers (p2 of a neighbour) must never see calc without its my/mx
+      g.calc[o] = R;
       U4 rd = g.road[o];
       UState f = {R, MY, MX};
       UStatic dummy = {};
@@ -237,39 +293,40 @@ struct UTile {
     }
     return res;
   }
-  // p5a/p5b: does an uncalculated owned cell wait (transitively) on an uncalculated OUTER cell?
-  // The taint plane reuses MY (no longer needed after p4).
+  // p5: does an uncalculated owned cell wait (transitively) on an uncalculated OUTER cell?  Only words
+  // still on the worklist (list `cur`) can be tainted.  The taint plane reuses MY (dead after p4).
   FA_HD void p5a(int tid, int nt) {
     for (int i = tid; i < NW; i += nt) {
       int r = i / SW, c = i - r * SW;
       s.MY[i] = ~cmask(r, c) & ~s.R[i];
     }
   }
-  FA_HD bool p5b(int tid, int nt) {
-    bool changed = false;
-    for (int i = tid; i < NW; i += nt) {
-      int r = i / SW, c = i - r * SW;
-      u32 cm = cmask(r, c);
-      if (cm == 0u) continue;
-      if ((~s.T[i] & cm) == 0u) continue;
-      UStatic st = links(i);
-      W3 Xu = w3(s.MY, r - 1, c), Xc = w3(s.MY, r, c), Xd = w3(s.MY, r + 1, c);
-      u32 x = (st.LN & Xu.c) | (st.LS & Xd.c) | (st.LW & west(Xc)) | (st.LE & east(Xc)) |
-              (st.LNW & west(Xu)) | (st.LNE & east(Xu)) | (st.LSW & west(Xd)) | (st.LSE & east(Xd));
-      u32 nx = s.MY[i] | (cm & x);
-      if (nx != s.MY[i]) { s.MY[i] = nx; changed = true; }
-    }
-    return changed;
+  FA_HD u32 p5b_compute(int tid, int cur, int base, int &iw) const {
+    iw = -1;
+    int k = base + tid;
+    if (k >= (int)s.wn[cur]) return 0u;
+    int i = s.wl[cur][k];
+    int r = i / SW, c = i - r * SW;
+    UStatic st = links(i);
+    W3 Xu = w3(s.MY, r - 1, c), Xc = w3(s.MY, r, c), Xd = w3(s.MY, r + 1, c);
+    u32 x = (st.LN & Xu.c) | (st.LS & Xd.c) | (st.LW & west(Xc)) | (st.LE & east(Xc)) |
+            (st.LNW & west(Xu)) | (st.LNE & east(Xu)) | (st.LSW & west(Xd)) | (st.LSE & east(Xd));
+    iw = i;
+    return s.MY[i] | (cmask(r, c) & x);
   }
-  FA_HD bool p5c(int tid, int nt) {
+  FA_HD bool p5b_commit(int iw, u32 x) {
+    if (iw < 0 || x == s.MY[iw]) return false;
+    s.MY[iw] = x;
+    return true;
+  }
+  FA_HD bool p5c(int tid, int nt, int cur) const {
     bool pending = false;
-    for (int i = tid; i < TR * TW; i += nt) {
-      int tr = i / TW, tc = i - tr * TW;
-      int r = tr + H + 1, c = tc + 1;
-      int y = grow(r), w = gword(c);
-      if (y >= g.gh || w >= g.pitch) continue;
-      Edge e = edge_masks(y, w, g.gh, g.gw);
-      if ((s.MY[idx(r, c)] & e.valid) != 0u) pending = true;
+    for (int k = tid; k < (int)s.wn[cur]; k += nt) {
+      int i = s.wl[cur][k];
+      int r = i / SW, c = i - r * SW;
+      if (r < H + 1 || r >= H + 1 + TR || c < 1 || c > TW) continue;  // not an owned word
+      Edge e = edge_masks(grow(r), gword(c), g.gh, g.gw);
+      if ((s.MY[i] & e.valid) != 0u) pending = true;
     }
     return pending;
   }
@@ -313,11 +370,28 @@ struct MTile {
     W3 v = {p[idx(r, c - 1)], p[idx(r, c)], p[idx(r, c + 1)]};
     return v;
   }
-  FA_HD MRow mrow(int r, int c) const {
+  // centre row: x-neighbours of every field that is looked at sideways (UYS is not)
+  FA_HD MRow mrow_center(int r, int c) const {
     MRow m;
-    m.UYN = w3(s.UYN, r, c); m.UYS = w3(s.UYS, r, c); m.UXN = w3(s.UXN, r, c); m.UXS = w3(s.UXS, r, c);
+    m.UYN = w3(s.UYN, r, c); m.UXN = w3(s.UXN, r, c); m.UXS = w3(s.UXS, r, c);
+    m.UYS.c = s.UYS[idx(r, c)]; m.UYS.l = m.UYS.r = 0u;
     m.DYN = w3(s.DYN, r, c); m.DYS = w3(s.DYS, r, c); m.DXN = w3(s.DXN, r, c); m.DXS = w3(s.DXS, r, c);
     m.MY = w3(s.MY, r, c); m.MX = w3(s.MX, r, c);
+    return m;
+  }
+  // rows above/below: only the same word, unless a diagonal heading needs the corner cells
+  FA_HD MRow mrow_side(int r, int c, bool diag) const {
+    MRow m;
+    int i = idx(r, c);
+    m.UYN.c = s.UYN[i]; m.UYS.c = s.UYS[i]; m.UXN.c = s.UXN[i]; m.UXS.c = s.UXS[i];
+    m.DYN.c = s.DYN[i]; m.DYS.c = s.DYS[i]; m.DXN.c = s.DXN[i]; m.DXS.c = s.DXS[i];
+    m.MY.c = s.MY[i]; m.MX.c = s.MX[i];
+    m.UYN.l = m.UYN.r = m.UYS.l = m.UYS.r = m.UXN.l = m.UXN.r = m.UXS.l = m.UXS.r = 0u;
+    m.DYN.l = m.DYN.r = m.DYS.l = m.DYS.r = m.DXN.l = m.DXN.r = m.DXS.l = m.DXS.r = 0u;
+    m.MY.l = m.MY.r = m.MX.l = m.MX.r = 0u;
+    if (diag) {
+      m.UYN = w3(s.UYN, r, c); m.UXN = w3(s.UXN, r, c); m.MY = w3(s.MY, r, c); m.MX = w3(s.MX, r, c);
+    }
     return m;
   }
   // p1: car planes of every owned word, arrival masks for the colour pass, RNG draws, leak count
@@ -328,8 +402,22 @@ struct MTile {
       int r = tr + 1, c = tc + 1;
       int y = y0 + tr, w = w0 + tc;
       if (y >= g.gh || w >= g.pitch) { s.AY[i] = 0; s.AX[i] = 0; continue; }
+      size_t go = (size_t)y * g.pitch + w;
+      {  // fast path: no car in this word, above, below, or in the two adjacent cells -> nothing moves here
+        int ci = idx(r, c);
+        u32 cars = s.DYN[ci] | s.DXN[ci] | s.DYN[ci - SW] | s.DXN[ci - SW] | s.DYN[ci + SW] | s.DXN[ci + SW] |
+                   ((s.DYN[ci - 1] | s.DXN[ci - 1]) >> 31) | ((s.DYN[ci + 1] | s.DXN[ci + 1]) & 1u);
+        if (cars == 0u) {
+          U4 z = {0, 0, 0, 0};
+          g.head_out[go] = z;
+          s.AY[i] = 0; s.AX[i] = 0;
+          if (leak_plane) leak_plane[go] = 0;
+          continue;
+        }
+      }
       Edge e = edge_masks(y, w, g.gh, g.gw);
-      MPre p = m_pre(mrow(r - 1, c), mrow(r, c), mrow(r + 1, c), e);
+      bool diag = (s.DYN[idx(r, c)] & s.DXN[idx(r, c)]) != 0u;
+      MPre p = m_pre(mrow_side(r - 1, c, diag), mrow_center(r, c), mrow_side(r + 1, c, diag), e);
       u32 CH = 0;
       u32 fk = p.fork & e.valid;
       if (fk) {
@@ -348,7 +436,6 @@ struct MTile {
         }
       }
       MOut o = m_post(p, CH);
-      size_t go = (size_t)y * g.pitch + w;
       U4 hd = {o.DYN, o.DYS, o.DXN, o.DXS};
       g.head_out[go] = hd;
       s.AY[i] = o.AY; s.AX[i] = o.AX;

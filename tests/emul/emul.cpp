@@ -59,23 +59,38 @@ bool run_u_tile(const GridView &g, int ty, int tx, bool first, int nt, int *res_
   for (int tid = 0; tid < nt; tid++) t.p0(tid, nt);
   for (int tid = 0; tid < nt; tid++) t.p1(tid, nt);
   for (int tid = 0; tid < nt; tid++) t.p2(tid, nt);
+  std::vector<typename UT::Pend> pd(nt);
+  int cur = 0;
   for (;;) {
+    int n = (int)sm->wn[cur];
+    if (n == 0) break;
     bool ch = false;
-    for (int tid = 0; tid < nt; tid++) ch |= t.p3(tid, nt);
+    for (int base = 0; base < n; base += nt) {
+      for (int tid = 0; tid < nt; tid++) t.p3a(tid, cur, base, pd[tid]);   // all reads ...
+      for (int tid = 0; tid < nt; tid++) ch |= t.p3b(cur, pd[tid]);        // ... then all writes
+    }
     (*iters)++;
+    sm->wn[cur] = 0;
+    cur ^= 1;
     if (!ch) break;
   }
   int res = 0;
   for (int tid = 0; tid < nt; tid++) res |= t.p4(tid, nt);
   bool pending = false;
-  if (res & 1) {
+  if ((res & 1) && sm->wn[cur] != 0) {
     for (int tid = 0; tid < nt; tid++) t.p5a(tid, nt);
+    int n = (int)sm->wn[cur];
+    std::vector<int> iw(nt);
+    std::vector<u32> xv(nt);
     for (;;) {
       bool ch = false;
-      for (int tid = 0; tid < nt; tid++) ch |= t.p5b(tid, nt);
+      for (int base = 0; base < n; base += nt) {
+        for (int tid = 0; tid < nt; tid++) xv[tid] = t.p5b_compute(tid, cur, base, iw[tid]);
+        for (int tid = 0; tid < nt; tid++) ch |= t.p5b_commit(iw[tid], xv[tid]);
+      }
       if (!ch) break;
     }
-    for (int tid = 0; tid < nt; tid++) pending |= t.p5c(tid, nt);
+    for (int tid = 0; tid < nt; tid++) pending |= t.p5c(tid, nt, cur);
   }
   *res_out = res;
   delete sm;
