@@ -237,7 +237,7 @@ def main():
     achieved = per_gpu_gcups * B_ALG  # GB/s of algorithmic traffic per GPU
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src,
-                "what": "whole tick (k_u_first + k_u_fix + k_move), 12 algorithmic B per cell-update (SURVEY 8d)",
+                "what": "whole tick (k_u_init + k_u_iter [+ k_rings] + k_move), 12 algorithmic B per cell-update (SURVEY 8d)",
                 "kernel_ms_per_tick": {k: v / prof_ticks for k, v in prof.items()},
                 "dominant_kernel": max(prof, key=prof.get),
                 "dominant_share": max(prof.values()) / prof_total if prof_total else None}
@@ -249,8 +249,9 @@ def main():
                        "grid": [S, S], "mode": args.mode, "rings": int(n_rings),
                        "parallelism": "1 grid" if world == 1 else f"{world} independent {S}x{S} grids (one per GPU)",
                        "l2": f"state {cells * 9.75 / 1e9:.2f} GB per tick >> 126 MB L2: inputs larger than L2, no flush"},
-            "fixpoint": {"passes_per_tick": st["passes"] / max(1, st["ticks"]),
-                         "sweeps_per_tile_visit": st["sweeps"] / max(1, st["passes"]) / max(1, (S // 48 + 1) * (S // 1024))},
+            "fixpoint": {"iterations_per_tick": st["passes"] / max(1, st["ticks"]),
+                         "worklist_entries_relaxed_per_tick": st["sweeps"] / max(1, st["ticks"]),
+                         "plane_words": (S // 32) * S},
             "roofline": roofline, "clocks": clocks, "gpu_launches": (3 + (1 if perfect and n_rings else 0)) * args.steps,
             "e2e": e2e}
     if rank == 0 and not args.no_cpu and world >= 1:

@@ -23,7 +23,7 @@ struct flowamok_context {
   cudaStream_t stream;
   bool own_stream;
   int num_sms;
-  int fix_blocks;  // co-resident CTAs of k_u_fix
+  int iter_blocks; // co-resident CTAs of k_u_iter
   std::string err;
 };
 
@@ -32,7 +32,8 @@ struct flowamok_grid {
   int gh, gw, pitch, wvalid;
   size_t nwords, ncells_p;  // plane words, pitched cells
   U4 *road, *head[2];
-  u32 *pref[2], *calc, *my, *mx, *color[2], *leak_plane;
+  u32 *pref[2], *calc, *color[2], *leak_plane;
+  u64 *mymx;
   u64 *rng;
   u64 rng_inc;
   int cur;
@@ -46,10 +47,12 @@ struct flowamok_grid {
   std::vector<int64_t> h_off, h_y, h_x;  // host copy for flowamok_get_cycles_dense
   std::vector<int8_t> h_cy, h_cx;
   // per-tick machinery
-  FixState *fs;
+  IterState *is;
   Diag *diag;
   Diag *h_diag;  // pinned
-  unsigned int *pend[2];
+  UEntry *table;          // worklist entries of the tick (at most one per plane word)
+  unsigned int *qlist[2]; // frontier lists (entry indices), ping-pong
+  u32 *ustate;            // per word: U_NONE or entry index (| U_QUEUED)
   int ntx, nty, mtx, mty;
   Diag base;  // diag values already reported
 };
@@ -95,13 +98,11 @@ int flowamok_context_new(flowamok_context **out, int device, void *stream) {
   ctx->num_sms = prop.multiProcessorCount;
   if (stream) ctx->stream = (cudaStream_t)stream;
   else { CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
-  CU(cudaFuncSetAttribute(k_u_first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UT::Smem)));
-  CU(cudaFuncSetAttribute(k_u_fix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(UT::Smem)));
   CU(cudaFuncSetAttribute(k_move, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MoveSmem)));
   int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_u_fix, U_THREADS, sizeof(UT::Smem)));
-  if (per_sm < 1) return fail(ctx, "k_u_fix does not fit on an SM");
-  ctx->fix_blocks = per_sm * ctx->num_sms;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_u_iter, UIT_THREADS, 0));
+  if (per_sm < 1) return fail(ctx, "k_u_iter does not fit on an SM");
+  ctx->iter_blocks = per_sm * ctx->num_sms;
   return 0;
 }
 
@@ -150,15 +151,15 @@ int flowamok_grid_new(flowamok_context *ctx, flowamok_grid **out, int64_t gh, in
     CU(cudaMalloc(&g->color[k], g->ncells_p * 4));
   }
   CU(cudaMalloc(&g->calc, g->nwords * 4));
-  CU(cudaMalloc(&g->my, g->nwords * 4));
-  CU(cudaMalloc(&g->mx, g->nwords * 4));
+  CU(cudaMalloc(&g->mymx, g->nwords * 8));
   CU(cudaMalloc(&g->rng, g->ncells_p * 8));
-  g->ntx = (g->pitch + UT::TW - 1) / UT::TW; g->nty = (g->gh + UT::TR - 1) / UT::TR;
+  g->ntx = (g->pitch + UIT::TW - 1) / UIT::TW; g->nty = (g->gh + UIT::TR - 1) / UIT::TR;
   g->mtx = (g->pitch + MT::TW - 1) / MT::TW; g->mty = (g->gh + MT::TR - 1) / MT::TR;
-  size_t ntiles = (size_t)g->ntx * g->nty;
-  CU(cudaMalloc(&g->pend[0], ntiles * 4));
-  CU(cudaMalloc(&g->pend[1], ntiles * 4));
-  CU(cudaMalloc(&g->fs, sizeof(FixState)));
+  CU(cudaMalloc(&g->table, g->nwords * sizeof(UEntry)));
+  CU(cudaMalloc(&g->qlist[0], g->nwords * 4));
+  CU(cudaMalloc(&g->qlist[1], g->nwords * 4));
+  CU(cudaMalloc(&g->ustate, g->nwords * 4));
+  CU(cudaMalloc(&g->is, sizeof(IterState)));
   CU(cudaMalloc(&g->diag, sizeof(Diag)));
   CU(cudaMallocHost(&g->h_diag, sizeof(Diag)));
   memset(&g->base, 0, sizeof(Diag));
@@ -170,10 +171,9 @@ int flowamok_grid_new(flowamok_context *ctx, flowamok_grid **out, int64_t gh, in
     CU(cudaMemsetAsync(g->color[k], 0, g->ncells_p * 4, st));
   }
   CU(cudaMemsetAsync(g->calc, 0, g->nwords * 4, st));
-  CU(cudaMemsetAsync(g->my, 0, g->nwords * 4, st));
-  CU(cudaMemsetAsync(g->mx, 0, g->nwords * 4, st));
+  CU(cudaMemsetAsync(g->mymx, 0, g->nwords * 8, st));
   CU(cudaMemsetAsync(g->rng, 0, g->ncells_p * 8, st));
-  CU(cudaMemsetAsync(g->fs, 0, sizeof(FixState), st));
+  CU(cudaMemsetAsync(g->is, 0, sizeof(IterState), st));
   CU(cudaMemsetAsync(g->diag, 0, sizeof(Diag), st));
   CU(cudaStreamSynchronize(st));
   return 0;
@@ -186,8 +186,9 @@ int flowamok_grid_free(flowamok_context *ctx, flowamok_grid *g) {
     cudaStreamSynchronize(ctx->stream);
   }
   cudaFree(g->road);
-  for (int k = 0; k < 2; k++) { cudaFree(g->head[k]); cudaFree(g->pref[k]); cudaFree(g->color[k]); cudaFree(g->pend[k]); }
-  cudaFree(g->calc); cudaFree(g->my); cudaFree(g->mx); cudaFree(g->rng); cudaFree(g->fs); cudaFree(g->diag);
+  for (int k = 0; k < 2; k++) { cudaFree(g->head[k]); cudaFree(g->pref[k]); cudaFree(g->color[k]); }
+  cudaFree(g->calc); cudaFree(g->mymx); cudaFree(g->rng); cudaFree(g->is); cudaFree(g->diag);
+  cudaFree(g->table); cudaFree(g->qlist[0]); cudaFree(g->qlist[1]); cudaFree(g->ustate);
   cudaFree(g->ring_cells); cudaFree(g->ring_off); cudaFree(g->leak_plane);
   cudaFreeHost(g->h_diag);
   delete g;
@@ -495,7 +496,7 @@ static GridView make_view(flowamok_grid *g) {
   v.road = g->road;
   v.head_in = g->head[g->cur]; v.head_out = g->head[g->cur ^ 1];
   v.pref_in = g->pref[g->cur]; v.pref_out = g->pref[g->cur ^ 1];
-  v.calc = g->calc; v.my = g->my; v.mx = g->mx;
+  v.calc = g->calc; v.mymx = g->mymx; v.ustate = g->ustate;
   v.color_in = g->color[g->cur]; v.color_out = g->color[g->cur ^ 1];
   v.rng = g->rng; v.rng_inc = g->rng_inc;
   v.chooser = g->chooser;
@@ -506,16 +507,14 @@ static GridView make_view(flowamok_grid *g) {
 static int enqueue_tick(flowamok_context *ctx, flowamok_grid *g, bool perfect, u32 *leak_plane, cudaEvent_t *ev = nullptr) {
   cudaStream_t st = ctx->stream;
   GridView v = make_view(g);
-  int ntiles = g->ntx * g->nty;
+  int nblocks = g->ntx * g->nty;
   if (ev) CU(cudaEventRecord(ev[0], st));
-  k_u_first<<<ntiles, U_THREADS, sizeof(UT::Smem), st>>>(v, g->ntx, g->diag, g->fs, g->pend[0]);
+  k_u_init<<<nblocks, UIT::NT, 0, st>>>(v, g->ntx, g->table, g->qlist[0], g->is);
   CU(cudaGetLastError());
   {
-    int fixb = std::min(ctx->fix_blocks, std::max(1, ntiles));
-    int ntx = g->ntx;
-    void *args[] = {(void *)&v, (void *)&ntx, (void *)&g->diag, (void *)&g->fs, (void *)&g->pend[0], (void *)&g->pend[1]};
+    void *args[] = {(void *)&v, (void *)&g->table, (void *)&g->qlist[0], (void *)&g->qlist[1], (void *)&g->is, (void *)&g->diag};
     if (ev) CU(cudaEventRecord(ev[1], st));
-    CU(cudaLaunchCooperativeKernel((void *)k_u_fix, dim3(fixb), dim3(U_THREADS), args, sizeof(UT::Smem), st));
+    CU(cudaLaunchCooperativeKernel((void *)k_u_iter, dim3(ctx->iter_blocks), dim3(UIT_THREADS), args, 0, st));
     if (ev) CU(cudaEventRecord(ev[2], st));
   }
   if (perfect && g->n_rings > 0) {
@@ -536,8 +535,8 @@ static int read_diag(flowamok_context *ctx, flowamok_grid *g, Diag *d) {
   CU(cudaStreamSynchronize(ctx->stream));
   *d = *g->h_diag;
   unsigned int err = 0;
-  CU(cudaMemcpy(&err, &g->fs->error, 4, cudaMemcpyDeviceToHost));
-  if (err) return fail(ctx, "grid barrier watchdog tripped in k_u_fix");
+  CU(cudaMemcpy(&err, &g->is->error, 4, cudaMemcpyDeviceToHost));
+  if (err) return fail(ctx, "grid barrier watchdog tripped in k_u_iter");
   return 0;
 }
 

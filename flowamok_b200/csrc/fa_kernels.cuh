@@ -1,15 +1,15 @@
 // flowamok_b200 -- CUDA kernels (sm_100a) of the per-tick grid update.
 //
-// Kernel list (one tick = k_u_first, k_u_fix, [k_rings], k_move):
-//   k_u_first : one CTA per U tile, local least fixpoint of update_can_be_moved_to_from
-//               (steppers.fut:9-56, :147-164) on bit planes staged in shared memory; tiles whose
-//               waiting chains leave their halo are queued.
-//   k_u_fix   : cooperative persistent kernel; iterates the queued tiles under a grid-wide barrier
-//               and a device-side changed/pending flag until the global fixpoint -- no host round
-//               trip per iteration.  Returns immediately when nothing was queued.
+// Kernel list (one tick = k_u_init, k_u_iter, [k_rings], k_move):
+//   k_u_init  : streaming, one thread per plane word (32 cells): statics and initial state of
+//               update_can_be_moved_to_from (steppers.fut:9-56) and compaction of the words that hold
+//               a waiting car into per-CTA worklists.
+//   k_u_iter  : cooperative persistent kernel; relaxes the worklists under a grid-wide barrier and
+//               a device-side changed flag until the global fixpoint (steppers.fut:147-164) -- no
+//               host round trip per iteration, and each iteration touches only unresolved words.
 //   k_rings   : resolve_cycles (steppers.fut:189-224) on the sparse ring list, one thread per ring.
-//   k_move    : move_cell + reset_cells (steppers.fut:58-145): new car planes, colour payload
-//               gather with 128-bit accesses, per-cell pcg32 draws at forks, leak count.
+//   k_move    : move_cell + reset_cells (steppers.fut:58-145): new car planes, colour payload moved
+//               by TMA bulk copies, per-cell pcg32 draws at forks, leak count.
 // plus packing / unpacking / generator / render helpers.
 #pragma once
 #include <cuda_runtime.h>
@@ -18,15 +18,14 @@
 
 namespace fa {
 
-// production tile shapes (tests/emul variant 0 uses the same)
-typedef UTile<48, 32, 4> UT;
 typedef MTile<16, 32> MT;
-constexpr int U_THREADS = 512;
 constexpr int M_THREADS = 512;
+typedef UInitTile<16, 32> UIT;             // k_u_init block: 16 rows x 32 words, one owned word per thread
+constexpr int UIT_THREADS = 512;           // k_u_iter block
 
-struct FixState {
-  unsigned int npend[2];    // queue lengths (ping-pong)
-  unsigned int changed[2];  // progress flags (ping-pong)
+struct IterState {
+  unsigned int n_entries;   // worklist entries written by k_u_init this tick (allocation cursor of the table)
+  unsigned int qn[3];       // frontier lengths: iteration it reads slot it % 3 (k_u_init fills slot 0) and writes (it + 1) % 3
   unsigned int bar[2];      // grid barrier: arrivals, generation
   unsigned int error;       // barrier watchdog tripped
   unsigned int pad;
@@ -34,102 +33,79 @@ struct FixState {
 
 struct Diag {
   unsigned long long leaks;    // summed cell leaks
-  unsigned long long passes;   // fixpoint passes (1 per tick + extra rounds)
-  unsigned long long sweeps;   // local relaxation sweeps over all tiles
+  unsigned long long passes;   // fixpoint iterations of k_u_iter
+  unsigned long long sweeps;   // worklist entries relaxed
   unsigned long long ticks;
 };
 
 // ---------------------------------------------------------------------------------------------
-// U tile driver shared by both fixpoint kernels
+// k_u_init
 // ---------------------------------------------------------------------------------------------
-template <bool FIRST>
-__device__ __forceinline__ void run_u_tile(const GridView &g, UT::Smem &s, int tile_id, int ntx, Diag *diag,
-                                           unsigned int *pend_out, unsigned int *npend_out,
-                                           unsigned int *changed_out) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  UT t(g, s, tile_id / ntx, tile_id % ntx, FIRST);
-  t.p0(tid, nt);
+__global__ void __launch_bounds__(UIT::NT, 2)
+k_u_init(const __grid_constant__ GridView g, int ntx, UEntry *table, unsigned int *qlist0, IterState *is) {
+  __shared__ UIT::Smem s;
+  __shared__ unsigned int wcnt[UIT::TR], wq[UIT::TR];
+  __shared__ unsigned int base_e, base_q;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  UIT tile(g, s, blockIdx.x / ntx, blockIdx.x % ntx);
+  UIT::Own o;
+  tile.pA_own(t, o);
+  if (t < UIT::N_HALO) tile.pA_halo(t);
   __syncthreads();
-  t.p1(tid, nt);
-  __syncthreads();
-  t.p2(tid, nt);
-  __syncthreads();
-  unsigned int sweeps = 0;
-  int cur = 0;
-  for (;;) {  // relaxation sweeps over the worklist of words that still hold a waiting car
-    const int n = (int)s.wn[cur];
-    if (n == 0) break;
-    bool ch = false;
-    for (int base = 0; base < n; base += nt) {
-      UT::Pend pd;
-      t.p3a(tid, cur, base, pd);
-      __syncthreads();
-      ch |= t.p3b(cur, pd);
-      __syncthreads();
-    }
-    sweeps++;
-    int any = __syncthreads_or(ch);
-    if (tid == 0) s.wn[cur] = 0;
-    cur ^= 1;
+  bool converged = false;
+  for (int k = 0; k < UIT::NS; k++) {
+    UState n;
+    const bool ch = tile.sweep_compute(o, n);
+    if (!__syncthreads_or(ch)) { converged = true; break; }   // also: every read of this sweep is done
+    tile.sweep_commit(o, n);
     __syncthreads();
-    if (!any) break;
   }
-  int res = t.p4(tid, nt);
-  int unready = __syncthreads_or(res & 1);
-  int differs = FIRST ? 0 : __syncthreads_or(res & 2);
-  int pending = 0;
-  if (unready && s.wn[cur] != 0) {
-    t.p5a(tid, nt);
-    __syncthreads();
-    const int n = (int)s.wn[cur];
-    for (;;) {
-      bool ch = false;
-      for (int base = 0; base < n; base += nt) {
-        int iw;
-        u32 x = t.p5b_compute(tid, cur, base, iw);
-        __syncthreads();
-        ch |= t.p5b_commit(iw, x);
-        __syncthreads();
-      }
-      if (!__syncthreads_or(ch)) break;
+  UEntry e = {0, 0, 0, 0};
+  const int kind = tile.pC(t, o, converged, e);
+  const unsigned m1 = __ballot_sync(0xFFFFFFFFu, kind >= 1), m2 = __ballot_sync(0xFFFFFFFFu, kind == 2);
+  if (lane == 0) { wcnt[warp] = __popc(m1); wq[warp] = __popc(m2); }
+  __syncthreads();
+  if (t == 0) {  // two global atomics per 512 words
+    unsigned te = 0, tq = 0;
+    for (int k = 0; k < UIT::TR; k++) {
+      unsigned c = wcnt[k]; wcnt[k] = te; te += c;
+      unsigned q = wq[k]; wq[k] = tq; tq += q;
     }
-    pending = __syncthreads_or(t.p5c(tid, nt, cur));
-  }
-  if (tid == 0) {
-    if (pending) pend_out[atomicAdd(npend_out, 1u)] = (unsigned int)tile_id;
-    if (differs) atomicExch(changed_out, 1u);
-    atomicAdd(&diag->sweeps, (unsigned long long)sweeps);
+    base_e = te ? atomicAdd(&is->n_entries, te) : 0u;
+    base_q = tq ? atomicAdd(&is->qn[0], tq) : 0u;
   }
   __syncthreads();
-}
-
-__global__ void __launch_bounds__(U_THREADS, 2)
-k_u_first(const __grid_constant__ GridView g, int ntx, Diag *diag, FixState *fs, unsigned int *pend0) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  UT::Smem &s = *reinterpret_cast<UT::Smem *>(smem_raw);
-  run_u_tile<true>(g, s, blockIdx.x, ntx, diag, pend0, &fs->npend[0], &fs->changed[0]);
+  const unsigned lt = (1u << lane) - 1u;
+  if (kind >= 1) {
+    const unsigned pos = base_e + wcnt[warp] + __popc(m1 & lt);
+    table[pos] = e;
+    g.ustate[e.wi] = kind == 2 ? (pos | U_QUEUED) : pos;
+    if (kind == 2) qlist0[base_q + wq[warp] + __popc(m2 & lt)] = pos;
+  } else if (o.in) {
+    g.ustate[(size_t)o.y * g.pitch + o.w] = U_NONE;
+  }
 }
 
 // Sense-reversing grid barrier; co-residency is guaranteed by the cooperative launch.  A watchdog
 // turns a would-be hang into an error flag.
-__device__ __forceinline__ bool grid_barrier(FixState *fs, unsigned int nblocks) {
+__device__ __forceinline__ bool grid_barrier(IterState *is, unsigned int nblocks) {
   __shared__ int ok;
   __syncthreads();
   if (threadIdx.x == 0) {
     ok = 1;
-    volatile unsigned int *vgen = &fs->bar[1];
+    volatile unsigned int *vgen = &is->bar[1];
     unsigned int gen = *vgen;
     __threadfence();
-    unsigned int prev = atomicAdd(&fs->bar[0], 1u);
+    unsigned int prev = atomicAdd(&is->bar[0], 1u);
     if (prev == nblocks - 1) {
-      atomicExch(&fs->bar[0], 0u);
+      atomicExch(&is->bar[0], 0u);
       __threadfence();
-      atomicAdd(&fs->bar[1], 1u);
+      atomicAdd(&is->bar[1], 1u);
     } else {
       long long spins = 0;
       while (*vgen == gen) {
-        if (++spins > (1LL << 25)) { atomicExch(&fs->error, 1u); ok = 0; break; }
-        __nanosleep(200);
+        if (++spins > (1LL << 25)) { atomicExch(&is->error, 1u); ok = 0; break; }
+        __nanosleep(100);
       }
     }
     __threadfence();
@@ -138,40 +114,70 @@ __device__ __forceinline__ bool grid_barrier(FixState *fs, unsigned int nblocks)
   return ok != 0;
 }
 
-__global__ void __launch_bounds__(U_THREADS, 2)
-k_u_fix(const __grid_constant__ GridView g, int ntx, Diag *diag, FixState *fs, unsigned int *pend0,
-        unsigned int *pend1) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  UT::Smem &s = *reinterpret_cast<UT::Smem *>(smem_raw);
-  volatile FixState *vfs = fs;
-  unsigned int *lists[2] = {pend0, pend1};
-  int in = 0;
-  unsigned long long extra = 0;
-  for (;;) {
-    unsigned int n = vfs->npend[in];
-    if (n == 0) break;
-    const int out = in ^ 1;
-    for (unsigned int t = blockIdx.x; t < n; t += gridDim.x)
-      run_u_tile<false>(g, s, (int)lists[in][t], ntx, diag, lists[out], &fs->npend[out], &fs->changed[out]);
-    extra++;
-    if (!grid_barrier(fs, gridDim.x)) return;
-    unsigned int ch = vfs->changed[out];
-    if (!grid_barrier(fs, gridDim.x)) return;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      fs->npend[in] = 0;
-      fs->changed[in] = 0;
-      if (!ch) { fs->npend[out] = 0; fs->changed[out] = 0; }
-      __threadfence();
+// ---------------------------------------------------------------------------------------------
+// k_u_iter: frontier iterations.  Iteration it visits the entry indices in qlist[it & 1] (k_u_init
+// filled list 0, iteration it-1 the others).  Pushes are staged in shared memory and
+// appended with one global atomic per CTA-chunk.  Ends when an iteration produces an empty list.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(UIT_THREADS, 2)
+k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *qlist0, unsigned int *qlist1,
+         IterState *is, Diag *diag) {
+  __shared__ unsigned int stage[UIT_THREADS * 9];
+  __shared__ unsigned int scnt, gbase;
+  const int tid = threadIdx.x, nt = blockDim.x, b = blockIdx.x, nb = gridDim.x, lane = tid & 31;
+  volatile IterState *vis = is;
+  unsigned int *ql[2] = {qlist0, qlist1};
+  unsigned long long relaxed = 0;
+  unsigned int it = 0;
+  for (;; it++) {
+    const unsigned int n = vis->qn[it % 3u];
+    if (n == 0) break;                       // same value in every CTA: uniform exit
+    const unsigned int *src = ql[it & 1];
+    unsigned int *dst = ql[(it + 1) & 1];
+    unsigned int *out_cnt = &is->qn[(it + 1) % 3u];
+    if (b == 0 && tid == 0) is->qn[(it + 2) % 3u] = 0;   // slot of iteration it+1's output; idle since barrier(it-1)
+    for (unsigned int k0 = (unsigned)b * nt; k0 < n; k0 += (unsigned)nb * nt) {
+      if (tid == 0) scnt = 0;
+      __syncthreads();
+      const unsigned int k = k0 + tid;
+      unsigned int push[9];
+      int np = 0;
+      if (k < n) {
+        const unsigned int idx = src[k];
+        const UEntry e = table[idx];
+        np = u_iter_entry(g, e, idx, push);
+      }
+#pragma unroll
+      for (int j = 0; j < 9; j++) {  // warp-aggregated append to the CTA's staging buffer
+        const bool p = j < np;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, p);
+        if (m) {
+          unsigned bs = 0;
+          if (lane == 0) bs = atomicAdd(&scnt, (unsigned)__popc(m));
+          bs = __shfl_sync(0xFFFFFFFFu, bs, 0);
+          if (p) stage[bs + __popc(m & ((1u << lane) - 1u))] = push[j];
+        }
+      }
+      __syncthreads();
+      const unsigned int sc = scnt;
+      if (sc) {
+        if (tid == 0) gbase = atomicAdd(out_cnt, sc);
+        __syncthreads();
+        for (unsigned int i = tid; i < sc; i += nt) dst[gbase + i] = stage[i];
+      }
+      __syncthreads();
     }
-    if (!grid_barrier(fs, gridDim.x)) return;
-    if (!ch) break;  // a whole pass without progress: global fixpoint (cars queued behind a full ring)
-    in = out;
+    relaxed += (n + nb - 1) / nb;
+    if (!grid_barrier(is, nb)) return;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    // nobody reads the flags outside a round; leave them clean for the next tick
-    fs->npend[0] = 0; fs->npend[1] = 0; fs->changed[0] = 0; fs->changed[1] = 0;
-    atomicAdd(&diag->passes, 1ull + extra);
-    atomicAdd(&diag->ticks, 1ull);
+  if (tid == 0) {
+    atomicAdd(&diag->sweeps, relaxed);
+    if (b == 0) {
+      is->n_entries = 0;
+      is->qn[0] = 0; is->qn[1] = 0; is->qn[2] = 0;   // the slot everyone just read is 0 already
+      atomicAdd(&diag->passes, (unsigned long long)it);
+      atomicAdd(&diag->ticks, 1ull);
+    }
   }
 }
 
@@ -203,7 +209,7 @@ __global__ void k_rings(const __grid_constant__ GridView g, const unsigned long 
   for (unsigned long long t = b; t < e; t++) {
     unsigned long long c = cells[t];
     unsigned int wi = (unsigned int)c, bit = 1u << ((c >> 32) & 31u);
-    atomicOr(((c >> 39) & 1ull) ? &g.mx[wi] : &g.my[wi], bit);
+    atomicOr(reinterpret_cast<unsigned int *>(&g.mymx[wi]) + ((c >> 39) & 1ull), bit);  // low word my, high word mx
   }
 }
 

@@ -4,22 +4,9 @@
 // strided set of words and phases are separated by a block barrier.  The CUDA kernels
 // (fa_kernels.cu) call phase(threadIdx.x, blockDim.x) with __syncthreads() between phases; the CPU
 // emulation used by tests/emul runs the same phases with a loop over tid.  So the bit logic, the
-// indexing, the halo/outer-ring bookkeeping and the pending/changed protocol are all unit-tested
+// indexing and the worklist protocol are all unit-tested
 // on the CPU against the oracle before they ever reach a GPU.
 //
-// Geometry of the U (fixpoint) tile, in words (32 cells) and rows:
-//
-//        c = 0        1 .. TW          TW+1
-//      +--------+-------------------+--------+   r = 0            outer ring row (not computed)
-//      | halo   |                   | halo   |   r = 1 .. H       computed halo rows
-//      | word   |   tile interior   | word   |   r = H+1 .. H+TR  tile rows (owned, written back)
-//      | 31 bits|                   | 31 bits|   r = H+TR+1 ..    computed halo rows
-//      +--------+-------------------+--------+   r = SR-1         outer ring row
-//   The outermost bit of each halo word and the two outer rows form the "outer ring": their
-//   CALC/MY/MX come from the global planes (previous pass; zero in pass 1) and are never updated.
-//   Everything else is recomputed locally to its least fixpoint (steppers.fut:147-164 is confluent,
-//   SURVEY 8a-U), so a chain of waiting cars is resolved inside one tile visit unless it runs more
-//   than H rows / 31 columns past the tile, in which case the tile is queued for another pass.
 #pragma once
 #include "fa_bits.h"
 
@@ -42,7 +29,9 @@ struct GridView {
   U4 *head_out;      // state after the tick
   const u32 *pref_in;
   u32 *pref_out;
-  u32 *calc, *my, *mx;     // per-tick planes (steppers.fut:140-145 resets them: here they are scratch)
+  u32 *calc;               // per-tick plane `calculated` (steppers.fut:140-145 resets it: here it is scratch)
+  u64 *mymx;               // per-tick planes direction.y (low word) / direction.x (high word), one 64-bit access
+  u32 *ustate;             // per word: U_NONE, or its worklist entry index (| U_QUEUED while on the next list)
   const u32 *color_in;     // [gh][pitch*32] argb payload
   u32 *color_out;
   u64 *rng;                // [gh][pitch*32] pcg32 state of each cell (inc is shared, utils.fut:15)
@@ -51,23 +40,24 @@ struct GridView {
   u32 tape_bit;            // CHOOSE_TAPE: this tick's choice
 };
 
-struct TickCounters {
-  unsigned long long leaks;      // cell leaks of this tick (explorer.fut:125 only needs the count)
-  unsigned int n_pending;        // tiles queued for the next fixpoint pass
-  unsigned int changed;          // a queued tile made progress in this pass
-  unsigned int u_iters;          // total local relaxation sweeps (diagnostics)
-  unsigned int passes;           // fixpoint passes executed this tick (diagnostics)
-};
-
 #if defined(__CUDA_ARCH__)
 #define FA_ATOMIC_ADD_U32(p, v) atomicAdd((p), (v))
 #define FA_ATOMIC_ADD_U64(p, v) atomicAdd((p), (v))
 #define FA_ATOMIC_OR_U32(p, v) atomicOr((p), (v))
+#define FA_ATOMIC_AND_U32(p, v) atomicAnd((p), (v))
+#define FA_ATOMIC_CAS_U32(p, c, v) atomicCAS((p), (c), (v))
+#define FA_ATOMIC_OR_U64(p, v) atomicOr((unsigned long long *)(p), (unsigned long long)(v))
 #else
 template <class T> inline T fa_host_add(T *p, T v) { T o = *p; *p = o + v; return o; }
 #define FA_ATOMIC_ADD_U32(p, v) fa_host_add<unsigned int>((p), (v))
 #define FA_ATOMIC_ADD_U64(p, v) fa_host_add<unsigned long long>((p), (v))
-#define FA_ATOMIC_OR_U32(p, v) (*(p) |= (v))
+template <class T> inline T fa_host_or(T *p, T v) { T o = *p; *p = o | v; return o; }
+template <class T> inline T fa_host_and(T *p, T v) { T o = *p; *p = o & v; return o; }
+#define FA_ATOMIC_OR_U32(p, v) fa_host_or<unsigned int>((p), (v))
+#define FA_ATOMIC_AND_U32(p, v) fa_host_and<unsigned int>((p), (v))
+inline unsigned int fa_host_cas(unsigned int *p, unsigned int c, unsigned int v) { unsigned int o = *p; if (o == c) *p = v; return o; }
+#define FA_ATOMIC_CAS_U32(p, c, v) fa_host_cas((p), (c), (v))
+#define FA_ATOMIC_OR_U64(p, v) fa_host_or<unsigned long long>((unsigned long long *)(p), (unsigned long long)(v))
 #endif
 
 FA_HD int popc32(u32 v) {
@@ -86,251 +76,279 @@ FA_HD int ffs32(u32 v) {  // index of lowest set bit, v != 0
 }
 
 // =============================================================================================
-// U tile: local least fixpoint of update_can_be_moved_to_from (steppers.fut:9-56, :147-164)
+// U phase: least fixpoint of update_can_be_moved_to_from (steppers.fut:9-56, :147-164)
 //
-// Only words that hold a waiting car ("link" cells: occupied, successor in bounds and on a road) can
-// ever change after initialisation, so they are compacted into a worklist in shared memory and the
-// relaxation sweeps touch nothing else.  A sweep is compute -> barrier -> commit -> barrier, which
-// makes every committed word a consistent (R, MY, MX) triple: a cell with R = 1 has final MY/MX.
+//   UInitTile   : every word once (k_u_init): statics, initial state (terminals calculated), a few
+//                 relaxation sweeps inside the block in shared memory, and a worklist entry for each
+//                 word that still holds an unresolved waiting car ("link" cell: occupied, successor in
+//                 bounds and on a road).
+//   u_iter_entry: one monotone relaxation of a worklist entry against the CURRENT global planes
+//                 (k_u_iter, frontier discipline).
+//
+// Only link cells can change after initialisation, so the iterations touch nothing else.  Confluence
+//  makes any relaxation order reach the reference's Jacobi result.  A word's state is
+// published my/mx first, calc last, and read calc first: whoever sees calc = 1 sees the final my/mx.
 // =============================================================================================
-FA_HD void fa_fence_block() {
-#if defined(__CUDA_ARCH__)
-  __threadfence_block();
-#endif
-}
 FA_HD void fa_fence_device() {
 #if defined(__CUDA_ARCH__)
   __threadfence();
 #endif
 }
-// append v to list if pred (warp-aggregated on the device)
-FA_HD void wl_push(unsigned short *list, unsigned int *cnt, bool pred, unsigned short v) {
-#if defined(__CUDA_ARCH__)
-  unsigned act = __activemask();
-  unsigned m = __ballot_sync(act, pred);
-  if (m) {
-    int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-    unsigned base = 0;
-    if (lane == leader) base = atomicAdd(cnt, (unsigned)__popc(m));
-    base = __shfl_sync(act, base, leader);
-    if (pred) list[base + __popc(m & ((1u << lane) - 1u))] = v;
+FA_HD u64 pack_mymx(u32 my, u32 mx) { return (u64)my | ((u64)mx << 32); }
+
+constexpr u32 U_NONE = 0xFFFFFFFFu;    // word has no unresolved waiting car
+constexpr u32 U_QUEUED = 0x80000000u;  // word is already on the next iteration's list
+
+struct alignas(16) UEntry {  // 16 bytes: one 128-bit access
+  u32 wi;        // plane word index
+  u32 T, GY, GX; // statics of the word (UStatic.T, GYr, GXr)
+};
+
+// Gathers the 3x3 word neighbourhood of (y, w) straight from the planes (zero outside the grid).
+struct UGather {
+  U4 road, head;
+  u32 pref;
+  W3 road_up, road_c, road_dn;  // UYN | UXN
+  u32 dyn_up, dyn_dn;
+  W3 dxn;
+};
+FA_HD UGather u_gather(const GridView &g, int y, int w) {
+  UGather q;
+  auto ld_road = [&](int yy, int ww) -> u32 {
+    if (yy < 0 || yy >= g.gh || ww < 0 || ww >= g.pitch) return 0u;
+    U4 r = g.road[(size_t)yy * g.pitch + ww];
+    return r.x | r.z;
+  };
+  auto ld_head = [&](int yy, int ww) -> U4 {
+    U4 z = {0, 0, 0, 0};
+    if (yy < 0 || yy >= g.gh || ww < 0 || ww >= g.pitch) return z;
+    return g.head_in[(size_t)yy * g.pitch + ww];
+  };
+  size_t o = (size_t)y * g.pitch + w;
+  q.road = g.road[o]; q.head = g.head_in[o]; q.pref = g.pref_in[o];
+  q.road_c.c = q.road.x | q.road.z; q.road_c.l = ld_road(y, w - 1); q.road_c.r = ld_road(y, w + 1);
+  q.road_up.c = ld_road(y - 1, w); q.road_dn.c = ld_road(y + 1, w);
+  q.road_up.l = q.road_up.r = q.road_dn.l = q.road_dn.r = 0u;
+  if (q.head.x & q.head.z) {  // a diagonal heading in this word: corner cells matter
+    q.road_up.l = ld_road(y - 1, w - 1); q.road_up.r = ld_road(y - 1, w + 1);
+    q.road_dn.l = ld_road(y + 1, w - 1); q.road_dn.r = ld_road(y + 1, w + 1);
   }
-#else
-  if (pred) list[(*cnt)++] = v;
-#endif
+  q.dyn_up = ld_head(y - 1, w).x; q.dyn_dn = ld_head(y + 1, w).x;
+  q.dxn.c = q.head.z; q.dxn.l = ld_head(y, w - 1).z; q.dxn.r = ld_head(y, w + 1).z;
+  return q;
 }
 
-template <int TR_, int TW_, int H_>
-struct UTile {
-  static constexpr int TR = TR_, TW = TW_, H = H_;
-  static constexpr int SR = TR + 2 * H + 2;
-  static constexpr int SW = TW + 2;
-  static constexpr int NW = SR * SW;
+// k_u_init block program: one block owns TR x TW words and sees one halo word all round.
+//   pA: statics + initial state (terminals calculated) of every region word, in shared memory
+//   sweeps (<= NS): relax the owned words against the shared-memory neighbourhood; halo words keep
+//       their initial state, so everything stays a valid lower bound of the fixpoint
+//   pC: publish the owned words; a word that still holds an uncalculated link cell gets a worklist
+//       entry.  It starts on the frontier only if it touches the halo or the block did not converge;
+//       otherwise it is dormant: consistent with all its neighbours, it can only change after one of
+//       them does, and that neighbour will wake it.
+template <int TR_, int TW_>
+struct UInitTile {
+  static constexpr int TR = TR_, TW = TW_, SR = TR + 2, SW = TW + 2, NW = SR * SW, NT = TR * TW, NS = 8;
   struct Smem {
-    u32 DYN[NW], DYS[NW], DXN[NW], DXS[NW];
-    u32 T[NW], GY[NW], GX[NW];
-    u32 R[NW], MY[NW], MX[NW];   // R doubles as ROAD staging during p0/p1; MY as the taint plane in p5
-    unsigned short wl[2][NW];    // worklists of active words (ping-pong)
-    unsigned int wn[2];
+    u32 T[NW], GY[NW], GX[NW], R[NW], MY[NW], MX[NW];
   };
-  struct Pend {  // a thread's computed-but-uncommitted word of the current sweep
-    int i;
-    u32 R, MY, MX;
-    bool changed;
+  struct Own {  // registers of the thread that owns an interior word
+    bool in;
+    int y, w, si;
+    UStatic st;
+    u32 valid;
+    UState cur;
   };
-
   const GridView &g;
   Smem &s;
-  int y0, w0;      // first tile row / word
-  bool first_pass; // outer ring unknown (all zero) instead of read from the global planes
-
-  FA_HD UTile(const GridView &g_, Smem &s_, int tile_y, int tile_w, bool first)
-      : g(g_), s(s_), y0(tile_y * TR), w0(tile_w * TW), first_pass(first) {}
-
+  int y0, w0;
+  FA_HD UInitTile(const GridView &g_, Smem &s_, int ty, int tx) : g(g_), s(s_), y0(ty * TR), w0(tx * TW) {}
   FA_HD static int idx(int r, int c) { return r * SW + c; }
-  FA_HD int grow(int r) const { return y0 - H - 1 + r; }
-  FA_HD int gword(int c) const { return w0 - 1 + c; }
-  FA_HD bool in_grid(int r, int c) const {
-    int y = grow(r), w = gword(c);
-    return y >= 0 && y < g.gh && w >= 0 && w < g.pitch;
-  }
-  // bits of word (r,c) that this tile recomputes
-  FA_HD static u32 cmask(int r, int c) {
-    if (r == 0 || r == SR - 1) return 0u;
-    if (c == 0) return 0xFFFFFFFEu;
-    if (c == SW - 1) return 0x7FFFFFFFu;
-    return 0xFFFFFFFFu;
-  }
   FA_HD W3 w3(const u32 *p, int r, int c) const {
-    W3 v;
-    v.c = p[idx(r, c)];
-    v.l = c > 0 ? p[idx(r, c - 1)] : 0u;
-    v.r = c < SW - 1 ? p[idx(r, c + 1)] : 0u;
+    W3 v = {p[idx(r, c - 1)], p[idx(r, c)], p[idx(r, c + 1)]};
     return v;
   }
-
-  // p0: stage car planes and the road-presence plane of the whole smem region
-  FA_HD void p0(int tid, int nt) {
-    if (tid == 0) { s.wn[0] = 0; s.wn[1] = 0; }
-    for (int i = tid; i < NW; i += nt) {
-      int r = i / SW, c = i - r * SW;
-      U4 hd = {0, 0, 0, 0};
-      u32 road = 0;
-      if (in_grid(r, c)) {
-        size_t o = (size_t)grow(r) * g.pitch + gword(c);
-        hd = g.head_in[o];
-        U4 rd = g.road[o];
-        road = rd.x | rd.z;
-      }
-      s.DYN[i] = hd.x; s.DYS[i] = hd.y; s.DXN[i] = hd.z; s.DXS[i] = hd.w;
-      s.R[i] = road;
+  // statics of region word i (any word of the (TR+2)x(TW+2) region); returns them for the caller's registers
+  FA_HD UStatic pA_word(int i, Edge &ed, Heading &h, bool &in) {
+    int r = i / SW, c = i - r * SW;
+    int y = y0 - 1 + r, w = w0 - 1 + c;
+    UStatic st = {};
+    in = y >= 0 && y < g.gh && w >= 0 && w < g.pitch;
+    u32 R = 0, MY = 0, MX = 0;
+    ed = edge_masks(y, w, g.gh, g.gw);
+    h = heading(0, 0, 0, 0);
+    if (in) {
+      UGather q = u_gather(g, y, w);
+      st = u_statics(q.road.x, q.road.y, q.road.z, q.road.w, q.head.x, q.head.y, q.head.z, q.head.w, q.pref,
+                     q.road_up, q.road_c, q.road_dn, q.dyn_up, q.dyn_dn, q.dxn, ed);
+      h = heading(q.head.x, q.head.y, q.head.z, q.head.w);
+      R = st.T & ed.valid; MY = R & st.GYr; MX = R & st.GXr;
     }
-  }
-  // p1: statics of every computed word
-  FA_HD void p1(int tid, int nt) {
-    for (int i = tid; i < NW; i += nt) {
-      int r = i / SW, c = i - r * SW;
-      u32 T = 0, GY = 0, GX = 0;
-      if (cmask(r, c) != 0u && in_grid(r, c)) {
-        int y = grow(r), w = gword(c);
-        size_t o = (size_t)y * g.pitch + w;
-        U4 rd = g.road[o];
-        u32 pref = g.pref_in[o];
-        Edge e = edge_masks(y, w, g.gh, g.gw);
-        UStatic st = u_statics(rd.x, rd.y, rd.z, rd.w, s.DYN[i], s.DYS[i], s.DXN[i], s.DXS[i], pref,
-                               w3(s.R, r - 1, c), w3(s.R, r, c), w3(s.R, r + 1, c), s.DYN[idx(r - 1, c)],
-                               s.DYN[idx(r + 1, c)], w3(s.DXN, r, c), e);
-        T = st.T; GY = st.GYr; GX = st.GXr;
-      }
-      s.T[i] = T; s.GY[i] = GY; s.GX[i] = GX;
-    }
-  }
-  // p2: initial state (computed bits start from the terminals, outer bits come from the global planes)
-  //     and the first worklist: every word holding a link cell
-  FA_HD void p2(int tid, int nt) {
-    for (int i0 = 0; i0 < NW; i0 += nt) {
-      int i = i0 + tid;
-      bool act = false;
-      if (i < NW) {
-        int r = i / SW, c = i - r * SW;
-        u32 cm = cmask(r, c);
-        u32 oR = 0, oMY = 0, oMX = 0;
-        if (!first_pass && cm != 0xFFFFFFFFu && in_grid(r, c)) {
-          size_t o = (size_t)grow(r) * g.pitch + gword(c);
-          oR = g.calc[o];       // calc BEFORE my/mx: the writer publishes my/mx first (p4)
-          fa_fence_device();
-          oMY = g.my[o]; oMX = g.mx[o];
-        }
-        u32 T = s.T[i];
-        s.R[i] = (cm & T) | (~cm & oR);
-        s.MY[i] = (cm & T & s.GY[i]) | (~cm & oMY);
-        s.MX[i] = (cm & T & s.GX[i]) | (~cm & oMX);
-        act = (~T & cm) != 0u;
-      }
-      wl_push(s.wl[0], &s.wn[0], act, (unsigned short)i);
-    }
-  }
-  FA_HD UStatic links(int i) const {
-    UStatic st;
-    Heading h = heading(s.DYN[i], s.DYS[i], s.DXN[i], s.DXS[i]);
-    u32 link = ~s.T[i];
-    st.T = s.T[i];
-    st.LN = link & h.cN; st.LS = link & h.cS; st.LW = link & h.cW; st.LE = link & h.cE;
-    st.LNW = link & h.dNW; st.LNE = link & h.dNE; st.LSW = link & h.dSW; st.LSE = link & h.dSE;
-    st.GYr = s.GY[i]; st.GXr = s.GX[i];
+    s.T[i] = st.T; s.GY[i] = st.GYr; s.GX[i] = st.GXr;
+    s.R[i] = R; s.MY[i] = MY; s.MX[i] = MX;
     return st;
   }
-  // p3a: compute the new state of worklist entry (base + tid) of list `cur` (no smem writes)
-  FA_HD void p3a(int tid, int cur, int base, Pend &pd) const {
-    pd.i = -1; pd.changed = false;
-    int k = base + tid;
-    if (k >= (int)s.wn[cur]) return;
-    int i = s.wl[cur][k];
-    int r = i / SW, c = i - r * SW;
-    u32 cm = cmask(r, c);
-    UStatic st = links(i);
-    UState n = u_relax(st, w3(s.R, r - 1, c), w3(s.R, r, c), w3(s.R, r + 1, c), w3(s.MY, r - 1, c),
-                       w3(s.MY, r + 1, c), w3(s.MX, r, c), w3(s.MX, r - 1, c), w3(s.MX, r + 1, c));
-    pd.i = i;
-    pd.R = (cm & n.R) | (~cm & s.R[i]);
-    pd.MY = (cm & n.MY) | (~cm & s.MY[i]);
-    pd.MX = (cm & n.MX) | (~cm & s.MX[i]);
-    pd.changed = pd.R != s.R[i] || pd.MY != s.MY[i] || pd.MX != s.MX[i];
+  // owner thread `t` (0 .. NT-1) of interior word (t / TW, t % TW)
+  FA_HD void pA_own(int t, Own &o) {
+    int tr = t / TW, tc = t - tr * TW;
+    o.si = idx(tr + 1, tc + 1);
+    o.y = y0 + tr; o.w = w0 + tc;
+    Edge ed; Heading h;
+    o.st = pA_word(o.si, ed, h, o.in);
+    o.valid = ed.valid;
+    u32 link = ~o.st.T;
+    o.st.LN = link & h.cN; o.st.LS = link & h.cS; o.st.LW = link & h.cW; o.st.LE = link & h.cE;
+    o.st.LNW = link & h.dNW; o.st.LNE = link & h.dNE; o.st.LSW = link & h.dSW; o.st.LSE = link & h.dSE;
+    o.cur.R = s.R[o.si]; o.cur.MY = s.MY[o.si]; o.cur.MX = s.MX[o.si];
   }
-  // p3b: commit, and keep the word on the next list while it still holds an uncalculated link cell
-  FA_HD bool p3b(int cur, const Pend &pd) {
-    bool keep = false;
-    if (pd.i >= 0) {
-      if (pd.changed) { s.R[pd.i] = pd.R; s.MY[pd.i] = pd.MY; s.MX[pd.i] = pd.MX; }
-      int r = pd.i / SW, c = pd.i - r * SW;
-      keep = (~pd.R & ~s.T[pd.i] & cmask(r, c)) != 0u;
-    }
-    wl_push(s.wl[cur ^ 1], &s.wn[cur ^ 1], keep, (unsigned short)(pd.i >= 0 ? pd.i : 0));
-    return pd.changed;
+  // halo words are computed by the first threads in a second round: region words not owned by anybody
+  FA_HD void pA_halo(int t) {
+    // enumerate halo word number t: top row, bottom row, then left/right columns
+    int i;
+    if (t < SW) i = idx(0, t);
+    else if (t < 2 * SW) i = idx(SR - 1, t - SW);
+    else if (t < 2 * SW + TR) i = idx(t - 2 * SW + 1, 0);
+    else if (t < 2 * SW + 2 * TR) i = idx(t - 2 * SW - TR + 1, SW - 1);
+    else return;
+    Edge ed; Heading h; bool in;
+    (void)pA_word(i, ed, h, in);
   }
-  // p4: write the tile's own words; returns bit0 = some owned cell is still uncalculated,
-  //     bit1 = the written planes differ from what the previous pass left in global memory
-  FA_HD int p4(int tid, int nt) {
-    int res = 0;
-    for (int i = tid; i < TR * TW; i += nt) {
-      int tr = i / TW, tc = i - tr * TW;
-      int r = tr + H + 1, c = tc + 1;
-      int y = grow(r), w = gword(c);
-      if (y >= g.gh || w >= g.pitch) continue;
-      int si = idx(r, c);
-      size_t o = (size_t)y * g.pitch + w;
-      Edge e = edge_masks(y, w, g.gh, g.gw);
-      u32 R = s.R[si] & e.valid, MY = s.MY[si] & e.valid, MX = s.MX[si] & e.valid;
-      if (!first_pass && (g.calc[o] != R || g.my[o] != MY || g.mx[o] != MX)) res |= 2;
-      g.my[o] = MY; g.mx[o] = MX;
-      if (!first_pass) fa_fence_device();   // concurrent readers (p2 of a neighbour) must never see calc without its my/mx
-      g.calc[o] = R;
-      U4 rd = g.road[o];
-      UState f = {R, MY, MX};
-      UStatic dummy = {};
-      g.pref_out[o] = u_pref_next(rd.x | rd.z, g.pref_in[o], f, dummy) & e.valid;
-      if ((~R & e.valid) != 0u) res |= 1;
-    }
-    return res;
+  static constexpr int N_HALO = 2 * (TW + 2) + 2 * TR;
+  // one sweep: compute from shared memory (no writes) ...
+  FA_HD bool sweep_compute(Own &o, UState &n) const {
+    n = o.cur;
+    if (!o.in || (~o.st.T & o.valid) == 0u) return false;
+    int r = o.si / SW, c = o.si - r * SW;
+    n = u_relax(o.st, w3(s.R, r - 1, c), w3(s.R, r, c), w3(s.R, r + 1, c), w3(s.MY, r - 1, c), w3(s.MY, r + 1, c),
+                w3(s.MX, r, c), w3(s.MX, r - 1, c), w3(s.MX, r + 1, c));
+    n.R &= o.valid; n.MY &= o.valid; n.MX &= o.valid;
+    return n.R != o.cur.R || n.MY != o.cur.MY || n.MX != o.cur.MX;
   }
-  // p5: does an uncalculated owned cell wait (transitively) on an uncalculated OUTER cell?  Only words
-  // still on the worklist (list `cur`) can be tainted.  The taint plane reuses MY (dead after p4).
-  FA_HD void p5a(int tid, int nt) {
-    for (int i = tid; i < NW; i += nt) {
-      int r = i / SW, c = i - r * SW;
-      s.MY[i] = ~cmask(r, c) & ~s.R[i];
-    }
+  // ... then commit
+  FA_HD void sweep_commit(Own &o, const UState &n) {
+    if (!o.in) return;
+    o.cur = n;
+    s.R[o.si] = n.R; s.MY[o.si] = n.MY; s.MX[o.si] = n.MX;
   }
-  FA_HD u32 p5b_compute(int tid, int cur, int base, int &iw) const {
-    iw = -1;
-    int k = base + tid;
-    if (k >= (int)s.wn[cur]) return 0u;
-    int i = s.wl[cur][k];
-    int r = i / SW, c = i - r * SW;
-    UStatic st = links(i);
-    W3 Xu = w3(s.MY, r - 1, c), Xc = w3(s.MY, r, c), Xd = w3(s.MY, r + 1, c);
-    u32 x = (st.LN & Xu.c) | (st.LS & Xd.c) | (st.LW & west(Xc)) | (st.LE & east(Xc)) |
-            (st.LNW & west(Xu)) | (st.LNE & east(Xu)) | (st.LSW & west(Xd)) | (st.LSE & east(Xd));
-    iw = i;
-    return s.MY[i] | (cmask(r, c) & x);
-  }
-  FA_HD bool p5b_commit(int iw, u32 x) {
-    if (iw < 0 || x == s.MY[iw]) return false;
-    s.MY[iw] = x;
-    return true;
-  }
-  FA_HD bool p5c(int tid, int nt, int cur) const {
-    bool pending = false;
-    for (int k = tid; k < (int)s.wn[cur]; k += nt) {
-      int i = s.wl[cur][k];
-      int r = i / SW, c = i - r * SW;
-      if (r < H + 1 || r >= H + 1 + TR || c < 1 || c > TW) continue;  // not an owned word
-      Edge e = edge_masks(grow(r), gword(c), g.gh, g.gw);
-      if ((s.MY[i] & e.valid) != 0u) pending = true;
-    }
-    return pending;
+  // publish; returns 0 = no entry, 1 = dormant entry, 2 = entry that starts on the frontier
+  FA_HD int pC(int t, const Own &o, bool converged, UEntry &e) const {
+    if (!o.in) return 0;
+    size_t off = (size_t)o.y * g.pitch + o.w;
+    g.mymx[off] = pack_mymx(o.cur.MY, o.cur.MX);
+    g.calc[off] = o.cur.R;
+    e.wi = (u32)off; e.T = o.st.T; e.GY = o.st.GYr; e.GX = o.st.GXr;
+    if ((~o.cur.R & ~o.st.T & o.valid) == 0u) return 0;
+    int tr = t / TW, tc = t - tr * TW;
+    bool border = tr == 0 || tr == TR - 1 || tc == 0 || tc == TW - 1;
+    return (border || !converged) ? 2 : 1;
   }
 };
+
+struct UPlanes {  // calc / my / mx of one word
+  u32 R, MY, MX;
+};
+FA_HD size_t u_off(const GridView &g, int y, int w, bool &ok) {
+  ok = !(y < 0 || y >= g.gh || w < 0 || w >= g.pitch);
+  return ok ? (size_t)y * g.pitch + w : 0;
+}
+FA_HD u32 u_ld_calc(const GridView &g, size_t o, bool ok) {
+  if (!ok) return 0u;
+#if defined(__CUDA_ARCH__)
+  return *(volatile const u32 *)&g.calc[o];
+#else
+  return g.calc[o];
+#endif
+}
+FA_HD void u_ld_mymx(const GridView &g, size_t o, bool ok, UPlanes &p) {
+  u64 m = 0;
+  if (ok) {
+#if defined(__CUDA_ARCH__)
+    m = *(volatile const u64 *)&g.mymx[o];
+#else
+    m = g.mymx[o];
+#endif
+  }
+  p.MY = (u32)m; p.MX = (u32)(m >> 32);
+}
+
+// Put word (y, w) on the next list unless it has nothing unresolved or is queued already.
+// Returns its entry index, or U_NONE.
+FA_HD u32 u_try_queue(const GridView &g, int y, int w) {
+  if (y < 0 || y >= g.gh || w < 0 || w >= g.pitch) return U_NONE;
+  size_t o = (size_t)y * g.pitch + w;
+#if defined(__CUDA_ARCH__)
+  u32 sv = *(volatile const u32 *)&g.ustate[o];
+#else
+  u32 sv = g.ustate[o];
+#endif
+  if (sv == U_NONE || (sv & U_QUEUED)) return U_NONE;
+  u32 old = FA_ATOMIC_OR_U32(&g.ustate[o], U_QUEUED);
+  if (old == U_NONE || (old & U_QUEUED)) return U_NONE;
+  return old;
+}
+
+// One relaxation of worklist entry `e` against the current planes (frontier discipline):
+//   clear QUEUED, re-read the neighbourhood, OR the new facts in (my/mx before calc);
+//   if anything changed, wake the eight neighbouring words (their waiting cars may point here)
+//   and this word itself while it still holds an uncalculated link cell;
+//   a word nobody changes is left dormant -- cars queued behind a full ring cost one visit per tick.
+// push[] receives up to 9 entry indices for the next list; returns their number.
+FA_HD int u_iter_entry(const GridView &g, const UEntry &e, u32 idx, u32 *push) {
+  int y = (int)(e.wi / (u32)g.pitch), w = (int)(e.wi - (u32)y * (u32)g.pitch);
+  FA_ATOMIC_AND_U32(&g.ustate[e.wi], ~U_QUEUED);
+  fa_fence_device();
+  U4 hd = g.head_in[e.wi];
+  Heading h = heading(hd.x, hd.y, hd.z, hd.w);
+  UStatic st;
+  u32 link = ~e.T;
+  st.T = e.T; st.GYr = e.GY; st.GXr = e.GX;
+  st.LN = link & h.cN; st.LS = link & h.cS; st.LW = link & h.cW; st.LE = link & h.cE;
+  st.LNW = link & h.dNW; st.LNE = link & h.dNE; st.LSW = link & h.dSW; st.LSE = link & h.dSE;
+  bool diag = (st.LNW | st.LNE | st.LSW | st.LSE) != 0u;
+  // which of the 9 words are needed; all `calculated` words first, ONE fence, then their my/mx
+  bool need[9];
+  need[4] = true;
+  need[3] = (st.LW & 1u) || diag; need[5] = (st.LE >> 31) || diag;
+  need[1] = (st.LN | st.LNW | st.LNE) != 0u; need[7] = (st.LS | st.LSW | st.LSE) != 0u;
+  need[0] = need[2] = need[6] = need[8] = diag;
+  UPlanes nb[9];
+  size_t off[9];
+  bool ok[9];
+  for (int k = 0; k < 9; k++) {
+    nb[k].R = nb[k].MY = nb[k].MX = 0u;
+    ok[k] = false; off[k] = 0;
+    if (need[k]) { off[k] = u_off(g, y + k / 3 - 1, w + k % 3 - 1, ok[k]); nb[k].R = u_ld_calc(g, off[k], ok[k]); }
+  }
+  fa_fence_device();
+  for (int k = 0; k < 9; k++)
+    if (need[k]) u_ld_mymx(g, off[k], ok[k], nb[k]);
+  const UPlanes &ul = nb[0], &up = nb[1], &ur = nb[2], &l = nb[3], &c = nb[4], &r = nb[5], &dl = nb[6], &dn = nb[7], &dr = nb[8];
+  W3 R_up = {ul.R, up.R, ur.R}, R_c = {l.R, c.R, r.R}, R_dn = {dl.R, dn.R, dr.R};
+  W3 MY_up = {ul.MY, up.MY, ur.MY}, MY_dn = {dl.MY, dn.MY, dr.MY};
+  W3 MX_c = {l.MX, c.MX, r.MX}, MX_up = {ul.MX, up.MX, ur.MX}, MX_dn = {dl.MX, dn.MX, dr.MX};
+  UState n = u_relax(st, R_up, R_c, R_dn, MY_up, MY_dn, MX_c, MX_up, MX_dn);
+  const u32 valid = edge_masks(y, w, g.gh, g.gw).valid;
+  n.R = (n.R & valid) | c.R; n.MY = (n.MY & valid) | c.MY; n.MX = (n.MX & valid) | c.MX;   // monotone
+  bool changed = n.R != c.R || n.MY != c.MY || n.MX != c.MX;
+  bool unready = (~n.R & ~e.T) != 0u;
+  int np = 0;
+  if (changed) {
+    FA_ATOMIC_OR_U64(&g.mymx[e.wi], pack_mymx(n.MY, n.MX));
+    fa_fence_device();
+    FA_ATOMIC_OR_U32(&g.calc[e.wi], n.R);
+    fa_fence_device();
+    for (int dy = -1; dy <= 1; dy++)
+      for (int dx = -1; dx <= 1; dx++) {
+        if (dy == 0 && dx == 0 && !unready) continue;
+        u32 q = u_try_queue(g, y + dy, w + dx);
+        if (q != U_NONE) push[np++] = q & ~U_QUEUED;
+      }
+  }
+  // resolved for good: retire the word -- with a CAS, because a neighbour may be queueing it right now (then it
+  // stays queued, gets one idle visit next iteration and is retired there)
+  if (!unready) FA_ATOMIC_CAS_U32(&g.ustate[e.wi], idx, U_NONE);
+  return np;
+}
 
 // =============================================================================================
 // M tile: move_cell + reset_cells (steppers.fut:58-145), colour/aux payload gather, per-cell RNG
@@ -359,7 +377,9 @@ struct MTile {
       u32 my = 0, mx = 0;
       if (y >= 0 && y < g.gh && w >= 0 && w < g.pitch) {
         size_t o = (size_t)y * g.pitch + w;
-        rd = g.road[o]; hd = g.head_in[o]; my = g.my[o]; mx = g.mx[o];
+        rd = g.road[o]; hd = g.head_in[o];
+        u64 m = g.mymx[o];
+        my = (u32)m; mx = (u32)(m >> 32);
       }
       s.UYN[i] = rd.x; s.UYS[i] = rd.y; s.UXN[i] = rd.z; s.UXS[i] = rd.w;
       s.DYN[i] = hd.x; s.DYS[i] = hd.y; s.DXN[i] = hd.z; s.DXS[i] = hd.w;
@@ -403,6 +423,15 @@ struct MTile {
       int y = y0 + tr, w = w0 + tc;
       if (y >= g.gh || w >= g.pitch) { s.AY[i] = 0; s.AX[i] = 0; continue; }
       size_t go = (size_t)y * g.pitch + w;
+      {  // next_preference_flow_x (steppers.fut:41-50): decided by the fixpoint's own grants only; cells a ring
+         // resolution marked (steppers.fut:189-224) have calc = 0 and keep their preference
+        int ci = idx(r, c);
+        u32 cal = g.calc[go];
+        UState f = {cal, s.MY[ci] & cal, s.MX[ci] & cal};
+        UStatic dummy = {};
+        Edge ev = edge_masks(y, w, g.gh, g.gw);
+        g.pref_out[go] = u_pref_next(s.UYN[ci] | s.UXN[ci], g.pref_in[go], f, dummy) & ev.valid;
+      }
       {  // fast path: no car in this word, above, below, or in the two adjacent cells -> nothing moves here
         int ci = idx(r, c);
         u32 cars = s.DYN[ci] | s.DXN[ci] | s.DYN[ci - SW] | s.DXN[ci - SW] | s.DYN[ci + SW] | s.DXN[ci + SW] |

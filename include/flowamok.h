@@ -91,7 +91,7 @@ int flowamok_step_quick(flowamok_context *ctx, flowamok_grid *g, int64_t n_ticks
 int flowamok_step_perfect(flowamok_context *ctx, flowamok_grid *g, int64_t n_ticks, int64_t *n_leaks);
 
 /* Like flowamok_step_*, but brackets every kernel of every tick with CUDA events on the context's stream
- * and returns the summed device time in milliseconds of {k_u_first, k_u_fix, k_rings, k_move}.  Synchronous;
+ * and returns the summed device time in milliseconds of {k_u_init, k_u_iter, k_rings, k_move}.  Synchronous;
  * n_ticks <= 4096.  Measurement aid for bench.py's roofline object, not a reference operator. */
 int flowamok_step_profile(flowamok_context *ctx, flowamok_grid *g, int perfect, int64_t n_ticks, double *ms);
 
@@ -103,7 +103,7 @@ int flowamok_step_leaks(flowamok_context *ctx, flowamok_grid *g, int perfect, in
 /* render (flowamok.fut:16-64) into a host buffer [gh*scale][gw*scale] of argb.  Synchronous. */
 int flowamok_render(flowamok_context *ctx, const flowamok_grid *g, int64_t scale, uint32_t *pixels);
 
-/* diagnostics of the ticks since the last call: fixpoint passes, local relaxation sweeps, ticks */
+/* diagnostics of the ticks since the last call: ticks, fixpoint iterations, worklist entries relaxed */
 int flowamok_stats(flowamok_context *ctx, flowamok_grid *g, int64_t *ticks, int64_t *passes, int64_t *sweeps);
 
 /* Synthetic road network of SURVEY.md App. E (monotone avenue lattice + ring tiles), generated on the

@@ -18,7 +18,9 @@ namespace {
 struct HostGrid {
   int gh, gw, pitch, wvalid;
   std::vector<U4> road, head[2];
-  std::vector<u32> pref[2], calc, my, mx, color[2];
+  std::vector<u32> pref[2], calc, color[2];
+  std::vector<u64> mymx;
+  std::vector<u32> ustate;
   std::vector<u64> rng;
   u64 rng_inc;
   int cur = 0;
@@ -33,7 +35,7 @@ HostGrid *make(int gh, int gw) {
   size_t nw = (size_t)gh * h->pitch, nc = nw * 32;
   h->road.assign(nw, U4{0, 0, 0, 0});
   for (int k = 0; k < 2; k++) { h->head[k].assign(nw, U4{0, 0, 0, 0}); h->pref[k].assign(nw, 0); h->color[k].assign(nc, 0); }
-  h->calc.assign(nw, 0); h->my.assign(nw, 0); h->mx.assign(nw, 0);
+  h->calc.assign(nw, 0); h->mymx.assign(nw, 0); h->ustate.assign(nw, 0);
   h->rng.assign(nc, 0);
   h->rng_inc = 0;
   return h;
@@ -45,56 +47,11 @@ GridView view(HostGrid *h, int chooser, u32 tape_bit) {
   g.road = h->road.data();
   g.head_in = h->head[h->cur].data(); g.head_out = h->head[h->cur ^ 1].data();
   g.pref_in = h->pref[h->cur].data(); g.pref_out = h->pref[h->cur ^ 1].data();
-  g.calc = h->calc.data(); g.my = h->my.data(); g.mx = h->mx.data();
+  g.calc = h->calc.data(); g.mymx = h->mymx.data(); g.ustate = h->ustate.data();
   g.color_in = h->color[h->cur].data(); g.color_out = h->color[h->cur ^ 1].data();
   g.rng = h->rng.data(); g.rng_inc = h->rng_inc;
   g.chooser = chooser; g.tape_bit = tape_bit;
   return g;
-}
-
-template <class UT>
-bool run_u_tile(const GridView &g, int ty, int tx, bool first, int nt, int *res_out, unsigned *iters) {
-  typename UT::Smem *sm = new typename UT::Smem();
-  UT t(g, *sm, ty, tx, first);
-  for (int tid = 0; tid < nt; tid++) t.p0(tid, nt);
-  for (int tid = 0; tid < nt; tid++) t.p1(tid, nt);
-  for (int tid = 0; tid < nt; tid++) t.p2(tid, nt);
-  std::vector<typename UT::Pend> pd(nt);
-  int cur = 0;
-  for (;;) {
-    int n = (int)sm->wn[cur];
-    if (n == 0) break;
-    bool ch = false;
-    for (int base = 0; base < n; base += nt) {
-      for (int tid = 0; tid < nt; tid++) t.p3a(tid, cur, base, pd[tid]);   // all reads ...
-      for (int tid = 0; tid < nt; tid++) ch |= t.p3b(cur, pd[tid]);        // ... then all writes
-    }
-    (*iters)++;
-    sm->wn[cur] = 0;
-    cur ^= 1;
-    if (!ch) break;
-  }
-  int res = 0;
-  for (int tid = 0; tid < nt; tid++) res |= t.p4(tid, nt);
-  bool pending = false;
-  if ((res & 1) && sm->wn[cur] != 0) {
-    for (int tid = 0; tid < nt; tid++) t.p5a(tid, nt);
-    int n = (int)sm->wn[cur];
-    std::vector<int> iw(nt);
-    std::vector<u32> xv(nt);
-    for (;;) {
-      bool ch = false;
-      for (int base = 0; base < n; base += nt) {
-        for (int tid = 0; tid < nt; tid++) xv[tid] = t.p5b_compute(tid, cur, base, iw[tid]);
-        for (int tid = 0; tid < nt; tid++) ch |= t.p5b_commit(iw[tid], xv[tid]);
-      }
-      if (!ch) break;
-    }
-    for (int tid = 0; tid < nt; tid++) pending |= t.p5c(tid, nt, cur);
-  }
-  *res_out = res;
-  delete sm;
-  return pending;
 }
 
 struct Rings {
@@ -104,30 +61,60 @@ struct Rings {
   std::vector<uint8_t> grant;
 };
 
-template <class UT, class MT>
-int64_t tick(HostGrid *h, int chooser, u32 tape_bit, const Rings *rings, int nt, unsigned *stats) {
+// Frontier discipline of k_u_init / k_u_iter: iteration 0 visits every entry, later iterations visit
+// what the previous one queued; stop on an empty list.  `order` varies the processing order inside
+// an iteration (the result must not depend on it).
+template <class MT, class UIT>
+int64_t tick(HostGrid *h, int chooser, u32 tape_bit, const Rings *rings, int nt, unsigned *stats, int order) {
   GridView g = view(h, chooser, tape_bit);
-  int nty = (h->gh + UT::TR - 1) / UT::TR, ntx = (h->pitch + UT::TW - 1) / UT::TW;
-  std::vector<int> pend, next;
-  unsigned iters = 0, passes = 1;
-  for (int ty = 0; ty < nty; ty++)
-    for (int tx = 0; tx < ntx; tx++) {
-      int res;
-      if (run_u_tile<UT>(g, ty, tx, true, nt, &res, &iters)) pend.push_back(ty * ntx + tx);
-    }
-  while (!pend.empty()) {
-    bool changed = false;
-    next.clear();
-    passes++;
-    for (int id : pend) {
-      int res;
-      bool p = run_u_tile<UT>(g, id / ntx, id % ntx, false, nt, &res, &iters);
-      if (res & 2) changed = true;
-      if (p) next.push_back(id);
-    }
-    if (!changed) break;
-    pend.swap(next);
+  std::vector<UEntry> table;
+  std::vector<u32> cur, next;
+  {  // k_u_init: one "block" per UIT tile, NT threads emulated in lock step
+    typename UIT::Smem *sm = new typename UIT::Smem();
+    std::vector<typename UIT::Own> own(UIT::NT);
+    std::vector<UState> nn(UIT::NT);
+    int nty = (h->gh + UIT::TR - 1) / UIT::TR, ntx = (h->pitch + UIT::TW - 1) / UIT::TW;
+    for (int ty = 0; ty < nty; ty++)
+      for (int tx = 0; tx < ntx; tx++) {
+        UIT tile(g, *sm, ty, tx);
+        for (int t = 0; t < UIT::NT; t++) tile.pA_own(t, own[t]);
+        for (int t = 0; t < UIT::N_HALO; t++) tile.pA_halo(t);
+        bool converged = false;
+        for (int k = 0; k < UIT::NS; k++) {
+          bool any = false;
+          for (int t = 0; t < UIT::NT; t++) any |= tile.sweep_compute(own[t], nn[t]);
+          if (!any) { converged = true; break; }
+          for (int t = 0; t < UIT::NT; t++) tile.sweep_commit(own[t], nn[t]);
+        }
+        for (int t = 0; t < UIT::NT; t++) {
+          UEntry e;
+          int kind = tile.pC(t, own[t], converged, e);
+          if (kind >= 1) {
+            u32 pos = (u32)table.size();
+            table.push_back(e);
+            g.ustate[e.wi] = kind == 2 ? (pos | U_QUEUED) : pos;
+            if (kind == 2) cur.push_back(pos);
+          } else if (own[t].in) g.ustate[(size_t)own[t].y * h->pitch + own[t].w] = U_NONE;
+        }
+      }
+    delete sm;
   }
+  unsigned iters = 0, relaxed = 0;
+  while (!cur.empty()) {
+    iters++;
+    next.clear();
+    size_t n = cur.size();
+    for (size_t k = 0; k < n; k++) {
+      size_t kk = order == 2 ? n - 1 - k : (order == 1 ? (k * 7919u) % n : k);
+      if (order == 1 && n % 7919u == 0) kk = k;
+      u32 push[9];
+      int np = u_iter_entry(g, table[cur[kk]], cur[kk], push);
+      relaxed++;
+      for (int j = 0; j < np; j++) next.push_back(push[j]);
+    }
+    cur.swap(next);
+  }
+  (void)nt;
   if (rings) {  // steppers.fut:189-224, sparse form
     size_t n = rings->off.size() - 1;
     std::vector<char> pass(n);
@@ -147,7 +134,7 @@ int64_t tick(HostGrid *h, int chooser, u32 tape_bit, const Rings *rings, int nt,
         for (int64_t t = rings->off[k]; t < rings->off[k + 1]; t++) {
           size_t o = (size_t)rings->y[t] * h->pitch + (rings->x[t] >> 5);
           u32 bit = 1u << (rings->x[t] & 31);
-          if (rings->grant[t] == 1) g.my[o] |= bit; else g.mx[o] |= bit;
+          if (rings->grant[t] == 1) g.mymx[o] |= (u64)bit; else g.mymx[o] |= (u64)bit << 32;
         }
   }
   int64_t leaks = 0;
@@ -163,7 +150,7 @@ int64_t tick(HostGrid *h, int chooser, u32 tape_bit, const Rings *rings, int nt,
     }
   delete sm;
   h->cur ^= 1;
-  if (stats) { stats[0] += passes; stats[1] += iters; }
+  if (stats) { stats[0] += iters; stats[1] += relaxed; }
   return leaks;
 }
 
@@ -226,10 +213,10 @@ int64_t emul_step(void *p, int variant, int nthreads, int chooser, uint32_t tape
     R.cy.assign(cy, cy + tot); R.cx.assign(cx, cx + tot); R.grant.assign(grant, grant + tot);
     rp = &R;
   }
-  switch (variant) {
-  case 1: return tick<UTile<2, 1, 1>, MTile<3, 1>>(h, chooser, tape_bit, rp, nthreads, stats);
-  case 2: return tick<UTile<8, 2, 2>, MTile<4, 2>>(h, chooser, tape_bit, rp, nthreads, stats);
-  default: return tick<UTile<48, 32, 4>, MTile<16, 32>>(h, chooser, tape_bit, rp, nthreads, stats);
+  switch (variant) {  // variant: tile shapes / processing order of the frontier
+  case 1: return tick<MTile<3, 1>, UInitTile<2, 1>>(h, chooser, tape_bit, rp, nthreads, stats, 2);
+  case 2: return tick<MTile<4, 2>, UInitTile<5, 3>>(h, chooser, tape_bit, rp, nthreads, stats, 1);
+  default: return tick<MTile<16, 32>, UInitTile<16, 32>>(h, chooser, tape_bit, rp, nthreads, stats, 0);
   }
 }
 }

@@ -29,7 +29,7 @@ def test_dense_jam_needs_many_passes():
         nl, _ = og.step_quick(ch)
         assert nl == eg.step(variant=1)
         assert_state_equal(state_of(og), eg.state(), f"tick {t}")
-    assert eg.stats[0] > 6          # tiny tiles had to queue extra fixpoint passes
+    assert eg.stats[0] > 6 * 10     # long queues need many worklist iterations
 
 
 @pytest.mark.parametrize("chooser", [O.CHOOSE_Y, O.CHOOSE_X, O.CHOOSE_TAPE])
