@@ -50,8 +50,9 @@ struct flowamok_grid {
   IterState *is;
   Diag *diag;
   Diag *h_diag;  // pinned
-  UEntry *table;          // worklist entries of the tick (at most one per plane word)
-  unsigned int *qlist[2]; // frontier lists (entry indices), ping-pong
+  UEntry *table;          // worklist entries of the tick: k_u_init block b, thread t -> table[b*512 + t]
+  unsigned int *qlist[2]; // frontier lists (entry indices), ping-pong; qlist[0] first holds the per-block segments
+  unsigned int *qcnt;     // per k_u_init block: length of its frontier segment
   u32 *ustate;            // per word: U_NONE or entry index (| U_QUEUED)
   int ntx, nty, mtx, mty;
   Diag base;  // diag values already reported
@@ -155,10 +156,14 @@ int flowamok_grid_new(flowamok_context *ctx, flowamok_grid **out, int64_t gh, in
   CU(cudaMalloc(&g->rng, g->ncells_p * 8));
   g->ntx = (g->pitch + UIT::TW - 1) / UIT::TW; g->nty = (g->gh + UIT::TR - 1) / UIT::TR;
   g->mtx = (g->pitch + MT::TW - 1) / MT::TW; g->mty = (g->gh + MT::TR - 1) / MT::TR;
-  CU(cudaMalloc(&g->table, g->nwords * sizeof(UEntry)));
-  CU(cudaMalloc(&g->qlist[0], g->nwords * 4));
-  CU(cudaMalloc(&g->qlist[1], g->nwords * 4));
-  CU(cudaMalloc(&g->ustate, g->nwords * 4));
+  {
+    size_t nslots = (size_t)g->ntx * g->nty * UIT::NT;   // >= nwords (tiles are padded)
+    CU(cudaMalloc(&g->table, nslots * sizeof(UEntry)));
+    CU(cudaMalloc(&g->qlist[0], nslots * 4));
+    CU(cudaMalloc(&g->qlist[1], nslots * 4));
+    CU(cudaMalloc(&g->qcnt, (size_t)g->ntx * g->nty * 4));
+    CU(cudaMalloc(&g->ustate, g->nwords * 4));
+  }
   CU(cudaMalloc(&g->is, sizeof(IterState)));
   CU(cudaMalloc(&g->diag, sizeof(Diag)));
   CU(cudaMallocHost(&g->h_diag, sizeof(Diag)));
@@ -188,7 +193,7 @@ int flowamok_grid_free(flowamok_context *ctx, flowamok_grid *g) {
   cudaFree(g->road);
   for (int k = 0; k < 2; k++) { cudaFree(g->head[k]); cudaFree(g->pref[k]); cudaFree(g->color[k]); }
   cudaFree(g->calc); cudaFree(g->mymx); cudaFree(g->rng); cudaFree(g->is); cudaFree(g->diag);
-  cudaFree(g->table); cudaFree(g->qlist[0]); cudaFree(g->qlist[1]); cudaFree(g->ustate);
+  cudaFree(g->table); cudaFree(g->qlist[0]); cudaFree(g->qlist[1]); cudaFree(g->qcnt); cudaFree(g->ustate);
   cudaFree(g->ring_cells); cudaFree(g->ring_off); cudaFree(g->leak_plane);
   cudaFreeHost(g->h_diag);
   delete g;
@@ -509,10 +514,11 @@ static int enqueue_tick(flowamok_context *ctx, flowamok_grid *g, bool perfect, u
   GridView v = make_view(g);
   int nblocks = g->ntx * g->nty;
   if (ev) CU(cudaEventRecord(ev[0], st));
-  k_u_init<<<nblocks, UIT::NT, 0, st>>>(v, g->ntx, g->table, g->qlist[0], g->is);
+  k_u_init<<<nblocks, UIT::NT, 0, st>>>(v, g->ntx, g->table, g->qlist[0], g->qcnt);
   CU(cudaGetLastError());
   {
-    void *args[] = {(void *)&v, (void *)&g->table, (void *)&g->qlist[0], (void *)&g->qlist[1], (void *)&g->is, (void *)&g->diag};
+    void *args[] = {(void *)&v, (void *)&g->table, (void *)&g->qlist[0], (void *)&g->qlist[1], (void *)&g->qcnt, (void *)&nblocks,
+                    (void *)&g->is, (void *)&g->diag};
     if (ev) CU(cudaEventRecord(ev[1], st));
     CU(cudaLaunchCooperativeKernel((void *)k_u_iter, dim3(ctx->iter_blocks), dim3(UIT_THREADS), args, 0, st));
     if (ev) CU(cudaEventRecord(ev[2], st));

@@ -18,17 +18,16 @@
 
 namespace fa {
 
-typedef MTile<16, 32> MT;
-constexpr int M_THREADS = 512;
+typedef MTile<8, 32> MT;
+constexpr int M_THREADS = 256;
 typedef UInitTile<16, 32> UIT;             // k_u_init block: 16 rows x 32 words, one owned word per thread
 constexpr int UIT_THREADS = 512;           // k_u_iter block
 
 struct IterState {
-  unsigned int n_entries;   // worklist entries written by k_u_init this tick (allocation cursor of the table)
-  unsigned int qn[3];       // frontier lengths: iteration it reads slot it % 3 (k_u_init fills slot 0) and writes (it + 1) % 3
+  unsigned int qn[3];       // frontier lengths: iteration it >= 1 reads slot it % 3 and writes (it + 1) % 3
   unsigned int bar[2];      // grid barrier: arrivals, generation
   unsigned int error;       // barrier watchdog tripped
-  unsigned int pad;
+  unsigned int pad[2];
 };
 
 struct Diag {
@@ -39,18 +38,20 @@ struct Diag {
 };
 
 // ---------------------------------------------------------------------------------------------
-// k_u_init
+// k_u_init: no global atomics.  Block b owns table[b*NT .. b*NT+NT) (entry of thread t at b*NT+t) and
+// the frontier segment qseg[b*NT .. ) of length qcnt[b].
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(UIT::NT, 2)
-k_u_init(const __grid_constant__ GridView g, int ntx, UEntry *table, unsigned int *qlist0, IterState *is) {
+k_u_init(const __grid_constant__ GridView g, int ntx, UEntry *table, unsigned int *qseg, unsigned int *qcnt) {
   __shared__ UIT::Smem s;
-  __shared__ unsigned int wcnt[UIT::TR], wq[UIT::TR];
-  __shared__ unsigned int base_e, base_q;
+  __shared__ unsigned int wq[UIT::TR];
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   UIT tile(g, s, blockIdx.x / ntx, blockIdx.x % ntx);
+  UIT::Raw own, ring;
+  tile.p0(t, own, ring);
+  __syncthreads();
   UIT::Own o;
-  tile.pA_own(t, o);
-  if (t < UIT::N_HALO) tile.pA_halo(t);
+  tile.pA(t, own, ring, o);
   __syncthreads();
   bool converged = false;
   for (int k = 0; k < UIT::NS; k++) {
@@ -62,28 +63,21 @@ k_u_init(const __grid_constant__ GridView g, int ntx, UEntry *table, unsigned in
   }
   UEntry e = {0, 0, 0, 0};
   const int kind = tile.pC(t, o, converged, e);
-  const unsigned m1 = __ballot_sync(0xFFFFFFFFu, kind >= 1), m2 = __ballot_sync(0xFFFFFFFFu, kind == 2);
-  if (lane == 0) { wcnt[warp] = __popc(m1); wq[warp] = __popc(m2); }
-  __syncthreads();
-  if (t == 0) {  // two global atomics per 512 words
-    unsigned te = 0, tq = 0;
-    for (int k = 0; k < UIT::TR; k++) {
-      unsigned c = wcnt[k]; wcnt[k] = te; te += c;
-      unsigned q = wq[k]; wq[k] = tq; tq += q;
-    }
-    base_e = te ? atomicAdd(&is->n_entries, te) : 0u;
-    base_q = tq ? atomicAdd(&is->qn[0], tq) : 0u;
-  }
-  __syncthreads();
-  const unsigned lt = (1u << lane) - 1u;
+  const unsigned pos = blockIdx.x * (unsigned)UIT::NT + (unsigned)t;
   if (kind >= 1) {
-    const unsigned pos = base_e + wcnt[warp] + __popc(m1 & lt);
     table[pos] = e;
     g.ustate[e.wi] = kind == 2 ? (pos | U_QUEUED) : pos;
-    if (kind == 2) qlist0[base_q + wq[warp] + __popc(m2 & lt)] = pos;
   } else if (o.in) {
     g.ustate[(size_t)o.y * g.pitch + o.w] = U_NONE;
   }
+  const unsigned m2 = __ballot_sync(0xFFFFFFFFu, kind == 2);
+  if (lane == 0) wq[warp] = __popc(m2);
+  __syncthreads();
+  unsigned before = 0, total = 0;
+#pragma unroll
+  for (int k = 0; k < UIT::TR; k++) { unsigned c = wq[k]; if (k < warp) before += c; total += c; }
+  if (kind == 2) qseg[(size_t)blockIdx.x * UIT::NT + before + __popc(m2 & ((1u << lane) - 1u))] = pos;
+  if (t == 0) qcnt[blockIdx.x] = total;
 }
 
 // Sense-reversing grid barrier; co-residency is guaranteed by the cooperative launch.  A watchdog
@@ -115,65 +109,103 @@ __device__ __forceinline__ bool grid_barrier(IterState *is, unsigned int nblocks
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_u_iter: frontier iterations.  Iteration it visits the entry indices in qlist[it & 1] (k_u_init
-// filled list 0, iteration it-1 the others).  Pushes are staged in shared memory and
-// appended with one global atomic per CTA-chunk.  Ends when an iteration produces an empty list.
+// k_u_iter: frontier iterations.  Iteration 0 visits the per-block frontier segments k_u_init left in
+// qlist0 (each CTA flattens the segments of its share of blocks); iteration it >= 1 visits the entry
+// indices iteration it-1 appended to qlist[it & 1].  Pushes are staged in shared memory and appended
+// with one global atomic per CTA-chunk.  Ends when an iteration produces an empty list.
 // ---------------------------------------------------------------------------------------------
+constexpr int UIT_SEG = 256;   // init-blocks whose frontier segments one CTA flattens at a time
+
 __global__ void __launch_bounds__(UIT_THREADS, 2)
 k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *qlist0, unsigned int *qlist1,
-         IterState *is, Diag *diag) {
+         const unsigned int *qcnt, int n_init_blocks, IterState *is, Diag *diag) {
   __shared__ unsigned int stage[UIT_THREADS * 9];
+  __shared__ unsigned int pre[UIT_SEG + 1];
   __shared__ unsigned int scnt, gbase;
   const int tid = threadIdx.x, nt = blockDim.x, b = blockIdx.x, nb = gridDim.x, lane = tid & 31;
   volatile IterState *vis = is;
   unsigned int *ql[2] = {qlist0, qlist1};
   unsigned long long relaxed = 0;
-  unsigned int it = 0;
+
+  // process one chunk: thread handles entry index `idx` if `has`
+  auto visit_and_flush = [&](bool has, unsigned int idx, unsigned int *dst, unsigned int *out_cnt) {
+    if (tid == 0) scnt = 0;
+    __syncthreads();
+    unsigned int push[9];
+    int np = 0;
+    if (has) {
+      const UEntry e = table[idx];
+      np = u_iter_entry(g, e, idx, push);
+    }
+#pragma unroll
+    for (int j = 0; j < 9; j++) {  // warp-aggregated append to the CTA's staging buffer
+      const bool p = j < np;
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, p);
+      if (m) {
+        unsigned bs = 0;
+        if (lane == 0) bs = atomicAdd(&scnt, (unsigned)__popc(m));
+        bs = __shfl_sync(0xFFFFFFFFu, bs, 0);
+        if (p) stage[bs + __popc(m & ((1u << lane) - 1u))] = push[j];
+      }
+    }
+    __syncthreads();
+    const unsigned int sc = scnt;
+    if (sc) {
+      if (tid == 0) gbase = atomicAdd(out_cnt, sc);
+      __syncthreads();
+      for (unsigned int i = tid; i < sc; i += nt) dst[gbase + i] = stage[i];
+    }
+    __syncthreads();
+  };
+
+  // ---- iteration 0: the per-block frontier segments; output goes to qlist1 / qn[1]
+  {
+    const int per = (n_init_blocks + nb - 1) / nb;
+    const int blk_lo = b * per, blk_hi = min(n_init_blocks, blk_lo + per);
+    for (int s0 = blk_lo; s0 < blk_hi; s0 += UIT_SEG) {
+      const int ns = min(UIT_SEG, blk_hi - s0);
+      // exclusive prefix of the segment lengths (ns <= 256: one warp-scan pass per 32, tiny)
+      if (tid < ns) pre[tid + 1] = qcnt[s0 + tid];
+      if (tid == 0) pre[0] = 0;
+      __syncthreads();
+      if (tid == 0) for (int k = 1; k <= ns; k++) pre[k] += pre[k - 1];
+      __syncthreads();
+      const unsigned int tot = pre[ns];
+      for (unsigned int k0 = 0; k0 < tot; k0 += nt) {
+        const unsigned int k = k0 + tid;
+        bool has = k < tot;
+        unsigned int idx = 0;
+        if (has) {
+          int lo = 0, hi = ns;   // largest lo with pre[lo] <= k
+          while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pre[mid] <= k) lo = mid; else hi = mid; }
+          idx = qlist0[(size_t)(s0 + lo) * UIT::NT + (k - pre[lo])];
+        }
+        visit_and_flush(has, idx, qlist1, &is->qn[1]);
+      }
+      relaxed += tot;
+      __syncthreads();
+    }
+    if (!grid_barrier(is, nb)) return;
+  }
+  // ---- iterations 1, 2, ...
+  unsigned int it = 1;
   for (;; it++) {
     const unsigned int n = vis->qn[it % 3u];
     if (n == 0) break;                       // same value in every CTA: uniform exit
     const unsigned int *src = ql[it & 1];
     unsigned int *dst = ql[(it + 1) & 1];
     unsigned int *out_cnt = &is->qn[(it + 1) % 3u];
-    if (b == 0 && tid == 0) is->qn[(it + 2) % 3u] = 0;   // slot of iteration it+1's output; idle since barrier(it-1)
+    if (b == 0 && tid == 0) is->qn[(it + 2) % 3u] = 0;   // output slot of iteration it+1; idle since barrier(it-1)
     for (unsigned int k0 = (unsigned)b * nt; k0 < n; k0 += (unsigned)nb * nt) {
-      if (tid == 0) scnt = 0;
-      __syncthreads();
       const unsigned int k = k0 + tid;
-      unsigned int push[9];
-      int np = 0;
-      if (k < n) {
-        const unsigned int idx = src[k];
-        const UEntry e = table[idx];
-        np = u_iter_entry(g, e, idx, push);
-      }
-#pragma unroll
-      for (int j = 0; j < 9; j++) {  // warp-aggregated append to the CTA's staging buffer
-        const bool p = j < np;
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, p);
-        if (m) {
-          unsigned bs = 0;
-          if (lane == 0) bs = atomicAdd(&scnt, (unsigned)__popc(m));
-          bs = __shfl_sync(0xFFFFFFFFu, bs, 0);
-          if (p) stage[bs + __popc(m & ((1u << lane) - 1u))] = push[j];
-        }
-      }
-      __syncthreads();
-      const unsigned int sc = scnt;
-      if (sc) {
-        if (tid == 0) gbase = atomicAdd(out_cnt, sc);
-        __syncthreads();
-        for (unsigned int i = tid; i < sc; i += nt) dst[gbase + i] = stage[i];
-      }
-      __syncthreads();
+      visit_and_flush(k < n, k < n ? src[k] : 0u, dst, out_cnt);
+      relaxed += min((unsigned)nt, n - k0);
     }
-    relaxed += (n + nb - 1) / nb;
     if (!grid_barrier(is, nb)) return;
   }
   if (tid == 0) {
     atomicAdd(&diag->sweeps, relaxed);
     if (b == 0) {
-      is->n_entries = 0;
       is->qn[0] = 0; is->qn[1] = 0; is->qn[2] = 0;   // the slot everyone just read is 0 already
       atomicAdd(&diag->passes, (unsigned long long)it);
       atomicAdd(&diag->ticks, 1ull);
@@ -254,7 +286,7 @@ struct MoveSmem {
   alignas(8) uint64_t bar;
 };
 
-__global__ void __launch_bounds__(M_THREADS, 2)
+__global__ void __launch_bounds__(M_THREADS, 4)
 k_move(const __grid_constant__ GridView g, int mtx, Diag *diag, unsigned int *leak_plane) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   MoveSmem &sm = *reinterpret_cast<MoveSmem *>(smem_raw);

@@ -138,7 +138,10 @@ FA_HD UGather u_gather(const GridView &g, int y, int w) {
   return q;
 }
 
-// k_u_init block program: one block owns TR x TW words and sees one halo word all round.
+// k_u_init block program: one block owns TR x TW words (one per thread) and sees one halo word all round.
+//   p0: ONE round of global loads: every thread keeps its own word's raw planes in registers; the
+//       first N_RING threads additionally fetch one word of the two rings around the tile.  The
+//       road-presence / DYN / DXN planes of the region plus one more ring go to shared memory.
 //   pA: statics + initial state (terminals calculated) of every region word, in shared memory
 //   sweeps (<= NS): relax the owned words against the shared-memory neighbourhood; halo words keep
 //       their initial state, so everything stays a valid lower bound of the fixpoint
@@ -149,8 +152,19 @@ FA_HD UGather u_gather(const GridView &g, int y, int w) {
 template <int TR_, int TW_>
 struct UInitTile {
   static constexpr int TR = TR_, TW = TW_, SR = TR + 2, SW = TW + 2, NW = SR * SW, NT = TR * TW, NS = 8;
+  static constexpr int ER = TR + 4, EW = TW + 4, NE = ER * EW;  // region + one more ring: raw planes the statics look at
+  static constexpr int N_HALO = 2 * SW + 2 * TR;                 // ring 1 (region border): statics needed
+  static constexpr int N_OUTER = 2 * EW + 2 * SR;                // ring 2 (extended border): raw planes only
+  static constexpr int N_RING = N_HALO + N_OUTER;
   struct Smem {
     u32 T[NW], GY[NW], GX[NW], R[NW], MY[NW], MX[NW];
+    u32 ROAD[NE], DYN[NE], DXN[NE];
+  };
+  struct Raw {  // raw planes of one word, in registers
+    bool in;
+    int y, w;
+    U4 road, head;
+    u32 pref;
   };
   struct Own {  // registers of the thread that owns an interior word
     bool in;
@@ -164,56 +178,109 @@ struct UInitTile {
   int y0, w0;
   FA_HD UInitTile(const GridView &g_, Smem &s_, int ty, int tx) : g(g_), s(s_), y0(ty * TR), w0(tx * TW) {}
   FA_HD static int idx(int r, int c) { return r * SW + c; }
+  FA_HD static int eidx(int r, int c) { return r * EW + c; }   // region (r, c) sits at extended (r + 1, c + 1)
   FA_HD W3 w3(const u32 *p, int r, int c) const {
     W3 v = {p[idx(r, c - 1)], p[idx(r, c)], p[idx(r, c + 1)]};
     return v;
   }
-  // statics of region word i (any word of the (TR+2)x(TW+2) region); returns them for the caller's registers
-  FA_HD UStatic pA_word(int i, Edge &ed, Heading &h, bool &in) {
-    int r = i / SW, c = i - r * SW;
-    int y = y0 - 1 + r, w = w0 - 1 + c;
+  FA_HD W3 e3(const u32 *p, int er, int ec) const {
+    W3 v = {p[eidx(er, ec - 1)], p[eidx(er, ec)], p[eidx(er, ec + 1)]};
+    return v;
+  }
+  // extended coordinates of ring word k: first ring 1 (region border), then ring 2 (extended border)
+  FA_HD static void ring_pos(int k, int &er, int &ec) {
+    if (k < N_HALO) {
+      int r, c;
+      if (k < SW) { r = 0; c = k; }
+      else if (k < 2 * SW) { r = SR - 1; c = k - SW; }
+      else if (k < 2 * SW + TR) { r = k - 2 * SW + 1; c = 0; }
+      else { r = k - 2 * SW - TR + 1; c = SW - 1; }
+      er = r + 1; ec = c + 1;
+    } else {
+      k -= N_HALO;
+      if (k < EW) { er = 0; ec = k; }
+      else if (k < 2 * EW) { er = ER - 1; ec = k - EW; }
+      else if (k < 2 * EW + SR) { er = k - 2 * EW + 1; ec = 0; }
+      else { er = k - 2 * EW - SR + 1; ec = EW - 1; }
+    }
+  }
+  FA_HD Raw load_raw(int er, int ec, bool want_pref) const {
+    Raw q;
+    q.y = y0 - 2 + er; q.w = w0 - 2 + ec;
+    q.in = q.y >= 0 && q.y < g.gh && q.w >= 0 && q.w < g.pitch;
+    U4 z = {0, 0, 0, 0};
+    q.road = z; q.head = z; q.pref = 0;
+    if (q.in) {
+      size_t o = (size_t)q.y * g.pitch + q.w;
+      q.road = g.road[o]; q.head = g.head_in[o];
+      if (want_pref) q.pref = g.pref_in[o];
+    }
+    return q;
+  }
+  FA_HD void stage(int er, int ec, const Raw &q) {
+    int i = eidx(er, ec);
+    s.ROAD[i] = q.road.x | q.road.z; s.DYN[i] = q.head.x; s.DXN[i] = q.head.z;
+  }
+  // p0: owner thread t loads its interior word; threads t < N_RING also load ring word t
+  FA_HD void p0(int t, Raw &own, Raw &ring) {
+    int tr = t / TW, tc = t - tr * TW;
+    own = load_raw(tr + 2, tc + 2, true);
+    if (t < N_RING) {
+      int er, ec;
+      ring_pos(t, er, ec);
+      ring = load_raw(er, ec, t < N_HALO);
+      stage(er, ec, ring);
+    }
+    if (N_RING > NT)  // tiny test tiles only: more ring words than threads
+      for (int k = t + NT; k < N_RING; k += NT) {
+        int er, ec;
+        ring_pos(k, er, ec);
+        stage(er, ec, load_raw(er, ec, false));
+      }
+    stage(tr + 2, tc + 2, own);
+  }
+  // statics + initial state of region word (r, c) from its raw planes and the staged neighbourhood
+  FA_HD UStatic pA_word(int r, int c, const Raw &q, Edge &ed, Heading &h) {
+    int i = idx(r, c), er = r + 1, ec = c + 1;
     UStatic st = {};
-    in = y >= 0 && y < g.gh && w >= 0 && w < g.pitch;
     u32 R = 0, MY = 0, MX = 0;
-    ed = edge_masks(y, w, g.gh, g.gw);
-    h = heading(0, 0, 0, 0);
-    if (in) {
-      UGather q = u_gather(g, y, w);
+    ed = edge_masks(q.y, q.w, g.gh, g.gw);
+    h = heading(q.head.x, q.head.y, q.head.z, q.head.w);
+    if (q.in) {
       st = u_statics(q.road.x, q.road.y, q.road.z, q.road.w, q.head.x, q.head.y, q.head.z, q.head.w, q.pref,
-                     q.road_up, q.road_c, q.road_dn, q.dyn_up, q.dyn_dn, q.dxn, ed);
-      h = heading(q.head.x, q.head.y, q.head.z, q.head.w);
+                     e3(s.ROAD, er - 1, ec), e3(s.ROAD, er, ec), e3(s.ROAD, er + 1, ec), s.DYN[eidx(er - 1, ec)],
+                     s.DYN[eidx(er + 1, ec)], e3(s.DXN, er, ec), ed);
       R = st.T & ed.valid; MY = R & st.GYr; MX = R & st.GXr;
     }
     s.T[i] = st.T; s.GY[i] = st.GYr; s.GX[i] = st.GXr;
     s.R[i] = R; s.MY[i] = MY; s.MX[i] = MX;
     return st;
   }
-  // owner thread `t` (0 .. NT-1) of interior word (t / TW, t % TW)
-  FA_HD void pA_own(int t, Own &o) {
+  FA_HD void pA(int t, const Raw &own, const Raw &ring, Own &o) {
     int tr = t / TW, tc = t - tr * TW;
     o.si = idx(tr + 1, tc + 1);
-    o.y = y0 + tr; o.w = w0 + tc;
+    o.y = own.y; o.w = own.w; o.in = own.in;
     Edge ed; Heading h;
-    o.st = pA_word(o.si, ed, h, o.in);
+    o.st = pA_word(tr + 1, tc + 1, own, ed, h);
     o.valid = ed.valid;
     u32 link = ~o.st.T;
     o.st.LN = link & h.cN; o.st.LS = link & h.cS; o.st.LW = link & h.cW; o.st.LE = link & h.cE;
     o.st.LNW = link & h.dNW; o.st.LNE = link & h.dNE; o.st.LSW = link & h.dSW; o.st.LSE = link & h.dSE;
     o.cur.R = s.R[o.si]; o.cur.MY = s.MY[o.si]; o.cur.MX = s.MX[o.si];
+    if (t < N_HALO) {
+      int er, ec;
+      ring_pos(t, er, ec);
+      Edge e2; Heading h2;
+      (void)pA_word(er - 1, ec - 1, ring, e2, h2);
+    }
+    if (N_HALO > NT)  // tiny test tiles only
+      for (int k = t + NT; k < N_HALO; k += NT) {
+        int er, ec;
+        ring_pos(k, er, ec);
+        Edge e2; Heading h2;
+        (void)pA_word(er - 1, ec - 1, load_raw(er, ec, true), e2, h2);
+      }
   }
-  // halo words are computed by the first threads in a second round: region words not owned by anybody
-  FA_HD void pA_halo(int t) {
-    // enumerate halo word number t: top row, bottom row, then left/right columns
-    int i;
-    if (t < SW) i = idx(0, t);
-    else if (t < 2 * SW) i = idx(SR - 1, t - SW);
-    else if (t < 2 * SW + TR) i = idx(t - 2 * SW + 1, 0);
-    else if (t < 2 * SW + 2 * TR) i = idx(t - 2 * SW - TR + 1, SW - 1);
-    else return;
-    Edge ed; Heading h; bool in;
-    (void)pA_word(i, ed, h, in);
-  }
-  static constexpr int N_HALO = 2 * (TW + 2) + 2 * TR;
   // one sweep: compute from shared memory (no writes) ...
   FA_HD bool sweep_compute(Own &o, UState &n) const {
     n = o.cur;

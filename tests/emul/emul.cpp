@@ -72,13 +72,14 @@ int64_t tick(HostGrid *h, int chooser, u32 tape_bit, const Rings *rings, int nt,
   {  // k_u_init: one "block" per UIT tile, NT threads emulated in lock step
     typename UIT::Smem *sm = new typename UIT::Smem();
     std::vector<typename UIT::Own> own(UIT::NT);
+    std::vector<typename UIT::Raw> rawo(UIT::NT), rawr(UIT::NT);
     std::vector<UState> nn(UIT::NT);
     int nty = (h->gh + UIT::TR - 1) / UIT::TR, ntx = (h->pitch + UIT::TW - 1) / UIT::TW;
     for (int ty = 0; ty < nty; ty++)
       for (int tx = 0; tx < ntx; tx++) {
         UIT tile(g, *sm, ty, tx);
-        for (int t = 0; t < UIT::NT; t++) tile.pA_own(t, own[t]);
-        for (int t = 0; t < UIT::N_HALO; t++) tile.pA_halo(t);
+        for (int t = 0; t < UIT::NT; t++) tile.p0(t, rawo[t], rawr[t]);
+        for (int t = 0; t < UIT::NT; t++) tile.pA(t, rawo[t], rawr[t], own[t]);
         bool converged = false;
         for (int k = 0; k < UIT::NS; k++) {
           bool any = false;
@@ -216,7 +217,7 @@ int64_t emul_step(void *p, int variant, int nthreads, int chooser, uint32_t tape
   switch (variant) {  // variant: tile shapes / processing order of the frontier
   case 1: return tick<MTile<3, 1>, UInitTile<2, 1>>(h, chooser, tape_bit, rp, nthreads, stats, 2);
   case 2: return tick<MTile<4, 2>, UInitTile<5, 3>>(h, chooser, tape_bit, rp, nthreads, stats, 1);
-  default: return tick<MTile<16, 32>, UInitTile<16, 32>>(h, chooser, tape_bit, rp, nthreads, stats, 0);
+  default: return tick<MTile<8, 32>, UInitTile<16, 32>>(h, chooser, tape_bit, rp, nthreads, stats, 0);
   }
 }
 }
