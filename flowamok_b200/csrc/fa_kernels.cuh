@@ -41,7 +41,7 @@ struct Diag {
 // k_u_init: no global atomics.  Block b owns table[b*NT .. b*NT+NT) (entry of thread t at b*NT+t) and
 // the frontier segment qseg[b*NT .. ) of length qcnt[b].
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(UIT::NT, 2)
+__global__ void __launch_bounds__(UIT::NT, 3)
 k_u_init(const __grid_constant__ GridView g, int ntx, UEntry *table, unsigned int *qseg, unsigned int *qcnt) {
   __shared__ UIT::Smem s;
   __shared__ unsigned int wq[UIT::TR];
