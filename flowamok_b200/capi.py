@@ -56,9 +56,30 @@ def lib():
         "flowamok_step_profile": (C.c_int, [P, P, C.c_int, I64, C.POINTER(C.c_double)]),
         "flowamok_step_leaks": (C.c_int, [P, P, C.c_int, I64, P, C.POINTER(I64)]),
         "flowamok_render": (C.c_int, [P, P, I64, P]),
+        "flowamok_render_device": (C.c_int, [P, P, I64, C.POINTER(P)]),
+        "flowamok_grid_clone": (C.c_int, [P, P, C.POINTER(P)]),
         "flowamok_stats": (C.c_int, [P, P, C.POINTER(I64), C.POINTER(I64), C.POINTER(I64)]),
         "flowamok_generate_synthetic": (C.c_int, [P, P, U64, U32, U32]),
         "flowamok_version": (C.c_char_p, []),
+        # Futhark-generated-library surface (include/flowamok_futhark.h)
+        "futhark_context_config_new": (P, []),
+        "futhark_context_config_free": (None, [P]),
+        "futhark_context_config_set_debugging": (None, [P, C.c_int]),
+        "futhark_context_config_set_profiling": (None, [P, C.c_int]),
+        "futhark_context_config_set_logging": (None, [P, C.c_int]),
+        "futhark_context_config_set_device": (None, [P, C.c_char_p]),
+        "flowamok_futhark_set_scenario": (None, [P, C.c_int]),
+        "futhark_context_new": (P, [P]),
+        "futhark_context_free": (None, [P]),
+        "futhark_context_sync": (C.c_int, [P]),
+        "futhark_context_get_error": (P, [P]),
+        "futhark_entry_init": (C.c_int, [P, C.POINTER(P), I64, I64, I64, I32]),
+        "futhark_entry_step": (C.c_int, [P, C.POINTER(P), C.POINTER(P), P]),
+        "futhark_free_opaque_state": (C.c_int, [P, P]),
+        "futhark_new_u32_2d": (P, [P, P, I64, I64]),
+        "futhark_free_u32_2d": (C.c_int, [P, P]),
+        "futhark_values_u32_2d": (C.c_int, [P, P, P]),
+        "futhark_shape_u32_2d": (C.POINTER(I64), [P, P]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)

@@ -648,6 +648,45 @@ int flowamok_render(flowamok_context *ctx, const flowamok_grid *g, int64_t scale
   return 0;
 }
 
+int flowamok_render_device(flowamok_context *ctx, const flowamok_grid *g, int64_t scale, void **pixels_dev) {
+  if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
+  if (!g || scale < 1 || !pixels_dev) return fail(ctx, "bad render arguments");
+  CU(cudaSetDevice(ctx->device));
+  long long n = (long long)g->gh * scale * g->gw * scale;
+  u32 *d = nullptr;
+  CU(cudaMalloc(&d, (size_t)n * 4));
+  k_render<<<nblk(n, 256), 256, 0, ctx->stream>>>(g->gh, g->gw, g->pitch, scale, g->road, g->head[g->cur], g->color[g->cur], d);
+  CU(cudaGetLastError());
+  *pixels_dev = d;
+  return 0;
+}
+
+int flowamok_grid_clone(flowamok_context *ctx, const flowamok_grid *src, flowamok_grid **out) {
+  if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
+  if (!src || !out) return fail(ctx, "null grid");
+  flowamok_grid *g = nullptr;
+  if (flowamok_grid_new(ctx, &g, src->gh, src->gw)) return 1;
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(g->road, src->road, src->nwords * sizeof(U4), cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(g->head[0], src->head[src->cur], src->nwords * sizeof(U4), cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(g->pref[0], src->pref[src->cur], src->nwords * 4, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(g->color[0], src->color[src->cur], src->ncells_p * 4, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(g->rng, src->rng, src->ncells_p * 8, cudaMemcpyDeviceToDevice, st));
+  g->cur = 0; g->rng_inc = src->rng_inc; g->chooser = src->chooser; g->tape = src->tape; g->tick = src->tick;
+  if (src->n_rings > 0) {
+    CU(cudaMalloc(&g->ring_cells, (size_t)src->n_ring_cells * 8));
+    CU(cudaMemcpyAsync(g->ring_cells, src->ring_cells, (size_t)src->n_ring_cells * 8, cudaMemcpyDeviceToDevice, st));
+    if (src->ring_off) {
+      CU(cudaMalloc(&g->ring_off, ((size_t)src->n_rings + 1) * 8));
+      CU(cudaMemcpyAsync(g->ring_off, src->ring_off, ((size_t)src->n_rings + 1) * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    g->n_rings = src->n_rings; g->n_ring_cells = src->n_ring_cells; g->ring_stride = src->ring_stride;
+    g->h_off = src->h_off; g->h_y = src->h_y; g->h_x = src->h_x; g->h_cy = src->h_cy; g->h_cx = src->h_cx;
+  }
+  *out = g;
+  return 0;
+}
+
 int flowamok_stats(flowamok_context *ctx, flowamok_grid *g, int64_t *ticks, int64_t *passes, int64_t *sweeps) {
   if (!g) return fail(ctx, "null grid");
   CU(cudaSetDevice(ctx->device));
@@ -693,3 +732,5 @@ int flowamok_generate_synthetic(flowamok_context *ctx, flowamok_grid *g, uint64_
 }
 
 }  // extern "C"
+
+#include "fa_futhark.inc"

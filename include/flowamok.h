@@ -103,6 +103,13 @@ int flowamok_step_leaks(flowamok_context *ctx, flowamok_grid *g, int perfect, in
 /* render (flowamok.fut:16-64) into a host buffer [gh*scale][gw*scale] of argb.  Synchronous. */
 int flowamok_render(flowamok_context *ctx, const flowamok_grid *g, int64_t scale, uint32_t *pixels);
 
+/* like flowamok_render but leaves the pixels in device memory (cudaMalloc'd, caller cudaFree's): what
+ * animation.fut:22 hands back as the first component of `step`'s result. */
+int flowamok_render_device(flowamok_context *ctx, const flowamok_grid *g, int64_t scale, void **pixels_dev);
+
+/* `copy s.grid` (animation.fut:23): a fresh grid value with the same cells, cycle_checks and chooser. */
+int flowamok_grid_clone(flowamok_context *ctx, const flowamok_grid *src, flowamok_grid **out);
+
 /* diagnostics of the ticks since the last call: ticks, fixpoint iterations, worklist entries relaxed */
 int flowamok_stats(flowamok_context *ctx, flowamok_grid *g, int64_t *ticks, int64_t *passes, int64_t *sweeps);
 

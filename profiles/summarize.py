@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""Turn an ncu report (--set full, --import-source on) into the text summary committed under profiles/.
+usage: python profiles/summarize.py gpurun_out/r01_k_move.ncu-rep > profiles/r01_k_move.txt"""
+import csv
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second",
+        "dram__bytes_write.sum.per_second", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__block_size",
+        "launch__grid_size", "launch__shared_mem_per_block_static", "launch__shared_mem_per_block_dynamic",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_warps",
+        "launch__waves_per_multiprocessor", "sm__cycles_elapsed.max", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "smsp__cycles_active.avg"]
+
+
+def main(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
+    print(f"# {rep}")
+    print(f"kernel: {d.get('Kernel Name', ('?',))[0]}   grid {d.get('Grid Size', ('?',))[0]} block {d.get('Block Size', ('?',))[0]}")
+    for k in KEYS:
+        if k in d:
+            print(f"{k:70s} {d[k][0]:>18s} {d[k][1]}")
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(src.splitlines()))
+    hdr = rows[1]
+    st = [i for i, h in enumerate(hdr) if h.startswith("stall_")]
+    tot = {hdr[i]: 0 for i in st}
+    for r in rows[2:]:
+        for i in st:
+            try:
+                tot[hdr[i]] += int(r[i])
+            except Exception:
+                pass
+    ssum = sum(tot.values()) or 1
+    print("\nwarp stall sampling (share of all samples):")
+    for k, v in sorted(tot.items(), key=lambda kv: -kv[1])[:10]:
+        print(f"  {k:40s} {v / ssum * 100:5.1f} %")
+    isrc, ismp, iex = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
+    data = [(r[isrc].strip(), int(r[iex]), int(r[ismp])) for r in rows[2:] if len(r) > iex]
+    S = sum(x[2] for x in data) or 1
+    print("\nhottest SASS instructions by samples:")
+    for s, c, sm in sorted(data, key=lambda t: -t[2])[:12]:
+        print(f"  {sm / S * 100:5.1f} %  x{c:<10d} {s[:100]}")
+    tma = [s for s, _, _ in data if "UBLKCP" in s or "UTMA" in s or "SYNCS" in s]
+    if tma:
+        print("\nTMA / mbarrier SASS present:", sorted(set(x.split()[0] if not x.startswith('@') else x.split()[1] for x in tma)))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])

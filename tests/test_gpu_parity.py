@@ -232,3 +232,53 @@ def test_band_of_16384_vs_oracle(ctx):
         nl, _ = og.step_quick(ch)
         assert g.step(False, 1) == nl
     assert_state_equal(state_of(og), dev_state(g), "band tick 30")
+
+
+def test_futhark_entry_points_readme_program(ctx):
+    """The surface `futhark cuda --library README.fut` would generate (include/flowamok_futhark.h):
+    init 30 30 10 123 then 60 steps; every returned frame and the final grid vs the oracle's mk_anim."""
+    import ctypes as C
+    import flowamok_b200.capi as capi
+    L = capi.lib()
+    cfg = L.futhark_context_config_new()
+    fctx = L.futhark_context_new(cfg)
+    assert not L.futhark_context_get_error(fctx)
+    st = C.c_void_p()
+    assert L.futhark_entry_init(fctx, C.byref(st), 30, 30, 10, 123) == 0
+    oa = O.Anim(8, 30, 30, 10, 123)
+    for k in range(60):
+        px, st2 = C.c_void_p(), C.c_void_p()
+        assert L.futhark_entry_step(fctx, C.byref(px), C.byref(st2), st) == 0
+        shp = L.futhark_shape_u32_2d(fctx, px)
+        assert (shp[0], shp[1]) == (300, 300)
+        frame = np.zeros((300, 300), np.uint32)
+        assert L.futhark_values_u32_2d(fctx, px, frame.ctypes.data) == 0
+        assert L.futhark_context_sync(fctx) == 0
+        assert np.array_equal(frame, oa.step(render=True)), f"frame {k}"
+        L.futhark_free_u32_2d(fctx, px)
+        L.futhark_free_opaque_state(fctx, st)      # the input state is ours to free; the step did not consume it
+        st = st2
+    L.futhark_free_opaque_state(fctx, st)
+    L.futhark_context_free(fctx)
+    L.futhark_context_config_free(cfg)
+
+
+def test_grid_clone_is_independent(ctx):
+    import ctypes as C
+    arrs = random_grid(5, 60, 90, car_p=0.5)
+    g = ctx.grid_from_arrays(**arrs)
+    h = C.c_void_p()
+    ctx.check(ctx.L.flowamok_grid_clone(ctx.h, g.h, C.byref(h)))
+    g.step(False, 3)
+    import flowamok_b200 as fa
+    c = fa.Grid.__new__(fa.Grid)
+    c.ctx, c.L, c.gh, c.gw, c.h, c.joined_rng = ctx, ctx.L, 60, 90, h, None
+    d = c.download()
+    for k in ("uy", "ux", "dy", "dx", "color", "pref", "rng_state"):
+        assert np.array_equal(d[k], arrs[k]), k
+    og, ch = oracle_grid(arrs), O.Chooser(O.CHOOSE_RANDOM)
+    for t in range(3):
+        og.step_quick(ch)
+        c.step(False, 1)
+    assert_state_equal(state_of(og), dev_state(c), "clone after 3 ticks")
+    assert_state_equal(state_of(og), dev_state(g), "original after 3 ticks")
