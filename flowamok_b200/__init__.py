@@ -47,6 +47,7 @@ class Context:
     def __init__(self, device: int = -1, stream: int | None = None):
         self.L = lib()
         self.h = C.c_void_p()
+        self.stream_ptr = int(stream) if stream else -1      # -1: the library's private stream
         rc = self.L.flowamok_context_new(C.byref(self.h), device, C.c_void_p(stream) if stream else None)
         if rc:
             msg = self._err()

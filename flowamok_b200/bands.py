@@ -1,0 +1,233 @@
+"""Row-band execution on several GPUs: one process per GPU, `torch.distributed` for the
+plumbing (NCCL over NVLink on the GPUs, gloo in the CPU tests), the stepping itself in the CUDA library.
+
+The reference is single-device; the decomposition follows from its stencil radius of exactly one cell in
+both phases (steppers.fut:19,33-34,66,77-79).  Per tick each band
+  1. swaps two heading/preference rows and one colour row with each neighbour        (state message)
+  2. runs its local fixpoint (k_u_init + k_u_iter)
+  3. swaps its boundary row of calc / my|mx, ORs the neighbour's row into its ghost row and wakes the owned
+     words next to every ghost word that changed; all bands all-reduce (MAX) the number of woken words and
+     resume k_u_iter until nobody was woken -- a waiting chain that crosses a cut costs one extra round
+  4. [perfect mode] resolves its rings and swaps the boundary my|mx once more
+  5. moves (k_move)
+Messages are a few hundred KB, so this is latency-, not bandwidth-bound; there is no collective on the
+data path other than the single all-reduced convergence word.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+
+def split_rows(gh: int, world: int, align: int = 16):
+    """Row ranges of the bands: as even as possible, boundaries on multiples of `align`."""
+    units = (gh + align - 1) // align
+    cuts = [min(gh, align * ((units * r) // world)) for r in range(world + 1)]
+    cuts[-1] = gh
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+class DeviceBand:
+    """A band living in the CUDA library (flowamok_band_* of include/flowamok.h)."""
+
+    def __init__(self, ctx, gh_global, gw, row_begin, row_end):
+        from . import Grid
+        self.ctx, self.L = ctx, ctx.L
+        self.gh_global, self.gw, self.rows = gh_global, gw, (row_begin, row_end)
+        h = C.c_void_p()
+        ctx.check(self.L.flowamok_band_new(ctx.h, C.byref(h), gh_global, gw, row_begin, row_end))
+        self.grid = Grid.__new__(Grid)      # reuse upload/download/chooser/cycles/synth of the Grid wrapper
+        self.grid.ctx, self.grid.L, self.grid.gh, self.grid.gw, self.grid.h, self.grid.joined_rng = \
+            ctx, ctx.L, gh_global, gw, h, None
+        sb, ub = C.c_int64(), C.c_int64()
+        ctx.check(self.L.flowamok_band_msg_bytes(ctx.h, h, C.byref(sb), C.byref(ub)))
+        self.state_bytes, self.u_bytes = sb.value, ub.value
+        self.device = torch.device("cuda", ctx.device)
+        # Messages and the woken counter are torch tensors: torch (NCCL, .item()) touches them on ITS current
+        # stream.  If the library context was not created on that stream, fence at every hand-over.
+        self.foreign_stream = ctx.stream_ptr != torch.cuda.current_stream(self.device).cuda_stream
+
+    def _fence(self):
+        if self.foreign_stream:
+            torch.cuda.synchronize(self.device)
+
+    def buffer(self, nbytes):
+        return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+
+    def counter(self):
+        return torch.zeros(1, dtype=torch.int32, device=self.device)
+
+    def _c(self, rc):
+        self.ctx.check(rc)
+
+    def pack_state(self, side, buf):
+        self._c(self.L.flowamok_band_pack_state(self.ctx.h, self.grid.h, side, buf.data_ptr()))
+        self._fence()
+
+    def unpack_state(self, side, buf):
+        self._fence()
+        self._c(self.L.flowamok_band_unpack_state(self.ctx.h, self.grid.h, side, buf.data_ptr()))
+
+    def u_begin(self):
+        self._c(self.L.flowamok_band_u_begin(self.ctx.h, self.grid.h))
+
+    def pack_u(self, side, buf):
+        self._c(self.L.flowamok_band_pack_u(self.ctx.h, self.grid.h, side, buf.data_ptr()))
+        self._fence()
+
+    def merge_u(self, side, buf, wake):
+        self._fence()
+        self._c(self.L.flowamok_band_merge_u(self.ctx.h, self.grid.h, side, buf.data_ptr(), int(wake), None))
+
+    def woken(self, counter):
+        self._c(self.L.flowamok_band_woken(self.ctx.h, self.grid.h, counter.data_ptr()))
+        self._fence()
+
+    def u_resume(self):
+        self._c(self.L.flowamok_band_u_resume(self.ctx.h, self.grid.h))
+
+    def rings(self):
+        self._c(self.L.flowamok_band_rings(self.ctx.h, self.grid.h))
+
+    def move(self):
+        self._c(self.L.flowamok_band_move(self.ctx.h, self.grid.h))
+
+    def leaks(self):
+        n = C.c_int64()
+        self._c(self.L.flowamok_band_leaks(self.ctx.h, self.grid.h, C.byref(n)))
+        return n.value
+
+
+class BandRunner:
+    """Drives one band; `band` is a DeviceBand (or the CPU emulation used by tests/test_bands_cpu.py)."""
+
+    def __init__(self, band, rank: int, world: int, group=None):
+        self.b, self.rank, self.world, self.group = band, rank, world, group
+        self.up = rank - 1 if rank > 0 else None          # neighbour with smaller rows (side 0)
+        self.down = rank + 1 if rank < world - 1 else None
+        mk = band.buffer
+        self.s_send = [mk(band.state_bytes), mk(band.state_bytes)]
+        self.s_recv = [mk(band.state_bytes), mk(band.state_bytes)]
+        self.u_send = [mk(band.u_bytes), mk(band.u_bytes)]
+        self.u_recv = [mk(band.u_bytes), mk(band.u_bytes)]
+        self.cnt = band.counter()
+        self.rounds = 0
+        self.ticks = 0
+
+    def _neigh(self):
+        return [(0, self.up), (1, self.down)]
+
+    def _swap(self, send, recv):
+        ops = []
+        for side, peer in self._neigh():
+            if peer is None:
+                continue
+            ops.append(dist.P2POp(dist.isend, send[side], peer, self.group))
+            ops.append(dist.P2POp(dist.irecv, recv[side], peer, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def exchange_state(self):
+        for side, peer in self._neigh():
+            if peer is not None:
+                self.b.pack_state(side, self.s_send[side])
+        self._swap(self.s_send, self.s_recv)
+        for side, peer in self._neigh():
+            if peer is not None:
+                self.b.unpack_state(side, self.s_recv[side])
+
+    def exchange_u(self, wake: bool):
+        for side, peer in self._neigh():
+            if peer is not None:
+                self.b.pack_u(side, self.u_send[side])
+        self._swap(self.u_send, self.u_recv)
+        for side, peer in self._neigh():
+            if peer is not None:
+                self.b.merge_u(side, self.u_recv[side], wake)
+
+    def tick(self, perfect: bool):
+        if self.world > 1:
+            self.exchange_state()
+        self.b.u_begin()
+        if self.world > 1:
+            while True:
+                self.exchange_u(wake=True)
+                self.b.woken(self.cnt)
+                dist.all_reduce(self.cnt, op=dist.ReduceOp.MAX, group=self.group)
+                self.rounds += 1
+                if int(self.cnt.item()) == 0:        # the one host round trip of the tick
+                    break
+                self.b.u_resume()
+        if perfect:
+            self.b.rings()
+            if self.world > 1:
+                self.exchange_u(wake=False)
+        self.b.move()
+        self.ticks += 1
+
+    def step(self, perfect: bool, n_ticks: int):
+        for _ in range(n_ticks):
+            self.tick(perfect)
+
+
+class LocalBands:
+    """All bands in ONE process on one device (no torch.distributed): the same protocol with the messages handed
+    over directly.  Used to validate the band entry points on a single GPU and for debugging."""
+
+    def __init__(self, bands):
+        self.bands = bands
+        n = len(bands)
+        self.s = [[b.buffer(b.state_bytes), b.buffer(b.state_bytes)] for b in bands]
+        self.u = [[b.buffer(b.u_bytes), b.buffer(b.u_bytes)] for b in bands]
+        self.cnt = [b.counter() for b in bands]
+        self.n = n
+        self.rounds = 0
+
+    def _pairs(self):
+        # (sender, side it sends to, receiver, side the receiver files it under)
+        for r in range(self.n):
+            if r > 0:
+                yield r, 0, r - 1, 1
+            if r < self.n - 1:
+                yield r, 1, r + 1, 0
+
+    def tick(self, perfect):
+        B = self.bands
+        if self.n > 1:
+            for r, side, _q, _qs in self._pairs():
+                B[r].pack_state(side, self.s[r][side])
+            for r, side, q, qs in self._pairs():
+                B[q].unpack_state(qs, self.s[r][side])
+        for b in B:
+            b.u_begin()
+        while self.n > 1:
+            for r, side, _q, _qs in self._pairs():
+                B[r].pack_u(side, self.u[r][side])
+            for r, side, q, qs in self._pairs():
+                B[q].merge_u(qs, self.u[r][side], True)
+            woken = 0
+            for r, b in enumerate(B):
+                b.woken(self.cnt[r])
+                woken = max(woken, int(self.cnt[r].item()))
+            self.rounds += 1
+            if woken == 0:
+                break
+            for b in B:
+                b.u_resume()
+        if perfect:
+            for b in B:
+                b.rings()
+            if self.n > 1:
+                for r, side, _q, _qs in self._pairs():
+                    B[r].pack_u(side, self.u[r][side])
+                for r, side, q, qs in self._pairs():
+                    B[q].merge_u(qs, self.u[r][side], False)
+        for b in B:
+            b.move()
+
+    def step(self, perfect, n_ticks):
+        for _ in range(n_ticks):
+            self.tick(perfect)

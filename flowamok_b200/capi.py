@@ -60,6 +60,18 @@ def lib():
         "flowamok_grid_clone": (C.c_int, [P, P, C.POINTER(P)]),
         "flowamok_stats": (C.c_int, [P, P, C.POINTER(I64), C.POINTER(I64), C.POINTER(I64)]),
         "flowamok_generate_synthetic": (C.c_int, [P, P, U64, U32, U32]),
+        "flowamok_band_new": (C.c_int, [P, C.POINTER(P), I64, I64, I64, I64]),
+        "flowamok_band_msg_bytes": (C.c_int, [P, P, C.POINTER(I64), C.POINTER(I64)]),
+        "flowamok_band_pack_state": (C.c_int, [P, P, C.c_int, P]),
+        "flowamok_band_unpack_state": (C.c_int, [P, P, C.c_int, P]),
+        "flowamok_band_u_begin": (C.c_int, [P, P]),
+        "flowamok_band_pack_u": (C.c_int, [P, P, C.c_int, P]),
+        "flowamok_band_merge_u": (C.c_int, [P, P, C.c_int, P, C.c_int, P]),
+        "flowamok_band_woken": (C.c_int, [P, P, P]),
+        "flowamok_band_u_resume": (C.c_int, [P, P]),
+        "flowamok_band_rings": (C.c_int, [P, P]),
+        "flowamok_band_move": (C.c_int, [P, P]),
+        "flowamok_band_leaks": (C.c_int, [P, P, C.POINTER(I64)]),
         "flowamok_version": (C.c_char_p, []),
         # Futhark-generated-library surface (include/flowamok_futhark.h)
         "futhark_context_config_new": (P, []),

@@ -29,7 +29,8 @@ struct flowamok_context {
 
 struct flowamok_grid {
   flowamok_context *ctx;
-  int gh, gw, pitch, wvalid;
+  int gh, gw, pitch, wvalid;   // gh = rows held locally (band + halo rows)
+  int gh_global, row0, own0, own1, halo;
   size_t nwords, ncells_p;  // plane words, pitched cells
   U4 *road, *head[2];
   u32 *pref[2], *calc, *color[2], *leak_plane;
@@ -74,6 +75,21 @@ static int fail(flowamok_context *ctx, const char *fmt, ...) {
   } while (0)
 
 static inline unsigned int nblk(long long n, int b) { return (unsigned int)((n + b - 1) / b); }
+
+// FLOWAMOK_DEBUG_SYNC=1: synchronise after every kernel so that a fault is reported at its launch site
+static bool debug_sync() {
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("FLOWAMOK_DEBUG_SYNC"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+#define KCHECK(name)                                                                              \
+  do {                                                                                            \
+    CU(cudaGetLastError());                                                                       \
+    if (debug_sync()) {                                                                           \
+      cudaError_t e2_ = cudaStreamSynchronize(ctx->stream);                                       \
+      if (e2_ != cudaSuccess) return fail(ctx, "kernel %s faulted: %s", name, cudaGetErrorString(e2_)); \
+    }                                                                                             \
+  } while (0)
 
 extern "C" {
 
@@ -128,13 +144,19 @@ char *flowamok_context_get_error(flowamok_context *ctx) {
 int flowamok_context_device(flowamok_context *ctx) { return ctx ? ctx->device : -1; }
 
 // ---------------------------------------------------------------------------------------------
-int flowamok_grid_new(flowamok_context *ctx, flowamok_grid **out, int64_t gh, int64_t gw) {
+}  // extern "C"
+
+static int grid_new_impl(flowamok_context *ctx, flowamok_grid **out, int64_t gh_global, int64_t gw, int64_t row_begin,
+                         int64_t row_end, int halo) {
   if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
-  if (gh < 1 || gw < 1 || gh > (1 << 20) || gw > (1 << 20)) return fail(ctx, "grid shape out of range");
+  if (gh_global < 1 || gw < 1 || gh_global > (1 << 20) || gw > (1 << 20)) return fail(ctx, "grid shape out of range");
+  if (row_begin < 0 || row_end > gh_global || row_end <= row_begin) return fail(ctx, "bad row band");
   CU(cudaSetDevice(ctx->device));
   flowamok_grid *g = new flowamok_grid();
   g->ctx = ctx;
-  g->gh = (int)gh; g->gw = (int)gw;
+  g->gh_global = (int)gh_global; g->halo = halo;
+  g->row0 = (int)row_begin - halo; g->own0 = halo; g->own1 = halo + (int)(row_end - row_begin);
+  g->gh = g->own1 + halo; g->gw = (int)gw;
   g->wvalid = (int)((gw + 31) / 32);
   g->pitch = ((g->wvalid + 3) / 4) * 4;
   g->nwords = (size_t)g->gh * g->pitch;
@@ -154,8 +176,9 @@ int flowamok_grid_new(flowamok_context *ctx, flowamok_grid **out, int64_t gh, in
   CU(cudaMalloc(&g->calc, g->nwords * 4));
   CU(cudaMalloc(&g->mymx, g->nwords * 8));
   CU(cudaMalloc(&g->rng, g->ncells_p * 8));
-  g->ntx = (g->pitch + UIT::TW - 1) / UIT::TW; g->nty = (g->gh + UIT::TR - 1) / UIT::TR;
-  g->mtx = (g->pitch + MT::TW - 1) / MT::TW; g->mty = (g->gh + MT::TR - 1) / MT::TR;
+  const int owned = g->own1 - g->own0;
+  g->ntx = (g->pitch + UIT::TW - 1) / UIT::TW; g->nty = (owned + UIT::TR - 1) / UIT::TR;
+  g->mtx = (g->pitch + MT::TW - 1) / MT::TW; g->mty = (owned + MT::TR - 1) / MT::TR;
   {
     size_t nslots = (size_t)g->ntx * g->nty * UIT::NT;   // >= nwords (tiles are padded)
     CU(cudaMalloc(&g->table, nslots * sizeof(UEntry)));
@@ -179,9 +202,21 @@ int flowamok_grid_new(flowamok_context *ctx, flowamok_grid **out, int64_t gh, in
   CU(cudaMemsetAsync(g->mymx, 0, g->nwords * 8, st));
   CU(cudaMemsetAsync(g->rng, 0, g->ncells_p * 8, st));
   CU(cudaMemsetAsync(g->is, 0, sizeof(IterState), st));
+  CU(cudaMemsetAsync(g->ustate, 0xFF, g->nwords * 4, st));   // U_NONE: halo rows never get entries
   CU(cudaMemsetAsync(g->diag, 0, sizeof(Diag), st));
   CU(cudaStreamSynchronize(st));
   return 0;
+}
+
+extern "C" {
+
+int flowamok_grid_new(flowamok_context *ctx, flowamok_grid **out, int64_t gh, int64_t gw) {
+  return grid_new_impl(ctx, out, gh, gw, 0, gh, 0);
+}
+/* a band of a larger grid: rows [row_begin, row_end) plus two halo rows on each side */
+int flowamok_band_new(flowamok_context *ctx, flowamok_grid **out, int64_t gh_global, int64_t gw, int64_t row_begin,
+                      int64_t row_end) {
+  return grid_new_impl(ctx, out, gh_global, gw, row_begin, row_end, 2);
 }
 
 int flowamok_grid_free(flowamok_context *ctx, flowamok_grid *g) {
@@ -202,7 +237,7 @@ int flowamok_grid_free(flowamok_context *ctx, flowamok_grid *g) {
 
 int flowamok_grid_shape(flowamok_context *ctx, const flowamok_grid *g, int64_t *gh, int64_t *gw) {
   if (!g) return fail(ctx, "null grid");
-  if (gh) *gh = g->gh;
+  if (gh) *gh = g->gh_global;
   if (gw) *gw = g->gw;
   return 0;
 }
@@ -220,12 +255,12 @@ int flowamok_create_grid(flowamok_context *ctx, flowamok_grid *g, int32_t seed, 
   CU(cudaMemsetAsync(g->color[g->cur], 0, g->ncells_p * 4, st));
   CU(cudaMemsetAsync(g->rng, 0, g->ncells_p * 8, st));
   long long n = (long long)g->gh * g->gw;
-  k_create<<<nblk(n, 256), 256, 0, st>>>(g->gh, g->gw, g->pitch, g->color[g->cur], g->rng, s0, inc);
+  k_create<<<nblk(n, 256), 256, 0, st>>>(g->gh, g->gw, g->pitch, g->row0, g->gh_global, g->color[g->cur], g->rng, s0, inc);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(st));
   if (joined_state || joined_inc) {  // join_rng (utils.fut:17): product of states, OR of incs
     u64 js = 1;
-    for (long long i = 0; i < n; i++) js *= pcg32_split_state(s0, inc, i);
+    for (long long i = 0; i < (long long)g->gh_global * g->gw; i++) js *= pcg32_split_state(s0, inc, i);
     if (joined_state) *joined_state = js;
     if (joined_inc) *joined_inc = inc;
   }
@@ -239,28 +274,32 @@ int flowamok_grid_upload(flowamok_context *ctx, flowamok_grid *g, const int8_t *
   if (!g) return fail(ctx, "null grid");
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  size_t n = (size_t)g->gh * g->gw;
+  // host arrays are [gh_global][gw]; this device takes the rows its planes hold (band + halo rows)
+  const int lo = std::max(0, g->row0), hi = std::min(g->gh_global, g->row0 + g->gh);   // global rows present
+  const size_t nrow = (size_t)(hi - lo), n = nrow * g->gw;
   int8_t *tmp = nullptr;
   CU(cudaMalloc(&tmp, n * 5));
   const void *src[5] = {uy, ux, dy, dx, pref};
   int8_t *dptr[5];
   for (int k = 0; k < 5; k++) {
     dptr[k] = src[k] ? tmp + n * k : nullptr;
-    if (src[k]) CU(cudaMemcpyAsync(dptr[k], src[k], n, cudaMemcpyHostToDevice, st));
+    if (src[k]) CU(cudaMemcpyAsync(dptr[k], (const int8_t *)src[k] + (size_t)lo * g->gw, n, cudaMemcpyHostToDevice, st));
   }
-  k_pack<<<nblk((long long)g->nwords * 32, 256), 256, 0, st>>>(g->gh, g->gw, g->pitch, dptr[0], dptr[1], dptr[2],
-                                                              dptr[3], (const uint8_t *)dptr[4], g->road,
+  // the staging arrays start at global row lo: present them to k_pack as a grid whose row 0 is global row lo
+  k_pack<<<nblk((long long)g->nwords * 32, 256), 256, 0, st>>>(g->gh, g->gw, g->pitch, g->row0 - lo, (int)nrow, dptr[0], dptr[1],
+                                                              dptr[2], dptr[3], (const uint8_t *)dptr[4], g->road,
                                                               g->head[g->cur], g->pref[g->cur]);
   CU(cudaGetLastError());
   size_t cp = (size_t)g->pitch * 32;
+  const int l0 = lo - g->row0;   // local row of global row lo
+  CU(cudaMemsetAsync(g->color[g->cur], color ? 0 : 0xFF, g->ncells_p * 4, st));
+  CU(cudaMemsetAsync(g->rng, 0, g->ncells_p * 8, st));
   if (color)
-    CU(cudaMemcpy2DAsync(g->color[g->cur], cp * 4, color, (size_t)g->gw * 4, (size_t)g->gw * 4, g->gh, cudaMemcpyHostToDevice, st));
-  else
-    CU(cudaMemsetAsync(g->color[g->cur], 0xFF, g->ncells_p * 4, st));
+    CU(cudaMemcpy2DAsync(g->color[g->cur] + (size_t)l0 * cp, cp * 4, color + (size_t)lo * g->gw, (size_t)g->gw * 4,
+                         (size_t)g->gw * 4, nrow, cudaMemcpyHostToDevice, st));
   if (rng_state)
-    CU(cudaMemcpy2DAsync(g->rng, cp * 8, rng_state, (size_t)g->gw * 8, (size_t)g->gw * 8, g->gh, cudaMemcpyHostToDevice, st));
-  else
-    CU(cudaMemsetAsync(g->rng, 0, g->ncells_p * 8, st));
+    CU(cudaMemcpy2DAsync(g->rng + (size_t)l0 * cp, cp * 8, rng_state + (size_t)lo * g->gw, (size_t)g->gw * 8,
+                         (size_t)g->gw * 8, nrow, cudaMemcpyHostToDevice, st));
   g->rng_inc = rng_inc;
   CU(cudaStreamSynchronize(st));
   CU(cudaFree(tmp));
@@ -272,25 +311,29 @@ int flowamok_grid_download(flowamok_context *ctx, const flowamok_grid *g, int8_t
   if (!g) return fail(ctx, "null grid");
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  size_t n = (size_t)g->gh * g->gw;
+  // host arrays are [gh_global][gw]; only the OWNED rows are written
+  const int owned = g->own1 - g->own0, grow = g->row0 + g->own0;
+  size_t n = (size_t)owned * g->gw;
   void *dst[5] = {uy, ux, dy, dx, pref};
   bool any = false;
   for (int k = 0; k < 5; k++) any |= dst[k] != nullptr;
   int8_t *tmp = nullptr;
   if (any) {
     CU(cudaMalloc(&tmp, n * 5));
-    k_unpack<<<nblk((long long)n, 256), 256, 0, st>>>(g->gh, g->gw, g->pitch, g->road, g->head[g->cur], g->pref[g->cur],
+    k_unpack<<<nblk((long long)n, 256), 256, 0, st>>>(g->own0, g->own1, g->gw, g->pitch, g->road, g->head[g->cur], g->pref[g->cur],
                                                       uy ? tmp : nullptr, ux ? tmp + n : nullptr, dy ? tmp + 2 * n : nullptr,
                                                       dx ? tmp + 3 * n : nullptr, pref ? (uint8_t *)(tmp + 4 * n) : nullptr);
     CU(cudaGetLastError());
     for (int k = 0; k < 5; k++)
-      if (dst[k]) CU(cudaMemcpyAsync(dst[k], tmp + n * k, n, cudaMemcpyDeviceToHost, st));
+      if (dst[k]) CU(cudaMemcpyAsync((int8_t *)dst[k] + (size_t)grow * g->gw, tmp + n * k, n, cudaMemcpyDeviceToHost, st));
   }
   size_t cp = (size_t)g->pitch * 32;
   if (color)
-    CU(cudaMemcpy2DAsync(color, (size_t)g->gw * 4, g->color[g->cur], cp * 4, (size_t)g->gw * 4, g->gh, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpy2DAsync(color + (size_t)grow * g->gw, (size_t)g->gw * 4, g->color[g->cur] + (size_t)g->own0 * cp, cp * 4,
+                         (size_t)g->gw * 4, owned, cudaMemcpyDeviceToHost, st));
   if (rng_state)
-    CU(cudaMemcpy2DAsync(rng_state, (size_t)g->gw * 8, g->rng, cp * 8, (size_t)g->gw * 8, g->gh, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpy2DAsync(rng_state + (size_t)grow * g->gw, (size_t)g->gw * 8, g->rng + (size_t)g->own0 * cp, cp * 8,
+                         (size_t)g->gw * 8, owned, cudaMemcpyDeviceToHost, st));
   if (rng_inc) *rng_inc = g->rng_inc;
   CU(cudaStreamSynchronize(st));
   if (tmp) CU(cudaFree(tmp));
@@ -300,28 +343,32 @@ int flowamok_grid_download(flowamok_context *ctx, const flowamok_grid *g, int8_t
 int flowamok_add_line_vertical(flowamok_context *ctx, flowamok_grid *g, int64_t y0, int64_t y1, int64_t x, int8_t flow) {
   if (!g) return fail(ctx, "null grid");
   if (y1 < y0) return 0;  // n <= 0: the reference loop body never runs (utils.fut:21-23)
-  if (y0 < 0 || y1 >= g->gh || x < 0 || x >= g->gw) return fail(ctx, "add_line_vertical: index out of bounds");
+  if (y0 < 0 || y1 >= g->gh_global || x < 0 || x >= g->gw) return fail(ctx, "add_line_vertical: index out of bounds");
   CU(cudaSetDevice(ctx->device));
-  int n = (int)(y1 - y0 + 1);
-  k_line_v<<<nblk(n, 128), 128, 0, ctx->stream>>>(g->pitch, g->road, (int)y0, n, (int)x, flow);
+  int64_t a = std::max<int64_t>(y0, g->row0), b = std::min<int64_t>(y1, (int64_t)g->row0 + g->gh - 1);   // rows held here
+  if (b < a) return 0;
+  int n = (int)(b - a + 1);
+  k_line_v<<<nblk(n, 128), 128, 0, ctx->stream>>>(g->pitch, g->road, (int)(a - g->row0), n, (int)x, flow);
   CU(cudaGetLastError());
   return 0;
 }
 int flowamok_add_line_horizontal(flowamok_context *ctx, flowamok_grid *g, int64_t y, int64_t x0, int64_t x1, int8_t flow) {
   if (!g) return fail(ctx, "null grid");
   if (x1 < x0) return 0;
-  if (x0 < 0 || x1 >= g->gw || y < 0 || y >= g->gh) return fail(ctx, "add_line_horizontal: index out of bounds");
+  if (x0 < 0 || x1 >= g->gw || y < 0 || y >= g->gh_global) return fail(ctx, "add_line_horizontal: index out of bounds");
   CU(cudaSetDevice(ctx->device));
+  if (y < g->row0 || y >= (int64_t)g->row0 + g->gh) return 0;   // not held by this band
   int nw = (int)((x1 >> 5) - (x0 >> 5) + 1);
-  k_line_h<<<nblk(nw, 128), 128, 0, ctx->stream>>>(g->pitch, g->road, (int)y, (int)x0, (int)x1, flow);
+  k_line_h<<<nblk(nw, 128), 128, 0, ctx->stream>>>(g->pitch, g->road, (int)(y - g->row0), (int)x0, (int)x1, flow);
   CU(cudaGetLastError());
   return 0;
 }
 int flowamok_add_cell(flowamok_context *ctx, flowamok_grid *g, int64_t y, int64_t x, uint32_t color, int8_t dy, int8_t dx) {
   if (!g) return fail(ctx, "null grid");
-  if (y < 0 || y >= g->gh || x < 0 || x >= g->gw) return fail(ctx, "add_cell: index out of bounds");
+  if (y < 0 || y >= g->gh_global || x < 0 || x >= g->gw) return fail(ctx, "add_cell: index out of bounds");
   CU(cudaSetDevice(ctx->device));
-  k_add_cell<<<1, 1, 0, ctx->stream>>>(g->pitch, g->head[g->cur], g->color[g->cur], (int)y, (int)x, color, dy, dx);
+  if (y < g->row0 || y >= (int64_t)g->row0 + g->gh) return 0;   // not held by this band
+  k_add_cell<<<1, 1, 0, ctx->stream>>>(g->pitch, g->head[g->cur], g->color[g->cur], (int)(y - g->row0), (int)x, color, dy, dx);
   CU(cudaGetLastError());
   return 0;
 }
@@ -352,12 +399,14 @@ static int install_rings(flowamok_context *ctx, flowamok_grid *g, int64_t n, con
   std::vector<unsigned long long> cells((size_t)tot), offs((size_t)n + 1);
   for (int64_t k = 0; k <= n; k++) offs[(size_t)k] = (unsigned long long)off[k];
   for (int64_t t = 0; t < tot; t++) {
-    if (y[t] < 0 || y[t] >= g->gh || x[t] < 0 || x[t] >= g->gw) return fail(ctx, "cycle cell out of bounds");
+    if (y[t] < 0 || y[t] >= g->gh_global || x[t] < 0 || x[t] >= g->gw) return fail(ctx, "cycle cell out of bounds");
+    if (y[t] < g->row0 + g->own0 || y[t] >= g->row0 + g->own1)
+      return fail(ctx, "cycle cell outside this device's row band (rings must not straddle bands)");
     bool single = (cy[t] != 0) != (cx[t] != 0);
     if (!single) return fail(ctx, "cycle check direction must be single-axis (steppers.fut:239-294)");
     unsigned int dir = cy[t] < 0 ? 0u : cy[t] > 0 ? 1u : cx[t] < 0 ? 2u : 3u;
     if (grant[t] != 1 && grant[t] != 2) return fail(ctx, "grant must be 1 (y) or 2 (x)");
-    cells[(size_t)t] = (unsigned long long)((size_t)y[t] * g->pitch + (x[t] >> 5)) | ((unsigned long long)(x[t] & 31) << 32) |
+    cells[(size_t)t] = (unsigned long long)((size_t)(y[t] - g->row0) * g->pitch + (x[t] >> 5)) | ((unsigned long long)(x[t] & 31) << 32) |
                        ((unsigned long long)dir << 37) | ((unsigned long long)(grant[t] == 2 ? 1 : 0) << 39);
   }
   CU(cudaMalloc(&g->ring_cells, std::max<size_t>(1, (size_t)tot) * 8));
@@ -392,6 +441,7 @@ struct Path {
 int flowamok_find_cycles(flowamok_context *ctx, flowamok_grid *g, int64_t max_paths, int64_t *n_cycles) {
   if (!g) return fail(ctx, "null grid");
   if (max_paths <= 0) max_paths = 1 << 16;
+  if (g->gh != g->gh_global) return fail(ctx, "find_cycles needs the whole grid (not available on a row band)");
   const int64_t gh = g->gh, gw = g->gw;
   std::vector<int8_t> uy((size_t)gh * gw), ux((size_t)gh * gw);
   if (flowamok_grid_download(ctx, g, uy.data(), ux.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr)) return 1;
@@ -482,7 +532,7 @@ int flowamok_cycle_count(flowamok_context *ctx, const flowamok_grid *g, int64_t 
 int flowamok_get_cycles_dense(flowamok_context *ctx, const flowamok_grid *g, int8_t *masks) {
   if (!g) return fail(ctx, "null grid");
   if (g->n_rings > 0 && g->h_off.empty()) return fail(ctx, "cycle list was generated on the device; dense form unavailable");
-  size_t per = (size_t)g->gh * g->gw * 2;
+  size_t per = (size_t)g->gh_global * g->gw * 2;
   memset(masks, 0, per * (size_t)g->n_rings);
   for (int64_t k = 0; k < g->n_rings; k++)
     for (int64_t t = g->h_off[k]; t < g->h_off[k + 1]; t++) {
@@ -498,6 +548,7 @@ int flowamok_get_cycles_dense(flowamok_context *ctx, const flowamok_grid *g, int
 static GridView make_view(flowamok_grid *g) {
   GridView v;
   v.gh = g->gh; v.gw = g->gw; v.pitch = g->pitch; v.wvalid = g->wvalid;
+  v.gh_global = g->gh_global; v.row0 = g->row0; v.own0 = g->own0; v.own1 = g->own1;
   v.road = g->road;
   v.head_in = g->head[g->cur]; v.head_out = g->head[g->cur ^ 1];
   v.pref_in = g->pref[g->cur]; v.pref_out = g->pref[g->cur ^ 1];
@@ -509,30 +560,47 @@ static GridView make_view(flowamok_grid *g) {
   return v;
 }
 
-static int enqueue_tick(flowamok_context *ctx, flowamok_grid *g, bool perfect, u32 *leak_plane, cudaEvent_t *ev = nullptr) {
-  cudaStream_t st = ctx->stream;
-  GridView v = make_view(g);
-  int nblocks = g->ntx * g->nty;
-  if (ev) CU(cudaEventRecord(ev[0], st));
-  k_u_init<<<nblocks, UIT::NT, 0, st>>>(v, g->ntx, g->table, g->qlist[0], g->qcnt);
-  CU(cudaGetLastError());
-  {
-    void *args[] = {(void *)&v, (void *)&g->table, (void *)&g->qlist[0], (void *)&g->qlist[1], (void *)&g->qcnt, (void *)&nblocks,
-                    (void *)&g->is, (void *)&g->diag};
-    if (ev) CU(cudaEventRecord(ev[1], st));
-    CU(cudaLaunchCooperativeKernel((void *)k_u_iter, dim3(ctx->iter_blocks), dim3(UIT_THREADS), args, 0, st));
-    if (ev) CU(cudaEventRecord(ev[2], st));
+static int launch_u_init(flowamok_context *ctx, flowamok_grid *g, const GridView &v) {
+  k_u_init<<<g->ntx * g->nty, UIT::NT, 0, ctx->stream>>>(v, g->ntx, g->table, g->qlist[0], g->qcnt);
+  KCHECK("k_u_init");
+  return 0;
+}
+// n_init_blocks > 0: iteration 0 takes the frontier segments k_u_init left; 0: resume from qlist[1] (band merge)
+static int launch_u_iter(flowamok_context *ctx, flowamok_grid *g, GridView &v, int n_init_blocks) {
+  void *args[] = {(void *)&v, (void *)&g->table, (void *)&g->qlist[0], (void *)&g->qlist[1], (void *)&g->qcnt,
+                  (void *)&n_init_blocks, (void *)&g->is, (void *)&g->diag};
+  CU(cudaLaunchCooperativeKernel((void *)k_u_iter, dim3(ctx->iter_blocks), dim3(UIT_THREADS), args, 0, ctx->stream));
+  KCHECK("k_u_iter");
+  return 0;
+}
+static int launch_rings(flowamok_context *ctx, flowamok_grid *g, const GridView &v) {
+  if (g->n_rings > 0) {
+    k_rings<<<nblk(g->n_rings, 128), 128, 0, ctx->stream>>>(v, g->ring_cells, g->ring_off, g->n_rings, g->ring_stride);
+    KCHECK("k_rings");
   }
-  if (perfect && g->n_rings > 0) {
-    k_rings<<<nblk(g->n_rings, 128), 128, 0, st>>>(v, g->ring_cells, g->ring_off, g->n_rings, g->ring_stride);
-    CU(cudaGetLastError());
-  }
-  if (ev) CU(cudaEventRecord(ev[3], st));
-  k_move<<<g->mtx * g->mty, M_THREADS, sizeof(MoveSmem), st>>>(v, g->mtx, g->diag, leak_plane);
-  CU(cudaGetLastError());
-  if (ev) CU(cudaEventRecord(ev[4], st));
+  return 0;
+}
+static int launch_move(flowamok_context *ctx, flowamok_grid *g, const GridView &v, u32 *leak_plane) {
+  k_move<<<g->mtx * g->mty, M_THREADS, sizeof(MoveSmem), ctx->stream>>>(v, g->mtx, g->diag, leak_plane);
+  KCHECK("k_move");
   g->cur ^= 1;
   g->tick++;
+  return 0;
+}
+
+static int enqueue_tick(flowamok_context *ctx, flowamok_grid *g, bool perfect, u32 *leak_plane, cudaEvent_t *ev = nullptr) {
+  if (g->gh != g->gh_global) return fail(ctx, "a row band is stepped with the flowamok_band_* calls");
+  cudaStream_t st = ctx->stream;
+  GridView v = make_view(g);
+  if (ev) CU(cudaEventRecord(ev[0], st));
+  if (launch_u_init(ctx, g, v)) return 1;
+  if (ev) CU(cudaEventRecord(ev[1], st));
+  if (launch_u_iter(ctx, g, v, g->ntx * g->nty)) return 1;
+  if (ev) CU(cudaEventRecord(ev[2], st));
+  if (perfect && launch_rings(ctx, g, v)) return 1;
+  if (ev) CU(cudaEventRecord(ev[3], st));
+  if (launch_move(ctx, g, v, leak_plane)) return 1;
+  if (ev) CU(cudaEventRecord(ev[4], st));
   return 0;
 }
 
@@ -621,7 +689,7 @@ int flowamok_step_leaks(flowamok_context *ctx, flowamok_grid *g, int perfect, in
     CU(cudaMalloc(&dout, (size_t)emit * 64));
     // the tuple copies the cell as move_cell saw it (steppers.fut:122): heading/colour of the old state,
     // next_preference_flow_x already updated by the fixpoint (written by U into the new buffer)
-    k_leak_emit<<<nblk((long long)g->nwords, 256), 256, 0, st>>>(g->gh, g->gw, g->pitch, g->leak_plane, offs, g->head[old],
+    k_leak_emit<<<nblk((long long)g->nwords, 256), 256, 0, st>>>(g->gh, g->gw, g->pitch, g->row0, g->leak_plane, offs, g->head[old],
                                                                 g->pref[old ^ 1], g->color[old], emit, dout);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(leaks, dout, (size_t)emit * 64, cudaMemcpyDeviceToHost, st));
@@ -636,6 +704,7 @@ int flowamok_step_leaks(flowamok_context *ctx, flowamok_grid *g, int perfect, in
 int flowamok_render(flowamok_context *ctx, const flowamok_grid *g, int64_t scale, uint32_t *pixels) {
   if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
   if (!g || scale < 1) return fail(ctx, "bad render arguments");
+  if (g->gh != g->gh_global) return fail(ctx, "render needs the whole grid (not available on a row band)");
   CU(cudaSetDevice(ctx->device));
   long long n = (long long)g->gh * scale * g->gw * scale;
   u32 *d = nullptr;
@@ -665,7 +734,7 @@ int flowamok_grid_clone(flowamok_context *ctx, const flowamok_grid *src, flowamo
   if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
   if (!src || !out) return fail(ctx, "null grid");
   flowamok_grid *g = nullptr;
-  if (flowamok_grid_new(ctx, &g, src->gh, src->gw)) return 1;
+  if (grid_new_impl(ctx, &g, src->gh_global, src->gw, src->row0 + src->own0, src->row0 + src->own1, src->halo)) return 1;
   cudaStream_t st = ctx->stream;
   CU(cudaMemcpyAsync(g->road, src->road, src->nwords * sizeof(U4), cudaMemcpyDeviceToDevice, st));
   CU(cudaMemcpyAsync(g->head[0], src->head[src->cur], src->nwords * sizeof(U4), cudaMemcpyDeviceToDevice, st));
@@ -687,6 +756,116 @@ int flowamok_grid_clone(flowamok_context *ctx, const flowamok_grid *src, flowamo
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Row bands.  side 0 = towards smaller rows, 1 = towards larger rows.
+//   state message: 2 heading rows + 2 preference rows + 1 colour row (what k_u_init / k_move read across the cut)
+//   u message    : 1 row of calc + 1 row of my|mx (what the fixpoint reads across the cut)
+// ---------------------------------------------------------------------------------------------
+int flowamok_band_msg_bytes(flowamok_context *ctx, const flowamok_grid *g, int64_t *state_bytes, int64_t *u_bytes) {
+  if (!g) return fail(ctx, "null grid");
+  if (state_bytes) *state_bytes = (int64_t)g->pitch * (2 * 16 + 2 * 4 + 128);
+  if (u_bytes) *u_bytes = (int64_t)g->pitch * (4 + 8);
+  return 0;
+}
+static int band_check(flowamok_context *ctx, const flowamok_grid *g, int side) {
+  if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
+  if (!g || g->halo < 2) return fail(ctx, "not a row band");
+  if (side != 0 && side != 1) return fail(ctx, "side must be 0 or 1");
+  if (g->own1 - g->own0 < 2) return fail(ctx, "a band needs at least 2 rows");
+  return 0;
+}
+int flowamok_band_pack_state(flowamok_context *ctx, flowamok_grid *g, int side, void *dev_buf) {
+  if (band_check(ctx, g, side)) return 1;
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t P = (size_t)g->pitch;
+  const int r2 = side == 0 ? g->own0 : g->own1 - 2;          // first / last two owned rows
+  const int rc = side == 0 ? g->own0 : g->own1 - 1;          // the owned row next to the cut
+  char *b = (char *)dev_buf;
+  CU(cudaMemcpyAsync(b, g->head[g->cur] + (size_t)r2 * P, 2 * P * 16, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(b + 2 * P * 16, g->pref[g->cur] + (size_t)r2 * P, 2 * P * 4, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(b + 2 * P * 20, g->color[g->cur] + (size_t)rc * P * 32, P * 128, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+int flowamok_band_unpack_state(flowamok_context *ctx, flowamok_grid *g, int side, const void *dev_buf) {
+  if (band_check(ctx, g, side)) return 1;
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t P = (size_t)g->pitch;
+  const int r2 = side == 0 ? g->own0 - 2 : g->own1;          // my halo rows on that side
+  const int rc = side == 0 ? g->own0 - 1 : g->own1;
+  const char *b = (const char *)dev_buf;
+  CU(cudaMemcpyAsync(g->head[g->cur] + (size_t)r2 * P, b, 2 * P * 16, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(g->pref[g->cur] + (size_t)r2 * P, b + 2 * P * 16, 2 * P * 4, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(g->color[g->cur] + (size_t)rc * P * 32, b + 2 * P * 20, P * 128, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+int flowamok_band_u_begin(flowamok_context *ctx, flowamok_grid *g) {
+  if (band_check(ctx, g, 0)) return 1;
+  CU(cudaSetDevice(ctx->device));
+  // a tick always starts with empty frontier counters, whatever the host did with the previous round
+  CU(cudaMemsetAsync(g->is->qn, 0, sizeof(g->is->qn), ctx->stream));
+  GridView v = make_view(g);
+  return launch_u_init(ctx, g, v) || launch_u_iter(ctx, g, v, g->ntx * g->nty);
+}
+int flowamok_band_pack_u(flowamok_context *ctx, flowamok_grid *g, int side, void *dev_buf) {
+  if (band_check(ctx, g, side)) return 1;
+  CU(cudaSetDevice(ctx->device));
+  const size_t P = (size_t)g->pitch;
+  const int r = side == 0 ? g->own0 : g->own1 - 1;
+  char *b = (char *)dev_buf;
+  CU(cudaMemcpyAsync(b, g->calc + (size_t)r * P, P * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(b + P * 4, g->mymx + (size_t)r * P, P * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+/* OR the neighbour's boundary row into my ghost row; wake=1 queues the owned words next to changed ghost words.
+ * dev_woken (device u32, may be NULL) receives the number of entries queued so far this round. */
+int flowamok_band_merge_u(flowamok_context *ctx, flowamok_grid *g, int side, const void *dev_buf, int wake, void *dev_woken) {
+  if (band_check(ctx, g, side)) return 1;
+  CU(cudaSetDevice(ctx->device));
+  const size_t P = (size_t)g->pitch;
+  const int ghost = side == 0 ? g->own0 - 1 : g->own1, own = side == 0 ? g->own0 : g->own1 - 1;
+  const char *b = (const char *)dev_buf;
+  GridView v = make_view(g);
+  k_band_merge<<<nblk(g->pitch, 128), 128, 0, ctx->stream>>>(v, ghost, own, (const u32 *)b, (const u64 *)(b + P * 4), wake,
+                                                            g->qlist[1], g->is);
+  KCHECK("k_band_merge");
+  if (dev_woken) CU(cudaMemcpyAsync(dev_woken, &g->is->qn[1], 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+int flowamok_band_woken(flowamok_context *ctx, flowamok_grid *g, void *dev_woken) {
+  if (band_check(ctx, g, 0)) return 1;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(dev_woken, &g->is->qn[1], 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  return 0;
+}
+int flowamok_band_u_resume(flowamok_context *ctx, flowamok_grid *g) {
+  if (band_check(ctx, g, 0)) return 1;
+  CU(cudaSetDevice(ctx->device));
+  GridView v = make_view(g);
+  return launch_u_iter(ctx, g, v, 0);
+}
+int flowamok_band_rings(flowamok_context *ctx, flowamok_grid *g) {
+  if (band_check(ctx, g, 0)) return 1;
+  CU(cudaSetDevice(ctx->device));
+  GridView v = make_view(g);
+  return launch_rings(ctx, g, v);
+}
+int flowamok_band_move(flowamok_context *ctx, flowamok_grid *g) {
+  if (band_check(ctx, g, 0)) return 1;
+  CU(cudaSetDevice(ctx->device));
+  GridView v = make_view(g);
+  return launch_move(ctx, g, v, nullptr);
+}
+int flowamok_band_leaks(flowamok_context *ctx, flowamok_grid *g, int64_t *n_leaks) {
+  if (!g) return fail(ctx, "null grid");
+  CU(cudaSetDevice(ctx->device));
+  Diag d;
+  if (read_diag(ctx, g, &d)) return 1;
+  if (n_leaks) *n_leaks = (int64_t)d.leaks;
+  return 0;
+}
+
 int flowamok_stats(flowamok_context *ctx, flowamok_grid *g, int64_t *ticks, int64_t *passes, int64_t *sweeps) {
   if (!g) return fail(ctx, "null grid");
   CU(cudaSetDevice(ctx->device));
@@ -705,26 +884,32 @@ int flowamok_generate_synthetic(flowamok_context *ctx, flowamok_grid *g, uint64_
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   CU(cudaStreamSynchronize(st));
-  k_synth<<<nblk((long long)g->nwords * 32, 256), 256, 0, st>>>(g->gh, g->gw, g->pitch, seed, density16, ring_full16, g->road,
-                                                               g->head[g->cur], g->pref[g->cur], g->color[g->cur], g->rng);
+  k_synth<<<nblk((long long)g->nwords * 32, 256), 256, 0, st>>>(g->gh, g->gw, g->pitch, g->row0, g->gh_global, seed, density16,
+                                                               ring_full16, g->road, g->head[g->cur], g->pref[g->cur],
+                                                               g->color[g->cur], g->rng);
   CU(cudaGetLastError());
   g->rng_inc = (0xda3e39cb94b95bdbULL << 1) | 1ULL;
   CU(cudaFree(g->ring_cells)); CU(cudaFree(g->ring_off));
   g->ring_cells = g->ring_off = nullptr; g->n_rings = g->n_ring_cells = 0; g->ring_stride = 0;
   g->h_off.clear(); g->h_y.clear(); g->h_x.clear(); g->h_cy.clear(); g->h_cx.clear();
-  int nby = g->gh >= 15 ? (g->gh - 15) / 16 + 1 : 0, nbx = g->gw >= 23 ? (g->gw - 23) / 16 + 1 : 0;
+  const int ghg = g->gh_global;
+  int nby = ghg >= 15 ? (ghg - 15) / 16 + 1 : 0, nbx = g->gw >= 23 ? (g->gw - 23) / 16 + 1 : 0;
   if (nby > 0 && nbx > 0) {
     unsigned int *cnt = nullptr;
-    CU(cudaMalloc(&cnt, 4));
-    CU(cudaMemsetAsync(cnt, 0, 4, st));
-    CU(cudaMalloc(&g->ring_cells, (size_t)nby * nbx * 48 * 8));
-    k_synth_rings<<<nblk((long long)nby * nbx, 128), 128, 0, st>>>(g->gh, g->gw, g->pitch, seed, nby, nbx, g->ring_cells, cnt);
+    CU(cudaMalloc(&cnt, 8));
+    CU(cudaMemsetAsync(cnt, 0, 8, st));
+    const int lo = g->row0 + g->own0, hi = g->row0 + g->own1;
+    const long long my_blocks = ((long long)(hi - lo) / 16 + 2) * nbx;   // ring blocks that can lie in this band
+    CU(cudaMalloc(&g->ring_cells, (size_t)my_blocks * 48 * 8));
+    k_synth_rings<<<nblk((long long)nby * nbx, 128), 128, 0, st>>>(ghg, g->gw, g->pitch, g->row0, lo, hi, seed, nby, nbx,
+                                                                   g->ring_cells, cnt, cnt + 1);
     CU(cudaGetLastError());
-    unsigned int n = 0;
-    CU(cudaMemcpyAsync(&n, cnt, 4, cudaMemcpyDeviceToHost, st));
+    unsigned int n[2] = {0, 0};
+    CU(cudaMemcpyAsync(n, cnt, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     CU(cudaFree(cnt));
-    g->n_rings = n; g->n_ring_cells = (long long)n * 48; g->ring_stride = 48;
+    if (n[1]) return fail(ctx, "%u synthetic rings straddle this row band: choose band boundaries that are multiples of 16", n[1]);
+    g->n_rings = n[0]; g->n_ring_cells = (long long)n[0] * 48; g->ring_stride = 48;
   }
   CU(cudaStreamSynchronize(st));
   g->tick = 0;

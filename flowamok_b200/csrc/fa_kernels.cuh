@@ -63,6 +63,7 @@ k_u_init(const __grid_constant__ GridView g, int ntx, UEntry *table, unsigned in
   }
   UEntry e = {0, 0, 0, 0};
   const int kind = tile.pC(t, o, converged, e);
+  if (g.gh != g.gh_global) tile.ghost_publish(t);   // row bands only
   const unsigned pos = blockIdx.x * (unsigned)UIT::NT + (unsigned)t;
   if (kind >= 1) {
     table[pos] = e;
@@ -208,8 +209,28 @@ k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *
     if (b == 0) {
       is->qn[0] = 0; is->qn[1] = 0; is->qn[2] = 0;   // the slot everyone just read is 0 already
       atomicAdd(&diag->passes, (unsigned long long)it);
-      atomicAdd(&diag->ticks, 1ull);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row bands: OR the neighbour's boundary row (calc, my|mx) into the ghost row; wake the owned words next to
+// every word that changed (their waiting cars may point into it).  One thread per word.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_band_merge(const __grid_constant__ GridView g, int ghost_row, int own_row, const u32 *recv_calc,
+                             const u64 *recv_mymx, int wake, unsigned int *qlist1, IterState *is) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= g.pitch) return;
+  size_t o = (size_t)ghost_row * g.pitch + w;
+  u32 oc = g.calc[o], nc = oc | recv_calc[w];
+  u64 om = g.mymx[o], nm = om | recv_mymx[w];
+  if (nc == oc && nm == om) return;
+  g.mymx[o] = nm;
+  g.calc[o] = nc;
+  if (!wake) return;
+  for (int dx = -1; dx <= 1; dx++) {
+    u32 q = u_try_queue(g, own_row, w + dx);
+    if (q != U_NONE) qlist1[atomicAdd(&is->qn[1], 1u)] = q & ~U_QUEUED;
   }
 }
 
@@ -293,8 +314,8 @@ k_move(const __grid_constant__ GridView g, int mtx, Diag *diag, unsigned int *le
   MT::Smem &s = sm.m;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int ty = blockIdx.x / mtx, tx = blockIdx.x % mtx;
-  const int y0 = ty * MT::TR, w0 = tx * MT::TW;
-  const int rows = min(MT::TR, g.gh - y0), words = min(MT::TW, g.pitch - w0);
+  const int y0 = g.own0 + ty * MT::TR, w0 = tx * MT::TW;
+  const int rows = min(MT::TR, g.own1 - y0), words = min(MT::TW, g.pitch - w0);
   const size_t cpitch = (size_t)g.pitch * 32;
   const uint32_t row_bytes = (uint32_t)words * 128u;
   // 1. kick off the colour tile: one bulk copy per row, completion counted on the mbarrier
@@ -340,21 +361,24 @@ k_move(const __grid_constant__ GridView g, int mtx, Diag *diag, unsigned int *le
     }
   }
   if (tid == 0 && s.leaks) atomicAdd(&diag->leaks, (unsigned long long)s.leaks);
+  if (tid == 0 && blockIdx.x == 0) atomicAdd(&diag->ticks, 1ull);
 }
 
 // ---------------------------------------------------------------------------------------------
 // packing helpers: one warp builds one plane word with __ballot_sync
 // ---------------------------------------------------------------------------------------------
-__global__ void k_pack(int gh, int gw, int pitch, const int8_t *uy, const int8_t *ux, const int8_t *dy,
-                       const int8_t *dx, const uint8_t *pref, U4 *road, U4 *head, u32 *prefp) {
+// host arrays are [gh_global][gw]; local row y holds global row y + row0 (rows outside the grid stay zero)
+__global__ void k_pack(int gh, int gw, int pitch, int row0, int gh_global, const int8_t *uy, const int8_t *ux,
+                       const int8_t *dy, const int8_t *dx, const uint8_t *pref, U4 *road, U4 *head, u32 *prefp) {
   long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   long long nwords = (long long)gh * pitch;
   if (warp >= nwords) return;
   int y = (int)(warp / pitch), w = (int)(warp % pitch);
   int x = w * 32 + lane;
-  bool in = x < gw;
-  size_t i = (size_t)y * gw + x;
+  int yg = y + row0;
+  bool in = x < gw && yg >= 0 && yg < gh_global;
+  size_t i = (size_t)(in ? yg : 0) * gw + (in ? x : 0);
   int vuy = (in && uy) ? uy[i] : 0, vux = (in && ux) ? ux[i] : 0;
   int vdy = (in && dy) ? dy[i] : 0, vdx = (in && dx) ? dx[i] : 0;
   int vp = (in && pref) ? pref[i] : 0;
@@ -371,11 +395,12 @@ __global__ void k_pack(int gh, int gw, int pitch, const int8_t *uy, const int8_t
   }
 }
 
-__global__ void k_unpack(int gh, int gw, int pitch, const U4 *road, const U4 *head, const u32 *prefp, int8_t *uy,
-                         int8_t *ux, int8_t *dy, int8_t *dx, uint8_t *pref) {
+// unpacks the owned rows [own0, own1) into arrays of shape [own1-own0][gw]
+__global__ void k_unpack(int own0, int own1, int gw, int pitch, const U4 *road, const U4 *head, const u32 *prefp,
+                         int8_t *uy, int8_t *ux, int8_t *dy, int8_t *dx, uint8_t *pref) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)gh * gw) return;
-  int y = (int)(i / gw), x = (int)(i % gw);
+  if (i >= (long long)(own1 - own0) * gw) return;
+  int y = own0 + (int)(i / gw), x = (int)(i % gw);
   size_t o = (size_t)y * pitch + (x >> 5);
   u32 bit = 1u << (x & 31);
   U4 r = road[o], h = head[o];
@@ -387,13 +412,15 @@ __global__ void k_unpack(int gh, int gw, int pitch, const U4 *road, const U4 *he
 }
 
 // create_grid (utils.fut:7-17): white, empty; rng_i = split_rng element i
-__global__ void k_create(int gh, int gw, int pitch, u32 *color, u64 *rng, u64 state0, u64 inc) {
+__global__ void k_create(int gh, int gw, int pitch, int row0, int gh_global, u32 *color, u64 *rng, u64 state0, u64 inc) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)gh * gw) return;
   int y = (int)(i / gw), x = (int)(i % gw);
+  long long yg = (long long)y + row0;
+  if (yg < 0 || yg >= gh_global) return;
   size_t c = (size_t)y * pitch * 32 + x;
   color[c] = 0xFFFFFFFFu;
-  rng[c] = pcg32_split_state(state0, inc, i);
+  rng[c] = pcg32_split_state(state0, inc, yg * gw + x);   // split_rng index = flat index in the WHOLE grid
 }
 
 // point edits (utils.fut:19-38)
@@ -484,14 +511,15 @@ __host__ __device__ inline SynthCell synth_cell(int gh, int gw, int y, int x, u6
   c.rng = synth_hash(seed, 4, (u64)y, (u64)x);
   return c;
 }
-__global__ void k_synth(int gh, int gw, int pitch, u64 seed, u32 density16, u32 ring_full16, U4 *road, U4 *head,
-                        u32 *prefp, u32 *color, u64 *rng) {
+__global__ void k_synth(int gh, int gw, int pitch, int row0, int gh_global, u64 seed, u32 density16, u32 ring_full16,
+                        U4 *road, U4 *head, u32 *prefp, u32 *color, u64 *rng) {
   long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (warp >= (long long)gh * pitch) return;
   int y = (int)(warp / pitch), w = (int)(warp % pitch), x = w * 32 + lane;
+  int yg = y + row0;
   SynthCell c = {0, 0, 0, 0, 0, 0};
-  if (x < gw) c = synth_cell(gh, gw, y, x, seed, density16, ring_full16);
+  if (x < gw && yg >= 0 && yg < gh_global) c = synth_cell(gh_global, gw, yg, x, seed, density16, ring_full16);
   U4 r, h;
   r.x = __ballot_sync(0xFFFFFFFFu, c.uy != 0); r.y = __ballot_sync(0xFFFFFFFFu, c.uy < 0);
   r.z = __ballot_sync(0xFFFFFFFFu, c.ux != 0); r.w = __ballot_sync(0xFFFFFFFFu, c.ux < 0);
@@ -503,12 +531,22 @@ __global__ void k_synth(int gh, int gw, int pitch, u64 seed, u32 density16, u32 
   rng[ci] = c.rng;
 }
 // analytic ring list of the generator: every ring has exactly 48 cells
-__global__ void k_synth_rings(int gh, int gw, int pitch, u64 seed, int nby, int nbx, unsigned long long *cells,
-                              unsigned int *nrings) {
+// rows [lo, hi) (global) are the band this device owns: a ring is listed by the device that owns ALL its rows
+__global__ void k_synth_rings(int gh, int gw, int pitch, int row0, int lo, int hi, u64 seed, int nby, int nbx,
+                              unsigned long long *cells, unsigned int *nrings, unsigned int *nstraddle) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nby * nbx) return;
   int by = b / nbx, bx = b % nbx;
   if (!((16 * by + 14 <= gh - 1) && (16 * bx + 22 <= gw - 1))) return;
+  {
+    int r_lo = 16 * by + 2, r_hi = 16 * by + 14;
+    if (r_hi < lo || r_lo >= hi) return;                       // another band's ring
+    if (r_lo < lo || r_hi >= hi) {                             // cut by a band boundary
+      u64 hb0 = synth_hash(seed, 1, (u64)by, (u64)bx);
+      if (hb0 & 1) atomicAdd(nstraddle, 1u);
+      return;
+    }
+  }
   u64 hb = synth_hash(seed, 1, (u64)by, (u64)bx);
   if (!(hb & 1)) return;
   bool cw = (hb >> 1) & 1;
@@ -531,7 +569,7 @@ __global__ void k_synth_rings(int gh, int gw, int pitch, u64 seed, int nby, int 
       bool corner = (ly == 0 || ly == 12) && (lx == 0 || lx == 12);
       bool grant_x = corner ? (hy != 0) : (hx != 0);
       unsigned int dir = hy < 0 ? 0u : hy > 0 ? 1u : hx < 0 ? 2u : 3u;
-      unsigned long long e = (unsigned long long)((size_t)y * pitch + (x >> 5)) | ((unsigned long long)(x & 31) << 32) |
+      unsigned long long e = (unsigned long long)((size_t)(y - row0) * pitch + (x >> 5)) | ((unsigned long long)(x & 31) << 32) |
                              ((unsigned long long)dir << 37) | ((unsigned long long)(grant_x ? 1 : 0) << 39);
       out[n++] = e;
     }
@@ -591,7 +629,7 @@ __global__ void k_leak_counts(long long nwords, const u32 *leak_plane, unsigned 
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nwords) counts[i] = __popc(leak_plane[i]);
 }
-__global__ void k_leak_emit(int gh, int gw, int pitch, const u32 *leak_plane, const unsigned int *offs,
+__global__ void k_leak_emit(int gh, int gw, int pitch, int row0, const u32 *leak_plane, const unsigned int *offs,
                             const U4 *head_old, const u32 *pref_old, const u32 *color_old, long long cap,
                             long long *out) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -608,7 +646,7 @@ __global__ void k_leak_emit(int gh, int gw, int pitch, const u32 *leak_plane, co
     int x = w * 32 + b;
     int dy = (h.x & bit) ? ((h.y & bit) ? -1 : 1) : 0, dx = (h.z & bit) ? ((h.w & bit) ? -1 : 1) : 0;
     long long *o = out + k * 8;
-    o[0] = y + dy; o[1] = x + dx; o[2] = y; o[3] = x; o[4] = dy; o[5] = dx;
+    o[0] = y + row0 + dy; o[1] = x + dx; o[2] = y + row0; o[3] = x; o[4] = dy; o[5] = dx;
     o[6] = color_old[(size_t)y * pitch * 32 + x]; o[7] = (pr & bit) ? 1 : 0;
     k++;
   }

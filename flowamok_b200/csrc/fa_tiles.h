@@ -21,9 +21,12 @@ enum { CHOOSE_RANDOM = 0, CHOOSE_Y = 1, CHOOSE_X = 2, CHOOSE_TAPE = 3 };
 
 // Device-resident grid in bit-plane form.
 struct GridView {
-  int gh, gw;        // cells
+  int gh, gw;        // rows held in this device's planes (a band plus its halo rows) / cells per row
   int pitch;         // words per plane row (multiple of 4 -> 16-byte aligned rows)
   int wvalid;        // ceil(gw / 32): words that hold cells
+  int gh_global;     // rows of the whole grid (== gh on a single GPU)
+  int row0;          // global row of local row 0 (0 on a single GPU; -halo for the first band)
+  int own0, own1;    // local rows [own0, own1) are owned (stepped and written) by this device
   const U4 *road;    // {UYN, UYS, UXN, UXS} per word                       [gh][pitch]
   const U4 *head_in; // {DYN, DYS, DXN, DXS} per word, state before the tick [gh][pitch]
   U4 *head_out;      // state after the tick
@@ -59,6 +62,10 @@ inline unsigned int fa_host_cas(unsigned int *p, unsigned int c, unsigned int v)
 #define FA_ATOMIC_CAS_U32(p, c, v) fa_host_cas((p), (c), (v))
 #define FA_ATOMIC_OR_U64(p, v) fa_host_or<unsigned long long>((unsigned long long *)(p), (unsigned long long)(v))
 #endif
+
+// local row y exists in the planes AND lies inside the global grid
+FA_HD bool row_in(const GridView &g, int y) { return y >= 0 && y < g.gh && y + g.row0 >= 0 && y + g.row0 < g.gh_global; }
+FA_HD Edge edge_of(const GridView &g, int y, int w) { return edge_masks((int64_t)y + g.row0, w, g.gh_global, g.gw); }
 
 FA_HD int popc32(u32 v) {
 #if defined(__CUDA_ARCH__)
@@ -104,40 +111,6 @@ struct alignas(16) UEntry {  // 16 bytes: one 128-bit access
   u32 T, GY, GX; // statics of the word (UStatic.T, GYr, GXr)
 };
 
-// Gathers the 3x3 word neighbourhood of (y, w) straight from the planes (zero outside the grid).
-struct UGather {
-  U4 road, head;
-  u32 pref;
-  W3 road_up, road_c, road_dn;  // UYN | UXN
-  u32 dyn_up, dyn_dn;
-  W3 dxn;
-};
-FA_HD UGather u_gather(const GridView &g, int y, int w) {
-  UGather q;
-  auto ld_road = [&](int yy, int ww) -> u32 {
-    if (yy < 0 || yy >= g.gh || ww < 0 || ww >= g.pitch) return 0u;
-    U4 r = g.road[(size_t)yy * g.pitch + ww];
-    return r.x | r.z;
-  };
-  auto ld_head = [&](int yy, int ww) -> U4 {
-    U4 z = {0, 0, 0, 0};
-    if (yy < 0 || yy >= g.gh || ww < 0 || ww >= g.pitch) return z;
-    return g.head_in[(size_t)yy * g.pitch + ww];
-  };
-  size_t o = (size_t)y * g.pitch + w;
-  q.road = g.road[o]; q.head = g.head_in[o]; q.pref = g.pref_in[o];
-  q.road_c.c = q.road.x | q.road.z; q.road_c.l = ld_road(y, w - 1); q.road_c.r = ld_road(y, w + 1);
-  q.road_up.c = ld_road(y - 1, w); q.road_dn.c = ld_road(y + 1, w);
-  q.road_up.l = q.road_up.r = q.road_dn.l = q.road_dn.r = 0u;
-  if (q.head.x & q.head.z) {  // a diagonal heading in this word: corner cells matter
-    q.road_up.l = ld_road(y - 1, w - 1); q.road_up.r = ld_road(y - 1, w + 1);
-    q.road_dn.l = ld_road(y + 1, w - 1); q.road_dn.r = ld_road(y + 1, w + 1);
-  }
-  q.dyn_up = ld_head(y - 1, w).x; q.dyn_dn = ld_head(y + 1, w).x;
-  q.dxn.c = q.head.z; q.dxn.l = ld_head(y, w - 1).z; q.dxn.r = ld_head(y, w + 1).z;
-  return q;
-}
-
 // k_u_init block program: one block owns TR x TW words (one per thread) and sees one halo word all round.
 //   p0: ONE round of global loads: every thread keeps its own word's raw planes in registers; the
 //       first N_RING threads additionally fetch one word of the two rings around the tile.  The
@@ -176,7 +149,7 @@ struct UInitTile {
   const GridView &g;
   Smem &s;
   int y0, w0;
-  FA_HD UInitTile(const GridView &g_, Smem &s_, int ty, int tx) : g(g_), s(s_), y0(ty * TR), w0(tx * TW) {}
+  FA_HD UInitTile(const GridView &g_, Smem &s_, int ty, int tx) : g(g_), s(s_), y0(g_.own0 + ty * TR), w0(tx * TW) {}
   FA_HD static int idx(int r, int c) { return r * SW + c; }
   FA_HD static int eidx(int r, int c) { return r * EW + c; }   // region (r, c) sits at extended (r + 1, c + 1)
   FA_HD W3 w3(const u32 *p, int r, int c) const {
@@ -207,7 +180,7 @@ struct UInitTile {
   FA_HD Raw load_raw(int er, int ec, bool want_pref) const {
     Raw q;
     q.y = y0 - 2 + er; q.w = w0 - 2 + ec;
-    q.in = q.y >= 0 && q.y < g.gh && q.w >= 0 && q.w < g.pitch;
+    q.in = row_in(g, q.y) && q.w >= 0 && q.w < g.pitch;
     U4 z = {0, 0, 0, 0};
     q.road = z; q.head = z; q.pref = 0;
     if (q.in) {
@@ -244,7 +217,7 @@ struct UInitTile {
     int i = idx(r, c), er = r + 1, ec = c + 1;
     UStatic st = {};
     u32 R = 0, MY = 0, MX = 0;
-    ed = edge_masks(q.y, q.w, g.gh, g.gw);
+    ed = edge_of(g, q.y, q.w);
     h = heading(q.head.x, q.head.y, q.head.z, q.head.w);
     if (q.in) {
       st = u_statics(q.road.x, q.road.y, q.road.z, q.road.w, q.head.x, q.head.y, q.head.z, q.head.w, q.pref,
@@ -259,7 +232,7 @@ struct UInitTile {
   FA_HD void pA(int t, const Raw &own, const Raw &ring, Own &o) {
     int tr = t / TW, tc = t - tr * TW;
     o.si = idx(tr + 1, tc + 1);
-    o.y = own.y; o.w = own.w; o.in = own.in;
+    o.y = own.y; o.w = own.w; o.in = own.in && own.y >= g.own0 && own.y < g.own1;   // rows past the band are halo-like
     Edge ed; Heading h;
     o.st = pA_word(tr + 1, tc + 1, own, ed, h);
     o.valid = ed.valid;
@@ -297,6 +270,25 @@ struct UInitTile {
     o.cur = n;
     s.R[o.si] = n.R; s.MY[o.si] = n.MY; s.MX[o.si] = n.MX;
   }
+  // Row bands: the rows just outside the owned range (own0-1 and own1) belong to the neighbouring device; the
+  // fixpoint needs a lower bound of their state, which is the initial state this block computed anyway.
+  FA_HD void ghost_word(int r, int c) const {
+    int y = y0 - 1 + r, w = w0 - 1 + c;
+    if ((y != g.own0 - 1 && y != g.own1) || !row_in(g, y) || w < 0 || w >= g.pitch) return;
+    int i = idx(r, c);
+    size_t off = (size_t)y * g.pitch + w;
+    g.mymx[off] = pack_mymx(s.MY[i], s.MX[i]);
+    g.calc[off] = s.R[i];
+  }
+  FA_HD void ghost_publish(int t) const {
+    int tr = t / TW, tc = t - tr * TW;
+    ghost_word(tr + 1, tc + 1);
+    for (int k = t; k < N_HALO; k += NT) {
+      int er, ec;
+      ring_pos(k, er, ec);
+      ghost_word(er - 1, ec - 1);
+    }
+  }
   // publish; returns 0 = no entry, 1 = dormant entry, 2 = entry that starts on the frontier
   FA_HD int pC(int t, const Own &o, bool converged, UEntry &e) const {
     if (!o.in) return 0;
@@ -315,7 +307,7 @@ struct UPlanes {  // calc / my / mx of one word
   u32 R, MY, MX;
 };
 FA_HD size_t u_off(const GridView &g, int y, int w, bool &ok) {
-  ok = !(y < 0 || y >= g.gh || w < 0 || w >= g.pitch);
+  ok = row_in(g, y) && w >= 0 && w < g.pitch;
   return ok ? (size_t)y * g.pitch + w : 0;
 }
 FA_HD u32 u_ld_calc(const GridView &g, size_t o, bool ok) {
@@ -341,7 +333,7 @@ FA_HD void u_ld_mymx(const GridView &g, size_t o, bool ok, UPlanes &p) {
 // Put word (y, w) on the next list unless it has nothing unresolved or is queued already.
 // Returns its entry index, or U_NONE.
 FA_HD u32 u_try_queue(const GridView &g, int y, int w) {
-  if (y < 0 || y >= g.gh || w < 0 || w >= g.pitch) return U_NONE;
+  if (y < g.own0 || y >= g.own1 || w < 0 || w >= g.pitch) return U_NONE;   // only owned words have entries
   size_t o = (size_t)y * g.pitch + w;
 #if defined(__CUDA_ARCH__)
   u32 sv = *(volatile const u32 *)&g.ustate[o];
@@ -394,7 +386,7 @@ FA_HD int u_iter_entry(const GridView &g, const UEntry &e, u32 idx, u32 *push) {
   W3 MY_up = {ul.MY, up.MY, ur.MY}, MY_dn = {dl.MY, dn.MY, dr.MY};
   W3 MX_c = {l.MX, c.MX, r.MX}, MX_up = {ul.MX, up.MX, ur.MX}, MX_dn = {dl.MX, dn.MX, dr.MX};
   UState n = u_relax(st, R_up, R_c, R_dn, MY_up, MY_dn, MX_c, MX_up, MX_dn);
-  const u32 valid = edge_masks(y, w, g.gh, g.gw).valid;
+  const u32 valid = edge_of(g, y, w).valid;
   n.R = (n.R & valid) | c.R; n.MY = (n.MY & valid) | c.MY; n.MX = (n.MX & valid) | c.MX;   // monotone
   bool changed = n.R != c.R || n.MY != c.MY || n.MX != c.MX;
   bool unready = (~n.R & ~e.T) != 0u;
@@ -432,7 +424,7 @@ struct MTile {
   const GridView &g;
   Smem &s;
   int y0, w0;
-  FA_HD MTile(const GridView &g_, Smem &s_, int tile_y, int tile_w) : g(g_), s(s_), y0(tile_y * TR), w0(tile_w * TW) {}
+  FA_HD MTile(const GridView &g_, Smem &s_, int tile_y, int tile_w) : g(g_), s(s_), y0(g_.own0 + tile_y * TR), w0(tile_w * TW) {}
   FA_HD static int idx(int r, int c) { return r * SW + c; }
 
   FA_HD void p0(int tid, int nt) {
@@ -442,7 +434,7 @@ struct MTile {
       int y = y0 - 1 + r, w = w0 - 1 + c;
       U4 rd = {0, 0, 0, 0}, hd = {0, 0, 0, 0};
       u32 my = 0, mx = 0;
-      if (y >= 0 && y < g.gh && w >= 0 && w < g.pitch) {
+      if (row_in(g, y) && w >= 0 && w < g.pitch) {
         size_t o = (size_t)y * g.pitch + w;
         rd = g.road[o]; hd = g.head_in[o];
         u64 m = g.mymx[o];
@@ -488,7 +480,7 @@ struct MTile {
       int tr = i / TW, tc = i - tr * TW;
       int r = tr + 1, c = tc + 1;
       int y = y0 + tr, w = w0 + tc;
-      if (y >= g.gh || w >= g.pitch) { s.AY[i] = 0; s.AX[i] = 0; continue; }
+      if (y >= g.own1 || w >= g.pitch) { s.AY[i] = 0; s.AX[i] = 0; continue; }
       size_t go = (size_t)y * g.pitch + w;
       {  // next_preference_flow_x (steppers.fut:41-50): decided by the fixpoint's own grants only; cells a ring
          // resolution marked (steppers.fut:189-224) have calc = 0 and keep their preference
@@ -496,7 +488,7 @@ struct MTile {
         u32 cal = g.calc[go];
         UState f = {cal, s.MY[ci] & cal, s.MX[ci] & cal};
         UStatic dummy = {};
-        Edge ev = edge_masks(y, w, g.gh, g.gw);
+        Edge ev = edge_of(g, y, w);
         g.pref_out[go] = u_pref_next(s.UYN[ci] | s.UXN[ci], g.pref_in[go], f, dummy) & ev.valid;
       }
       {  // fast path: no car in this word, above, below, or in the two adjacent cells -> nothing moves here
@@ -511,7 +503,7 @@ struct MTile {
           continue;
         }
       }
-      Edge e = edge_masks(y, w, g.gh, g.gw);
+      Edge e = edge_of(g, y, w);
       bool diag = (s.DYN[idx(r, c)] & s.DXN[idx(r, c)]) != 0u;
       MPre p = m_pre(mrow_side(r - 1, c, diag), mrow_center(r, c), mrow_side(r + 1, c, diag), e);
       u32 CH = 0;
@@ -548,7 +540,7 @@ struct MTile {
       int tr = i / q_per_row, q = i - tr * q_per_row;
       int tc = q >> 3, nib = q & 7;
       int y = y0 + tr, w = w0 + tc;
-      if (y >= g.gh || w >= g.pitch) continue;
+      if (y >= g.own1 || w >= g.pitch) continue;
       size_t base = (size_t)y * cpitch + (size_t)w * 32 + (size_t)nib * 4;
       U4 v = *reinterpret_cast<const U4 *>(g.color_in + base);
       int wi = tr * TW + tc;

@@ -118,6 +118,29 @@ int flowamok_stats(flowamok_context *ctx, flowamok_grid *g, int64_t *ticks, int6
  * completely full in 1/16.  Also installs the analytic cycle list.  Synchronous. */
 int flowamok_generate_synthetic(flowamok_context *ctx, flowamok_grid *g, uint64_t seed, uint32_t density16, uint32_t ring_full16);
 
+/* ---- row bands for multi-GPU runs (the reference is single device) ----
+ * A band holds rows [row_begin, row_end) of a gh_global x gw grid plus two halo rows per side.  upload/download use
+ * WHOLE-grid host arrays (upload reads the rows the band holds, download writes the rows it owns); edits and cycle
+ * lists take global coordinates.  One tick of a band, driven by the host (flowamok_b200/bands.py):
+ *     pack_state -> send/recv with both neighbours -> unpack_state          (heading, preference, colour rows)
+ *     u_begin                                                                (local fixpoint)
+ *     repeat: pack_u -> send/recv -> merge_u(wake=1); all-reduce(max) of the woken count; u_resume   until 0
+ *     [perfect: rings; pack_u -> send/recv -> merge_u(wake=0)]
+ *     move
+ * side 0 = neighbour with smaller rows, 1 = larger rows; buffers are device pointers of the sizes msg_bytes reports. */
+int flowamok_band_new(flowamok_context *ctx, flowamok_grid **out, int64_t gh_global, int64_t gw, int64_t row_begin, int64_t row_end);
+int flowamok_band_msg_bytes(flowamok_context *ctx, const flowamok_grid *g, int64_t *state_bytes, int64_t *u_bytes);
+int flowamok_band_pack_state(flowamok_context *ctx, flowamok_grid *g, int side, void *dev_buf);
+int flowamok_band_unpack_state(flowamok_context *ctx, flowamok_grid *g, int side, const void *dev_buf);
+int flowamok_band_u_begin(flowamok_context *ctx, flowamok_grid *g);
+int flowamok_band_pack_u(flowamok_context *ctx, flowamok_grid *g, int side, void *dev_buf);
+int flowamok_band_merge_u(flowamok_context *ctx, flowamok_grid *g, int side, const void *dev_buf, int wake, void *dev_woken);
+int flowamok_band_woken(flowamok_context *ctx, flowamok_grid *g, void *dev_woken);
+int flowamok_band_u_resume(flowamok_context *ctx, flowamok_grid *g);
+int flowamok_band_rings(flowamok_context *ctx, flowamok_grid *g);
+int flowamok_band_move(flowamok_context *ctx, flowamok_grid *g);
+int flowamok_band_leaks(flowamok_context *ctx, flowamok_grid *g, int64_t *n_leaks);
+
 /* library identification */
 const char *flowamok_version(void);
 

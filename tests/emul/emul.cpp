@@ -1,9 +1,10 @@
 // CPU emulation of the CUDA tile programs (TEST INFRASTRUCTURE).
 //
 // Compiles flowamok_b200/csrc/fa_tiles.h for the host and runs the very same phase functions the
-// kernels run, with a loop over "thread ids" in place of a thread block and the same multi-pass
-// pending/changed protocol as the host driver in fa_api.cu.  tests/test_emul.py compares it with
-// the oracle.  It is never part of the product library.
+// kernels run, with a loop over "thread ids" in place of a thread block, the same frontier worklist
+// discipline as k_u_init / k_u_iter, and the same row-band protocol as the flowamok_band_* calls of
+// fa_api.cu.  tests/test_emul.py and tests/test_bands_cpu.py compare it with the oracle.  It is never
+// part of the product library.
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -15,35 +16,47 @@ using namespace fa;
 
 namespace {
 
-struct HostGrid {
-  int gh, gw, pitch, wvalid;
-  std::vector<U4> road, head[2];
-  std::vector<u32> pref[2], calc, color[2];
-  std::vector<u64> mymx;
-  std::vector<u32> ustate;
-  std::vector<u64> rng;
-  u64 rng_inc;
-  int cur = 0;
+struct Rings {
+  std::vector<int64_t> off, y, x;   // y is GLOBAL
+  std::vector<int8_t> cy, cx;
+  std::vector<uint8_t> grant;
 };
 
-HostGrid *make(int gh, int gw) {
+struct HostGrid {
+  int gh, gw, pitch, wvalid, gh_global, row0, own0, own1, halo;
+  int variant;
+  std::vector<U4> road, head[2];
+  std::vector<u32> pref[2], calc, color[2], ustate;
+  std::vector<u64> mymx, rng;
+  u64 rng_inc = 0;
+  int cur = 0;
+  // fixpoint state of the current tick
+  std::vector<UEntry> table;
+  std::vector<u32> frontier;
+  unsigned iters = 0, relaxed = 0;
+  Rings rings;
+  bool has_rings = false;
+};
+
+HostGrid *make(int gh_global, int gw, int row_begin, int row_end, int halo, int variant) {
   HostGrid *h = new HostGrid();
-  h->gh = gh; h->gw = gw;
+  h->gh_global = gh_global; h->gw = gw; h->halo = halo; h->variant = variant;
+  h->row0 = row_begin - halo; h->own0 = halo; h->own1 = halo + (row_end - row_begin);
+  h->gh = h->own1 + halo;
   h->wvalid = (gw + 31) / 32;
   h->pitch = ((h->wvalid + 3) / 4) * 4;
-  if (h->pitch == 0) h->pitch = 4;
-  size_t nw = (size_t)gh * h->pitch, nc = nw * 32;
+  size_t nw = (size_t)h->gh * h->pitch, nc = nw * 32;
   h->road.assign(nw, U4{0, 0, 0, 0});
   for (int k = 0; k < 2; k++) { h->head[k].assign(nw, U4{0, 0, 0, 0}); h->pref[k].assign(nw, 0); h->color[k].assign(nc, 0); }
-  h->calc.assign(nw, 0); h->mymx.assign(nw, 0); h->ustate.assign(nw, 0);
+  h->calc.assign(nw, 0); h->mymx.assign(nw, 0); h->ustate.assign(nw, U_NONE);
   h->rng.assign(nc, 0);
-  h->rng_inc = 0;
   return h;
 }
 
 GridView view(HostGrid *h, int chooser, u32 tape_bit) {
   GridView g;
   g.gh = h->gh; g.gw = h->gw; g.pitch = h->pitch; g.wvalid = h->wvalid;
+  g.gh_global = h->gh_global; g.row0 = h->row0; g.own0 = h->own0; g.own1 = h->own1;
   g.road = h->road.data();
   g.head_in = h->head[h->cur].data(); g.head_out = h->head[h->cur ^ 1].data();
   g.pref_in = h->pref[h->cur].data(); g.pref_out = h->pref[h->cur ^ 1].data();
@@ -54,92 +67,89 @@ GridView view(HostGrid *h, int chooser, u32 tape_bit) {
   return g;
 }
 
-struct Rings {
-  std::vector<int64_t> off;
-  std::vector<int64_t> y, x;
-  std::vector<int8_t> cy, cx;
-  std::vector<uint8_t> grant;
-};
-
-// Frontier discipline of k_u_init / k_u_iter: iteration 0 visits every entry, later iterations visit
-// what the previous one queued; stop on an empty list.  `order` varies the processing order inside
-// an iteration (the result must not depend on it).
-template <class MT, class UIT>
-int64_t tick(HostGrid *h, int chooser, u32 tape_bit, const Rings *rings, int nt, unsigned *stats, int order) {
-  GridView g = view(h, chooser, tape_bit);
-  std::vector<UEntry> table;
-  std::vector<u32> cur, next;
-  {  // k_u_init: one "block" per UIT tile, NT threads emulated in lock step
-    typename UIT::Smem *sm = new typename UIT::Smem();
-    std::vector<typename UIT::Own> own(UIT::NT);
-    std::vector<typename UIT::Raw> rawo(UIT::NT), rawr(UIT::NT);
-    std::vector<UState> nn(UIT::NT);
-    int nty = (h->gh + UIT::TR - 1) / UIT::TR, ntx = (h->pitch + UIT::TW - 1) / UIT::TW;
-    for (int ty = 0; ty < nty; ty++)
-      for (int tx = 0; tx < ntx; tx++) {
-        UIT tile(g, *sm, ty, tx);
-        for (int t = 0; t < UIT::NT; t++) tile.p0(t, rawo[t], rawr[t]);
-        for (int t = 0; t < UIT::NT; t++) tile.pA(t, rawo[t], rawr[t], own[t]);
-        bool converged = false;
-        for (int k = 0; k < UIT::NS; k++) {
-          bool any = false;
-          for (int t = 0; t < UIT::NT; t++) any |= tile.sweep_compute(own[t], nn[t]);
-          if (!any) { converged = true; break; }
-          for (int t = 0; t < UIT::NT; t++) tile.sweep_commit(own[t], nn[t]);
-        }
-        for (int t = 0; t < UIT::NT; t++) {
-          UEntry e;
-          int kind = tile.pC(t, own[t], converged, e);
-          if (kind >= 1) {
-            u32 pos = (u32)table.size();
-            table.push_back(e);
-            g.ustate[e.wi] = kind == 2 ? (pos | U_QUEUED) : pos;
-            if (kind == 2) cur.push_back(pos);
-          } else if (own[t].in) g.ustate[(size_t)own[t].y * h->pitch + own[t].w] = U_NONE;
-        }
+// k_u_init: one "block" per UIT tile, NT threads emulated in lock step
+template <class UIT>
+void u_init(HostGrid *h, const GridView &g) {
+  h->table.clear(); h->frontier.clear();
+  typename UIT::Smem *sm = new typename UIT::Smem();
+  std::vector<typename UIT::Own> own(UIT::NT);
+  std::vector<typename UIT::Raw> rawo(UIT::NT), rawr(UIT::NT);
+  std::vector<UState> nn(UIT::NT);
+  int nty = (h->own1 - h->own0 + UIT::TR - 1) / UIT::TR, ntx = (h->pitch + UIT::TW - 1) / UIT::TW;
+  for (int ty = 0; ty < nty; ty++)
+    for (int tx = 0; tx < ntx; tx++) {
+      UIT tile(g, *sm, ty, tx);
+      for (int t = 0; t < UIT::NT; t++) tile.p0(t, rawo[t], rawr[t]);
+      for (int t = 0; t < UIT::NT; t++) tile.pA(t, rawo[t], rawr[t], own[t]);
+      bool converged = false;
+      for (int k = 0; k < UIT::NS; k++) {
+        bool any = false;
+        for (int t = 0; t < UIT::NT; t++) any |= tile.sweep_compute(own[t], nn[t]);
+        if (!any) { converged = true; break; }
+        for (int t = 0; t < UIT::NT; t++) tile.sweep_commit(own[t], nn[t]);
       }
-    delete sm;
-  }
-  unsigned iters = 0, relaxed = 0;
-  while (!cur.empty()) {
-    iters++;
+      for (int t = 0; t < UIT::NT; t++) {
+        UEntry e;
+        int kind = tile.pC(t, own[t], converged, e);
+        if (g.gh != g.gh_global) tile.ghost_publish(t);
+        if (kind >= 1) {
+          u32 pos = (u32)h->table.size();
+          h->table.push_back(e);
+          g.ustate[e.wi] = kind == 2 ? (pos | U_QUEUED) : pos;
+          if (kind == 2) h->frontier.push_back(pos);
+        } else if (own[t].in) g.ustate[(size_t)own[t].y * h->pitch + own[t].w] = U_NONE;
+      }
+    }
+  delete sm;
+}
+
+// k_u_iter: frontier iterations until nothing is queued; `order` varies the visiting order
+void u_iter(HostGrid *h, const GridView &g, int order) {
+  std::vector<u32> next;
+  while (!h->frontier.empty()) {
+    h->iters++;
     next.clear();
-    size_t n = cur.size();
+    size_t n = h->frontier.size();
     for (size_t k = 0; k < n; k++) {
-      size_t kk = order == 2 ? n - 1 - k : (order == 1 ? (k * 7919u) % n : k);
-      if (order == 1 && n % 7919u == 0) kk = k;
+      size_t kk = order == 2 ? n - 1 - k : (order == 1 && n % 7919u != 0 ? (k * 7919u) % n : k);
       u32 push[9];
-      int np = u_iter_entry(g, table[cur[kk]], cur[kk], push);
-      relaxed++;
+      int np = u_iter_entry(g, h->table[h->frontier[kk]], h->frontier[kk], push);
+      h->relaxed++;
       for (int j = 0; j < np; j++) next.push_back(push[j]);
     }
-    cur.swap(next);
+    h->frontier.swap(next);
   }
-  (void)nt;
-  if (rings) {  // steppers.fut:189-224, sparse form
-    size_t n = rings->off.size() - 1;
-    std::vector<char> pass(n);
-    for (size_t k = 0; k < n; k++) {
-      bool ok = true;
-      for (int64_t t = rings->off[k]; t < rings->off[k + 1] && ok; t++) {
-        size_t o = (size_t)rings->y[t] * h->pitch + (rings->x[t] >> 5);
-        u32 bit = 1u << (rings->x[t] & 31);
-        U4 hd = g.head_in[o];
-        int dy = (hd.x & bit) ? ((hd.y & bit) ? -1 : 1) : 0, dx = (hd.z & bit) ? ((hd.w & bit) ? -1 : 1) : 0;
-        if ((g.calc[o] & bit) || dy != rings->cy[t] || dx != rings->cx[t]) ok = false;
-      }
-      pass[k] = ok;
+}
+
+void do_rings(HostGrid *h, const GridView &g) {  // steppers.fut:189-224, sparse form
+  if (!h->has_rings) return;
+  const Rings &R = h->rings;
+  size_t n = R.off.size() - 1;
+  std::vector<char> pass(n);
+  for (size_t k = 0; k < n; k++) {
+    bool ok = true;
+    for (int64_t t = R.off[k]; t < R.off[k + 1] && ok; t++) {
+      size_t o = (size_t)(R.y[t] - h->row0) * h->pitch + (R.x[t] >> 5);
+      u32 bit = 1u << (R.x[t] & 31);
+      U4 hd = g.head_in[o];
+      int dy = (hd.x & bit) ? ((hd.y & bit) ? -1 : 1) : 0, dx = (hd.z & bit) ? ((hd.w & bit) ? -1 : 1) : 0;
+      if ((g.calc[o] & bit) || dy != R.cy[t] || dx != R.cx[t]) ok = false;
     }
-    for (size_t k = 0; k < n; k++)
-      if (pass[k])
-        for (int64_t t = rings->off[k]; t < rings->off[k + 1]; t++) {
-          size_t o = (size_t)rings->y[t] * h->pitch + (rings->x[t] >> 5);
-          u32 bit = 1u << (rings->x[t] & 31);
-          if (rings->grant[t] == 1) g.mymx[o] |= (u64)bit; else g.mymx[o] |= (u64)bit << 32;
-        }
+    pass[k] = ok;
   }
+  for (size_t k = 0; k < n; k++)
+    if (pass[k])
+      for (int64_t t = R.off[k]; t < R.off[k + 1]; t++) {
+        size_t o = (size_t)(R.y[t] - h->row0) * h->pitch + (R.x[t] >> 5);
+        u32 bit = 1u << (R.x[t] & 31);
+        if (R.grant[t] == 1) g.mymx[o] |= (u64)bit; else g.mymx[o] |= (u64)bit << 32;
+      }
+}
+
+template <class MT>
+int64_t do_move(HostGrid *h, const GridView &g, int nt) {
   int64_t leaks = 0;
-  int mty = (h->gh + MT::TR - 1) / MT::TR, mtx = (h->pitch + MT::TW - 1) / MT::TW;
+  int mty = (h->own1 - h->own0 + MT::TR - 1) / MT::TR, mtx = (h->pitch + MT::TW - 1) / MT::TW;
   typename MT::Smem *sm = new typename MT::Smem();
   for (int ty = 0; ty < mty; ty++)
     for (int tx = 0; tx < mtx; tx++) {
@@ -151,17 +161,37 @@ int64_t tick(HostGrid *h, int chooser, u32 tape_bit, const Rings *rings, int nt,
     }
   delete sm;
   h->cur ^= 1;
-  if (stats) { stats[0] += iters; stats[1] += relaxed; }
   return leaks;
+}
+
+// variant: 0 = production tile shapes, 1 = tiny tiles + reversed frontier order, 2 = odd tiles + scrambled order
+void v_u_init(HostGrid *h, const GridView &g) {
+  switch (h->variant) {
+  case 1: u_init<UInitTile<2, 1>>(h, g); break;
+  case 2: u_init<UInitTile<5, 3>>(h, g); break;
+  default: u_init<UInitTile<16, 32>>(h, g); break;
+  }
+}
+int v_order(const HostGrid *h) { return h->variant == 1 ? 2 : h->variant == 2 ? 1 : 0; }
+int64_t v_move(HostGrid *h, const GridView &g, int nt) {
+  switch (h->variant) {
+  case 1: return do_move<MTile<3, 1>>(h, g, nt);
+  case 2: return do_move<MTile<4, 2>>(h, g, nt);
+  default: return do_move<MTile<8, 32>>(h, g, nt);
+  }
 }
 
 }  // namespace
 
 extern "C" {
 
-void *emul_new(int gh, int gw) { return make(gh, gw); }
+void *emul_new(int gh, int gw) { return make(gh, gw, 0, gh, 0, 0); }
+void *emul_band_new(int gh_global, int gw, int row_begin, int row_end, int variant) {
+  return make(gh_global, gw, row_begin, row_end, 2, variant);
+}
 void emul_free(void *p) { delete (HostGrid *)p; }
 
+// host arrays are WHOLE-grid [gh_global][gw]; the rows this grid holds (band + halo) are taken
 void emul_upload(void *p, const int8_t *uy, const int8_t *ux, const int8_t *dy, const int8_t *dx,
                  const uint32_t *color, const uint8_t *pref, const uint64_t *rng_state, uint64_t rng_inc) {
   HostGrid *h = (HostGrid *)p;
@@ -169,9 +199,11 @@ void emul_upload(void *p, const int8_t *uy, const int8_t *ux, const int8_t *dy, 
   for (auto &v : h->road) v = U4{0, 0, 0, 0};
   for (auto &v : h->head[h->cur]) v = U4{0, 0, 0, 0};
   for (auto &v : h->pref[h->cur]) v = 0;
-  for (int y = 0; y < h->gh; y++)
+  for (int yl = 0; yl < h->gh; yl++) {
+    int y = yl + h->row0;
+    if (y < 0 || y >= h->gh_global) continue;
     for (int x = 0; x < h->gw; x++) {
-      size_t i = (size_t)y * h->gw + x, o = (size_t)y * h->pitch + (x >> 5);
+      size_t i = (size_t)y * h->gw + x, o = (size_t)yl * h->pitch + (x >> 5);
       u32 bit = 1u << (x & 31);
       if (uy[i]) { h->road[o].x |= bit; if (uy[i] < 0) h->road[o].y |= bit; }
       if (ux[i]) { h->road[o].z |= bit; if (ux[i] < 0) h->road[o].w |= bit; }
@@ -179,45 +211,133 @@ void emul_upload(void *p, const int8_t *uy, const int8_t *ux, const int8_t *dy, 
       if (dy[i]) { hd.x |= bit; if (dy[i] < 0) hd.y |= bit; }
       if (dx[i]) { hd.z |= bit; if (dx[i] < 0) hd.w |= bit; }
       if (pref[i]) h->pref[h->cur][o] |= bit;
-      h->color[h->cur][(size_t)y * cp + x] = color[i];
-      h->rng[(size_t)y * cp + x] = rng_state[i];
+      h->color[h->cur][(size_t)yl * cp + x] = color[i];
+      h->rng[(size_t)yl * cp + x] = rng_state[i];
     }
+  }
   h->rng_inc = rng_inc;
 }
 
+// writes the OWNED rows into whole-grid arrays
 void emul_download(void *p, int8_t *dy, int8_t *dx, uint32_t *color, uint8_t *pref, uint64_t *rng_state) {
   HostGrid *h = (HostGrid *)p;
   size_t cp = (size_t)h->pitch * 32;
-  for (int y = 0; y < h->gh; y++)
+  for (int yl = h->own0; yl < h->own1; yl++) {
+    int y = yl + h->row0;
     for (int x = 0; x < h->gw; x++) {
-      size_t i = (size_t)y * h->gw + x, o = (size_t)y * h->pitch + (x >> 5);
+      size_t i = (size_t)y * h->gw + x, o = (size_t)yl * h->pitch + (x >> 5);
       u32 bit = 1u << (x & 31);
       const U4 &hd = h->head[h->cur][o];
       dy[i] = (hd.x & bit) ? ((hd.y & bit) ? -1 : 1) : 0;
       dx[i] = (hd.z & bit) ? ((hd.w & bit) ? -1 : 1) : 0;
       pref[i] = (h->pref[h->cur][o] & bit) ? 1 : 0;
-      color[i] = h->color[h->cur][(size_t)y * cp + x];
-      rng_state[i] = h->rng[(size_t)y * cp + x];
+      color[i] = h->color[h->cur][(size_t)yl * cp + x];
+      rng_state[i] = h->rng[(size_t)yl * cp + x];
     }
+  }
 }
 
-// variant: 0 = production tile shapes, 1 = tiny tiles (stress halo / pending protocol), 2 = medium
+void emul_set_rings(void *p, int64_t n_rings, const int64_t *off, const int64_t *ry, const int64_t *rx, const int8_t *cy,
+                    const int8_t *cx, const uint8_t *grant) {
+  HostGrid *h = (HostGrid *)p;
+  h->has_rings = n_rings >= 0 && off;
+  if (!h->has_rings) return;
+  Rings &R = h->rings;
+  int64_t tot = off[n_rings];
+  R.off.assign(off, off + n_rings + 1);
+  R.y.assign(ry, ry + tot); R.x.assign(rx, rx + tot);
+  R.cy.assign(cy, cy + tot); R.cx.assign(cx, cx + tot); R.grant.assign(grant, grant + tot);
+}
+
+// one whole tick of a single (non-band) grid
 int64_t emul_step(void *p, int variant, int nthreads, int chooser, uint32_t tape_bit, int64_t n_rings,
                   const int64_t *off, const int64_t *ry, const int64_t *rx, const int8_t *cy,
                   const int8_t *cx, const uint8_t *grant, unsigned *stats) {
   HostGrid *h = (HostGrid *)p;
-  Rings R, *rp = nullptr;
-  if (n_rings >= 0 && off) {
-    R.off.assign(off, off + n_rings + 1);
-    int64_t tot = off[n_rings];
-    R.y.assign(ry, ry + tot); R.x.assign(rx, rx + tot);
-    R.cy.assign(cy, cy + tot); R.cx.assign(cx, cx + tot); R.grant.assign(grant, grant + tot);
-    rp = &R;
+  h->variant = variant;
+  emul_set_rings(p, n_rings, off, ry, rx, cy, cx, grant);
+  GridView g = view(h, chooser, tape_bit);
+  h->iters = h->relaxed = 0;
+  v_u_init(h, g);
+  u_iter(h, g, v_order(h));
+  do_rings(h, g);
+  int64_t leaks = v_move(h, g, nthreads);
+  if (stats) { stats[0] += h->iters; stats[1] += h->relaxed; }
+  return leaks;
+}
+
+// ---- row-band protocol: same messages and phases as flowamok_band_* (fa_api.cu) ----
+void emul_band_msg_bytes(void *p, int64_t *state_bytes, int64_t *u_bytes) {
+  HostGrid *h = (HostGrid *)p;
+  *state_bytes = (int64_t)h->pitch * (2 * 16 + 2 * 4 + 128);
+  *u_bytes = (int64_t)h->pitch * (4 + 8);
+}
+void emul_band_pack_state(void *p, int side, void *buf) {
+  HostGrid *h = (HostGrid *)p;
+  const size_t P = (size_t)h->pitch;
+  const int r2 = side == 0 ? h->own0 : h->own1 - 2, rc = side == 0 ? h->own0 : h->own1 - 1;
+  char *b = (char *)buf;
+  memcpy(b, h->head[h->cur].data() + (size_t)r2 * P, 2 * P * 16);
+  memcpy(b + 2 * P * 16, h->pref[h->cur].data() + (size_t)r2 * P, 2 * P * 4);
+  memcpy(b + 2 * P * 20, h->color[h->cur].data() + (size_t)rc * P * 32, P * 128);
+}
+void emul_band_unpack_state(void *p, int side, const void *buf) {
+  HostGrid *h = (HostGrid *)p;
+  const size_t P = (size_t)h->pitch;
+  const int r2 = side == 0 ? h->own0 - 2 : h->own1, rc = side == 0 ? h->own0 - 1 : h->own1;
+  const char *b = (const char *)buf;
+  memcpy(h->head[h->cur].data() + (size_t)r2 * P, b, 2 * P * 16);
+  memcpy(h->pref[h->cur].data() + (size_t)r2 * P, b + 2 * P * 16, 2 * P * 4);
+  memcpy(h->color[h->cur].data() + (size_t)rc * P * 32, b + 2 * P * 20, P * 128);
+}
+void emul_band_u_begin(void *p, int chooser, uint32_t tape_bit) {
+  HostGrid *h = (HostGrid *)p;
+  GridView g = view(h, chooser, tape_bit);
+  v_u_init(h, g);
+  u_iter(h, g, v_order(h));
+}
+void emul_band_pack_u(void *p, int side, void *buf) {
+  HostGrid *h = (HostGrid *)p;
+  const size_t P = (size_t)h->pitch;
+  const int r = side == 0 ? h->own0 : h->own1 - 1;
+  char *b = (char *)buf;
+  memcpy(b, h->calc.data() + (size_t)r * P, P * 4);
+  memcpy(b + P * 4, h->mymx.data() + (size_t)r * P, P * 8);
+}
+int64_t emul_band_merge_u(void *p, int side, const void *buf, int wake) {  // k_band_merge
+  HostGrid *h = (HostGrid *)p;
+  GridView g = view(h, 0, 0);
+  const size_t P = (size_t)h->pitch;
+  const int ghost = side == 0 ? h->own0 - 1 : h->own1, own = side == 0 ? h->own0 : h->own1 - 1;
+  const u32 *rc = (const u32 *)buf;
+  const u64 *rm = (const u64 *)((const char *)buf + P * 4);
+  for (int w = 0; w < h->pitch; w++) {
+    size_t o = (size_t)ghost * P + w;
+    u32 nc = h->calc[o] | rc[w];
+    u64 nm = h->mymx[o] | rm[w];
+    if (nc == h->calc[o] && nm == h->mymx[o]) continue;
+    h->mymx[o] = nm; h->calc[o] = nc;
+    if (!wake) continue;
+    for (int dx = -1; dx <= 1; dx++) {
+      u32 q = u_try_queue(g, own, w + dx);
+      if (q != U_NONE) h->frontier.push_back(q & ~U_QUEUED);
+    }
   }
-  switch (variant) {  // variant: tile shapes / processing order of the frontier
-  case 1: return tick<MTile<3, 1>, UInitTile<2, 1>>(h, chooser, tape_bit, rp, nthreads, stats, 2);
-  case 2: return tick<MTile<4, 2>, UInitTile<5, 3>>(h, chooser, tape_bit, rp, nthreads, stats, 1);
-  default: return tick<MTile<8, 32>, UInitTile<16, 32>>(h, chooser, tape_bit, rp, nthreads, stats, 0);
-  }
+  return (int64_t)h->frontier.size();
+}
+void emul_band_u_resume(void *p) {
+  HostGrid *h = (HostGrid *)p;
+  GridView g = view(h, 0, 0);
+  u_iter(h, g, v_order(h));
+}
+void emul_band_rings(void *p) {
+  HostGrid *h = (HostGrid *)p;
+  GridView g = view(h, 0, 0);
+  do_rings(h, g);
+}
+int64_t emul_band_move(void *p, int chooser, uint32_t tape_bit) {
+  HostGrid *h = (HostGrid *)p;
+  GridView g = view(h, chooser, tape_bit);
+  return v_move(h, g, 7);
 }
 }

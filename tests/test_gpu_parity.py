@@ -282,3 +282,47 @@ def test_grid_clone_is_independent(ctx):
         c.step(False, 1)
     assert_state_equal(state_of(og), dev_state(c), "clone after 3 ticks")
     assert_state_equal(state_of(og), dev_state(g), "original after 3 ticks")
+
+
+@pytest.mark.parametrize("n_bands,perfect", [(2, False), (3, False), (4, True)])
+def test_row_bands_on_one_gpu_equal_single_grid(ctx, n_bands, perfect):
+    """BASELINE config 5 shape at a size the oracle finishes in seconds: the grid split into row bands (the
+    flowamok_band_* entry points, messages handed over in-process) must equal the oracle's single grid and the
+    single-grid CUDA run, every few ticks."""
+    from flowamok_b200.bands import DeviceBand, LocalBands, split_rows
+    if perfect:
+        gh, gw = 256, 1300
+        arrs, rings = synth_ref.generate(gh, gw, seed=2)
+    else:
+        gh, gw = 150, 2100
+        arrs, rings = random_grid(9, gh, gw, n_lines=300, car_p=0.8, weird_p=0.02, offroad_p=0.01), None
+    bands = []
+    for lo, hi in split_rows(gh, n_bands, 16 if perfect else 1):
+        b = DeviceBand(ctx, gh, gw, lo, hi)
+        b.grid.upload(**arrs)
+        if perfect:
+            off, idx, cy, cx, grant = rings
+            ys = idx // gw
+            keep = [k for k in range(len(off) - 1) if lo <= ys[off[k]:off[k + 1]].min() and ys[off[k]:off[k + 1]].max() < hi]
+            sel = np.concatenate([np.arange(off[k], off[k + 1]) for k in keep]) if keep else np.zeros(0, np.int64)
+            o2 = np.concatenate([[0], np.cumsum([off[k + 1] - off[k] for k in keep])]).astype(np.int64)
+            b.grid.set_cycles(o2, ys[sel], idx[sel] % gw, cy[sel], cx[sel], grant[sel])
+        bands.append(b)
+    run = LocalBands(bands)
+    og, ch = oracle_grid(arrs), O.Chooser(O.CHOOSE_RANDOM)
+    leaks = 0
+    for t in range(12):
+        n, _l = og.step_perfect_sparse(ch, rings) if perfect else og.step_quick(ch)
+        leaks += n
+        run.tick(perfect)
+        if t % 3 == 2:
+            want = state_of(og)
+            got = {k: np.zeros((gh, gw), want[k].dtype) for k in STATE_FIELDS}
+            for b in bands:
+                d = b.grid.download(fields=STATE_FIELDS)
+                lo, hi = b.rows
+                for k in STATE_FIELDS:
+                    got[k][lo:hi] = d[k][lo:hi]
+            assert_state_equal(want, got, f"{n_bands} bands tick {t}")
+    assert sum(b.leaks() for b in bands) == leaks
+    assert run.rounds >= 12
