@@ -132,8 +132,8 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size", type=int, default=16384)
-    ap.add_argument("--mode", default="quick", choices=["quick", "perfect"])
+    ap.add_argument("--size", type=int, default=0, help="grid edge; default 16384 on 1 GPU, 65536 on several")
+    ap.add_argument("--mode", default="", choices=["", "quick", "perfect"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -141,13 +141,20 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # BASELINE.json: config 4 (16384^2, quick) is the 1-GPU headline; config 5 (65536^2 row bands, perfect) the multi-GPU one
+    if not args.size:
+        args.size = 16384 if world == 1 else 65536
+    if not args.mode:
+        args.mode = "quick" if world == 1 else "perfect"
 
     if args.impl == "reference":
         return run_reference(args, rank)
 
+    import ctypes as C
     import numpy as np
     import torch
     import flowamok_b200 as fa
+    from flowamok_b200.bands import BandRunner, DeviceBand, split_rows
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (flowamok_b200 has no CPU path)")
@@ -162,17 +169,40 @@ def main():
     cells = S * S
     with torch.cuda.stream(stream):
         ctx = fa.Context(local_rank, stream.cuda_stream)
-        g = ctx.grid(S, S)
-        g.generate_synthetic(seed=1 + rank, density16=6554, ring_full16=2)
+        if world == 1:
+            g = ctx.grid(S, S)
+            rows = (0, S)
+            runner = None
+        else:
+            rows = split_rows(S, world, 16)[rank]
+            band = DeviceBand(ctx, S, S, rows[0], rows[1])
+            g = band.grid
+            runner = BandRunner(band, rank, world)
+        g.generate_synthetic(seed=1, density16=6554, ring_full16=2)
         n_rings, _ = g.cycle_count()
-        g.step(perfect, args.warmup, leaks=False)
-        ctx.sync()
-        g.stats()
+
+        def run_ticks(n, leaks=False):
+            if runner is None:
+                return g.step(perfect, n, leaks=leaks)
+            runner.step(perfect, n)
+            return band.leaks() if leaks else None
 
         def barrier():
             if dist is not None:
                 dist.barrier()
             torch.cuda.synchronize()
+
+        def maxr(x):
+            if dist is None:
+                return x
+            t = torch.tensor([x], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        run_ticks(args.warmup)
+        ctx.sync()
+        g.stats()
+        rounds0 = runner.rounds if runner else 0
 
         # ---- device-resident throughput: K ticks, inputs already in HBM, CUDA events on the launching stream
         sampler = ClockSampler(local_rank)
@@ -180,88 +210,99 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record(stream)
-        g.step(perfect, args.steps, leaks=False)
+        run_ticks(args.steps)
         e1.record(stream)
         barrier()
-        ms = e0.elapsed_time(e1)
+        ms = maxr(e0.elapsed_time(e1))
         clocks = sampler.stop()
         st = g.stats()
-        if dist is not None:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        value = world * cells * args.steps / (ms * 1e-3) / 1e9
+        rounds = (runner.rounds - rounds0) if runner else 0
+        value = cells * args.steps / (ms * 1e-3) / 1e9
 
-        # ---- per-kernel device time (events between the launches, same stream)
-        prof_ticks = min(50, args.steps)
-        prof = g.step_profile(perfect, prof_ticks)
-        prof_total = sum(prof.values())
+        # ---- per-kernel device time (events between the launches, same stream); single-grid path only
+        prof, prof_ticks = None, min(50, args.steps)
+        if runner is None:
+            prof = g.step_profile(perfect, prof_ticks)
 
         # ---- end to end through the C ABI with HOST buffers: upload + K ticks + leak count + download
         e2e = None
         if not args.no_e2e:
-            host = g.download()
-            pin = {}
-            for k in ("uy", "ux", "dy", "dx", "color", "pref", "rng_state"):
-                tt = torch.from_numpy(host[k]).pin_memory()
-                pin[k] = tt.numpy()
-            out = {k: torch.empty_like(torch.from_numpy(host[k])).pin_memory().numpy()
-                   for k in ("dy", "dx", "color", "pref", "rng_state")}
+            fields_up = ("uy", "ux", "dy", "dx", "color", "pref", "rng_state")
+            fields_dn = ("dy", "dx", "color", "pref", "rng_state")
+            host = g.download()                              # whole-grid shaped arrays; only my rows are filled
+            lo, hi = rows
+            pinned = world == 1                              # several ranks: pageable (bounded host pinning)
+            def hostbuf(a):
+                t = torch.from_numpy(np.ascontiguousarray(a[lo:hi]))
+                return (t.pin_memory() if pinned else t).numpy()
+            up = {k: hostbuf(host[k]) for k in fields_up}
             del host
-            h2d = sum(v.nbytes for v in pin.values())
-            d2h = sum(v.nbytes for v in out.values()) + 8
-            import ctypes as C
+            dn = {k: np.empty_like(up[k]) for k in fields_dn}
+            if pinned:
+                dn = {k: torch.from_numpy(v).pin_memory().numpy() for k, v in dn.items()}
+            h2d = sum(v.nbytes for v in up.values())
+            d2h = sum(v.nbytes for v in dn.values()) + 8
+
+            def band_ptr(a):                                 # the ABI takes whole-grid base pointers
+                return a.ctypes.data - lo * a.strides[0]
             barrier()
             t0 = time.perf_counter()
-            g.upload(**pin, rng_inc=fa.PCG_INC)
-            leaks = g.step(perfect, args.steps, leaks=True)
+            ctx.check(ctx.L.flowamok_grid_upload(ctx.h, g.h, *[band_ptr(up[k]) for k in fields_up], fa.PCG_INC))
+            leaks = run_ticks(args.steps, leaks=True)
             inc = C.c_uint64()
-            ctx.check(ctx.L.flowamok_grid_download(ctx.h, g.h, None, None, out["dy"].ctypes.data, out["dx"].ctypes.data,
-                                                   out["color"].ctypes.data, out["pref"].ctypes.data,
-                                                   out["rng_state"].ctypes.data, C.byref(inc)))
+            ctx.check(ctx.L.flowamok_grid_download(ctx.h, g.h, None, None, *[band_ptr(dn[k]) for k in fields_dn], C.byref(inc)))
             barrier()
-            dt = time.perf_counter() - t0
+            dt = maxr(time.perf_counter() - t0)
             if dist is not None:
-                t = torch.tensor([dt], device="cuda")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                dt = float(t.item())
-            e2e = {"value": world * cells * args.steps / dt / 1e9, "unit": "GCUPS",
+                t = torch.tensor([h2d, d2h, int(leaks)], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t)
+                h2d, d2h, leaks = (float(x) for x in t.tolist())
+            e2e = {"value": cells * args.steps / dt / 1e9, "unit": "GCUPS",
                    "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
-                   "seconds": dt, "leaks": int(leaks),
-                   "what": "flowamok_grid_upload (pinned host record-of-arrays) + flowamok_step_quick x steps "
-                           "+ leak count + flowamok_grid_download, wall clock"}
-            del pin, out
+                   "seconds": dt, "leaks": int(leaks), "host_memory": "pinned" if pinned else "pageable",
+                   "what": "flowamok_grid_upload (host record-of-arrays, every band its rows) + steps ticks through the "
+                           "C ABI + leak count + flowamok_grid_download, wall clock, max over ranks"}
+            del up, dn
 
     peak, peak_src = measured_peak()
     per_gpu_gcups = value / world
     achieved = per_gpu_gcups * B_ALG  # GB/s of algorithmic traffic per GPU
+    kernels = "k_u_init + k_u_iter" + (" + k_rings" if perfect else "") + " + k_move"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src,
-                "what": "whole tick (k_u_init + k_u_iter [+ k_rings] + k_move), 12 algorithmic B per cell-update (SURVEY 8d)",
-                "kernel_ms_per_tick": {k: v / prof_ticks for k, v in prof.items()},
-                "dominant_kernel": max(prof, key=prof.get),
-                "dominant_share": max(prof.values()) / prof_total if prof_total else None}
+                "what": f"whole tick ({kernels}), 12 algorithmic B per cell-update (SURVEY 8d), per GPU"}
+    if prof:
+        tot = sum(prof.values())
+        roofline.update({"kernel_ms_per_tick": {k: v / prof_ticks for k, v in prof.items()},
+                         "dominant_kernel": max(prof, key=prof.get),
+                         "dominant_share": max(prof.values()) / tot if tot else None})
+    launches_per_tick = 3 + (1 if perfect and n_rings else 0)
+    gpu_launches = launches_per_tick * args.steps
+    if runner is not None:   # + per convergence round: 2 pack copies are memcpys; k_band_merge x sides, k_u_iter resumes
+        sides = (1 if rank > 0 else 0) + (1 if rank < world - 1 else 0)
+        gpu_launches += rounds * sides + max(0, rounds - args.steps)
     line = {"metric": "cell-updates/sec", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak" if world == 1 else "strong",
             "vs_baseline": None, "dtype": "u32 bit-planes (32 cells per word) + u32 colour payload",
             "data": "synthetic",
             "config": {"workload": f"synthetic-{S}x{S}-{args.mode} (SURVEY App. E, seed 1, 10% of road cells occupied)",
-                       "grid": [S, S], "mode": args.mode, "rings": int(n_rings),
-                       "parallelism": "1 grid" if world == 1 else f"{world} independent {S}x{S} grids (one per GPU)",
-                       "l2": f"state {cells * 9.75 / 1e9:.2f} GB per tick >> 126 MB L2: inputs larger than L2, no flush"},
+                       "grid": [S, S], "mode": args.mode, "rings_on_rank0": int(n_rings),
+                       "parallelism": "1 grid" if world == 1 else
+                       f"{world} row bands of {S // world} rows, per-tick halo rows over NCCL send/recv + 1 all-reduced convergence word",
+                       "l2": f"state {cells / world * 9.75 / 1e9:.2f} GB per GPU per tick >> 126 MB L2: inputs larger than L2, no flush"},
             "fixpoint": {"iterations_per_tick": st["passes"] / max(1, st["ticks"]),
                          "worklist_entries_relaxed_per_tick": st["sweeps"] / max(1, st["ticks"]),
-                         "plane_words": (S // 32) * S},
-            "roofline": roofline, "clocks": clocks, "gpu_launches": (3 + (1 if perfect and n_rings else 0)) * args.steps,
-            "e2e": e2e}
-    if rank == 0 and not args.no_cpu and world >= 1:
+                         "band_convergence_rounds_per_tick": rounds / args.steps if runner else None},
+            "roofline": roofline, "clocks": clocks, "gpu_launches": int(gpu_launches), "e2e": e2e}
+    if rank == 0 and not args.no_cpu:
         try:
             g1, dt1, thr = cpu_oracle_run(S, 64, 2, 1)
-            rows = int(15.0 / (dt1 / (64 * S * 2) * S * 6))
-            rows = max(32, min(S, (rows // 16) * 16))
-            gc, dt, thr = cpu_oracle_run(S, rows, 5, 1)
+            rows_c = int(15.0 / (dt1 / (64 * S * 2) * S * 6))
+            rows_c = max(32, min(S, (rows_c // 16) * 16))
+            gc, dt, thr = cpu_oracle_run(S, rows_c, 5, 1)
             line["cpu_baseline"] = {"value": gc, "unit": "GCUPS", "cores": thr, "kind": "port",
-                                    "sample": f"{rows}x{S} band of the same network, 5 ticks, quick mode, {dt:.1f} s"}
+                                    "sample": f"{rows_c}x{S} band of the same network, 5 ticks, quick mode, {dt:.1f} s"}
         except Exception as e:  # the oracle is only a reported baseline
             line["cpu_baseline"] = {"value": None, "unit": "GCUPS", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
     if rank == 0:
