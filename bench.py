@@ -177,6 +177,7 @@ def main():
             rows = split_rows(S, world, 16)[rank]
             band = DeviceBand(ctx, S, S, rows[0], rows[1])
             g = band.grid
+            band.comm_init(rank, world)               # the library's own NCCL communicator: ticks run natively
             runner = BandRunner(band, rank, world)
         g.generate_synthetic(seed=1, density16=6554, ring_full16=2)
         n_rings, _ = g.cycle_count()
@@ -227,7 +228,10 @@ def main():
         # ---- end to end through the C ABI with HOST buffers: upload + K ticks + leak count + download
         e2e = None
         if not args.no_e2e:
-            fields_up = ("uy", "ux", "dy", "dx", "color", "pref", "rng_state")
+            # one grid: the whole value (roads included); row bands: the car state of the owned rows (roads, cycles
+            # and halo rows stay resident: flowamok_grid_upload_cars)
+            fields_up = ("uy", "ux", "dy", "dx", "color", "pref", "rng_state") if world == 1 else \
+                        ("dy", "dx", "color", "pref", "rng_state")
             fields_dn = ("dy", "dx", "color", "pref", "rng_state")
             host = g.download()                              # whole-grid shaped arrays; only my rows are filled
             lo, hi = rows
@@ -237,9 +241,7 @@ def main():
                 return (t.pin_memory() if pinned else t).numpy()
             up = {k: hostbuf(host[k]) for k in fields_up}
             del host
-            dn = {k: np.empty_like(up[k]) for k in fields_dn}
-            if pinned:
-                dn = {k: torch.from_numpy(v).pin_memory().numpy() for k, v in dn.items()}
+            dn = {k: up[k] for k in fields_dn}               # the result lands in the buffers the input came from
             h2d = sum(v.nbytes for v in up.values())
             d2h = sum(v.nbytes for v in dn.values()) + 8
 
@@ -247,7 +249,10 @@ def main():
                 return a.ctypes.data - lo * a.strides[0]
             barrier()
             t0 = time.perf_counter()
-            ctx.check(ctx.L.flowamok_grid_upload(ctx.h, g.h, *[band_ptr(up[k]) for k in fields_up], fa.PCG_INC))
+            if world == 1:
+                ctx.check(ctx.L.flowamok_grid_upload(ctx.h, g.h, *[band_ptr(up[k]) for k in fields_up], fa.PCG_INC))
+            else:
+                band.upload_cars(*[band_ptr(up[k]) for k in fields_up])
             leaks = run_ticks(args.steps, leaks=True)
             inc = C.c_uint64()
             ctx.check(ctx.L.flowamok_grid_download(ctx.h, g.h, None, None, *[band_ptr(dn[k]) for k in fields_dn], C.byref(inc)))
@@ -260,8 +265,9 @@ def main():
             e2e = {"value": cells * args.steps / dt / 1e9, "unit": "GCUPS",
                    "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                    "seconds": dt, "leaks": int(leaks), "host_memory": "pinned" if pinned else "pageable",
-                   "what": "flowamok_grid_upload (host record-of-arrays, every band its rows) + steps ticks through the "
-                           "C ABI + leak count + flowamok_grid_download, wall clock, max over ranks"}
+                   "what": ("flowamok_grid_upload (host record-of-arrays)" if world == 1 else
+                            "flowamok_grid_upload_cars (car state of every band's rows)") +
+                           " + steps ticks through the C ABI + leak count + flowamok_grid_download, wall clock, max over ranks"}
             del up, dn
 
     peak, peak_src = measured_peak()

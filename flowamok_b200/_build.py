@@ -15,7 +15,7 @@ DEPS = [CSRC / "fa_api.cu", CSRC / "fa_kernels.cuh", CSRC / "fa_tiles.h", CSRC /
         PKG.parent / "include" / "flowamok.h"]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "-ldl"]
 
 
 def nvcc_path() -> str:

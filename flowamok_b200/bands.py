@@ -53,6 +53,29 @@ class DeviceBand:
         if self.foreign_stream:
             torch.cuda.synchronize(self.device)
 
+    native = False
+
+    def comm_init(self, rank, world, group=None):
+        """Join the library's own NCCL communicator (unique id from rank 0, broadcast through torch.distributed);
+        afterwards BandRunner.step runs whole ticks inside the library (flowamok_band_step)."""
+        ident = (C.c_ubyte * 128)()
+        if rank == 0:
+            if self.L.flowamok_band_comm_id(ident):
+                raise RuntimeError("NCCL is not available to the library")
+        obj = [bytes(ident)]
+        dist.broadcast_object_list(obj, src=0, group=group)
+        self._c(self.L.flowamok_band_comm_init(self.ctx.h, obj[0], rank, world))
+        self.native = True
+
+    def step_native(self, perfect, n_ticks):
+        r = C.c_int64()
+        self._c(self.L.flowamok_band_step(self.ctx.h, self.grid.h, int(perfect), n_ticks, C.byref(r)))
+        return r.value
+
+    def upload_cars(self, dy, dx, color, pref, rng_state):
+        """whole-grid base pointers (ints); only the owned rows are read"""
+        self._c(self.L.flowamok_grid_upload_cars(self.ctx.h, self.grid.h, dy, dx, color, pref, rng_state))
+
     def buffer(self, nbytes):
         return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
 
@@ -169,6 +192,10 @@ class BandRunner:
         self.ticks += 1
 
     def step(self, perfect: bool, n_ticks: int):
+        if getattr(self.b, "native", False):      # the same protocol, driven inside the library over its own NCCL comm
+            self.rounds = self.b.step_native(perfect, n_ticks)
+            self.ticks += n_ticks
+            return
         for _ in range(n_ticks):
             self.tick(perfect)
 

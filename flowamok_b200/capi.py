@@ -72,6 +72,10 @@ def lib():
         "flowamok_band_rings": (C.c_int, [P, P]),
         "flowamok_band_move": (C.c_int, [P, P]),
         "flowamok_band_leaks": (C.c_int, [P, P, C.POINTER(I64)]),
+        "flowamok_band_comm_id": (C.c_int, [P]),
+        "flowamok_band_comm_init": (C.c_int, [P, P, C.c_int, C.c_int]),
+        "flowamok_band_step": (C.c_int, [P, P, C.c_int, I64, C.POINTER(I64)]),
+        "flowamok_grid_upload_cars": (C.c_int, [P, P, P, P, P, P, P]),
         "flowamok_version": (C.c_char_p, []),
         # Futhark-generated-library surface (include/flowamok_futhark.h)
         "futhark_context_config_new": (P, []),

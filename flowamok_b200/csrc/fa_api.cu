@@ -4,6 +4,8 @@
 #include "../../include/flowamok.h"
 
 #include <cub/device/device_scan.cuh>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -18,7 +20,37 @@
 
 using namespace fa;
 
+// NCCL is reached through dlopen: the process (torch) has already loaded its own libnccl.so.2, and the library
+// must keep loading on machines without NCCL.
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool load() {
+    if (lib) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) return false;
+#define SYM(f, name) f = (decltype(f))dlsym(lib, name); if (!f) return false
+    SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
+    SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv"); SYM(AllReduce, "ncclAllReduce"); SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd"); SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    return true;
+  }
+};
+static NcclApi g_nccl;
+
 struct flowamok_context {
+  ncclComm_t comm = nullptr;   // row-band communicator (flowamok_band_comm_init)
+  int rank = 0, world = 1;
   int device;
   cudaStream_t stream;
   bool own_stream;
@@ -57,6 +89,11 @@ struct flowamok_grid {
   u32 *ustate;            // per word: U_NONE or entry index (| U_QUEUED)
   int ntx, nty, mtx, mty;
   Diag base;  // diag values already reported
+  // native band stepping: message buffers [side] and the all-reduced convergence word
+  char *msg_s_send[2] = {nullptr, nullptr}, *msg_s_recv[2] = {nullptr, nullptr};
+  char *msg_u_send[2] = {nullptr, nullptr}, *msg_u_recv[2] = {nullptr, nullptr};
+  unsigned int *d_woken = nullptr, *h_woken = nullptr;
+  long long band_rounds = 0;
 };
 
 static int fail(flowamok_context *ctx, const char *fmt, ...) {
@@ -125,6 +162,7 @@ int flowamok_context_new(flowamok_context **out, int device, void *stream) {
 
 int flowamok_context_free(flowamok_context *ctx) {
   if (!ctx) return 0;
+  if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return 0;
@@ -228,6 +266,8 @@ int flowamok_grid_free(flowamok_context *ctx, flowamok_grid *g) {
   cudaFree(g->road);
   for (int k = 0; k < 2; k++) { cudaFree(g->head[k]); cudaFree(g->pref[k]); cudaFree(g->color[k]); }
   cudaFree(g->calc); cudaFree(g->mymx); cudaFree(g->rng); cudaFree(g->is); cudaFree(g->diag);
+  for (int k = 0; k < 2; k++) { cudaFree(g->msg_s_send[k]); cudaFree(g->msg_s_recv[k]); cudaFree(g->msg_u_send[k]); cudaFree(g->msg_u_recv[k]); }
+  cudaFree(g->d_woken); if (g->h_woken) cudaFreeHost(g->h_woken);
   cudaFree(g->table); cudaFree(g->qlist[0]); cudaFree(g->qlist[1]); cudaFree(g->qcnt); cudaFree(g->ustate);
   cudaFree(g->ring_cells); cudaFree(g->ring_off); cudaFree(g->leak_plane);
   cudaFreeHost(g->h_diag);
@@ -857,6 +897,126 @@ int flowamok_band_move(flowamok_context *ctx, flowamok_grid *g) {
   GridView v = make_view(g);
   return launch_move(ctx, g, v, nullptr);
 }
+#define NC(call)                                                                                   \
+  do {                                                                                             \
+    ncclResult_t r_ = (call);                                                                      \
+    if (r_ != ncclSuccess) return fail(ctx, "%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); \
+  } while (0)
+
+/* NCCL bootstrap: rank 0 calls comm_id and broadcasts the 128 bytes (e.g. with torch.distributed); every rank then
+ * calls comm_init on its own context. */
+int flowamok_band_comm_id(void *id128) {
+  if (!g_nccl.load()) return 1;
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return 1;
+  memcpy(id128, &id, sizeof id);
+  return 0;
+}
+int flowamok_band_comm_init(flowamok_context *ctx, const void *id128, int rank, int world) {
+  if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
+  if (!g_nccl.load()) return fail(ctx, "libnccl.so.2 could not be loaded: %s", dlerror());
+  CU(cudaSetDevice(ctx->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  NC(g_nccl.CommInitRank(&ctx->comm, world, id, rank));
+  ctx->rank = rank; ctx->world = world;
+  return 0;
+}
+
+// swap `bytes` with both neighbours: send[side] goes to the neighbour on that side, recv[side] comes from it
+static int band_swap(flowamok_context *ctx, char *const send[2], char *const recv[2], size_t bytes) {
+  NC(g_nccl.GroupStart());
+  for (int side = 0; side < 2; side++) {
+    int peer = side == 0 ? ctx->rank - 1 : ctx->rank + 1;
+    if (peer < 0 || peer >= ctx->world) continue;
+    NC(g_nccl.Send(send[side], bytes, ncclUint8, peer, ctx->comm, ctx->stream));
+    NC(g_nccl.Recv(recv[side], bytes, ncclUint8, peer, ctx->comm, ctx->stream));
+  }
+  NC(g_nccl.GroupEnd());
+  return 0;
+}
+
+/* n_ticks of stepper_quick / stepper_perfect on this band, the whole per-tick protocol (see above) driven from here
+ * with NCCL send/recv on the context's stream: one host synchronisation per convergence round, no Python in the loop. */
+int flowamok_band_step(flowamok_context *ctx, flowamok_grid *g, int perfect, int64_t n_ticks, int64_t *rounds) {
+  if (band_check(ctx, g, 0)) return 1;
+  const bool multi = ctx->world > 1;
+  if (multi && !ctx->comm) return fail(ctx, "flowamok_band_comm_init has not been called");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t sb = (size_t)g->pitch * (2 * 16 + 2 * 4 + 128), ub = (size_t)g->pitch * (4 + 8);
+  if (!g->d_woken) {
+    for (int k = 0; k < 2; k++) {
+      CU(cudaMalloc(&g->msg_s_send[k], sb)); CU(cudaMalloc(&g->msg_s_recv[k], sb));
+      CU(cudaMalloc(&g->msg_u_send[k], ub)); CU(cudaMalloc(&g->msg_u_recv[k], ub));
+    }
+    CU(cudaMalloc(&g->d_woken, 4));
+    CU(cudaMallocHost(&g->h_woken, 4));
+  }
+  auto has = [&](int side) { int peer = side == 0 ? ctx->rank - 1 : ctx->rank + 1; return multi && peer >= 0 && peer < ctx->world; };
+  auto swap_u = [&](int wake) -> int {
+    for (int side = 0; side < 2; side++)
+      if (has(side) && flowamok_band_pack_u(ctx, g, side, g->msg_u_send[side])) return 1;
+    if (band_swap(ctx, g->msg_u_send, g->msg_u_recv, ub)) return 1;
+    for (int side = 0; side < 2; side++)
+      if (has(side) && flowamok_band_merge_u(ctx, g, side, g->msg_u_recv[side], wake, nullptr)) return 1;
+    return 0;
+  };
+  for (int64_t t = 0; t < n_ticks; t++) {
+    if (multi) {
+      for (int side = 0; side < 2; side++)
+        if (has(side) && flowamok_band_pack_state(ctx, g, side, g->msg_s_send[side])) return 1;
+      if (band_swap(ctx, g->msg_s_send, g->msg_s_recv, sb)) return 1;
+      for (int side = 0; side < 2; side++)
+        if (has(side) && flowamok_band_unpack_state(ctx, g, side, g->msg_s_recv[side])) return 1;
+    }
+    if (flowamok_band_u_begin(ctx, g)) return 1;
+    while (multi) {
+      if (swap_u(1)) return 1;
+      CU(cudaMemcpyAsync(g->d_woken, &g->is->qn[1], 4, cudaMemcpyDeviceToDevice, st));
+      NC(g_nccl.AllReduce(g->d_woken, g->d_woken, 1, ncclUint32, ncclMax, ctx->comm, st));
+      CU(cudaMemcpyAsync(g->h_woken, g->d_woken, 4, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));            // the host round trip of this round: one 4-byte word
+      g->band_rounds++;
+      if (*g->h_woken == 0) break;
+      if (flowamok_band_u_resume(ctx, g)) return 1;
+    }
+    if (perfect) {
+      if (flowamok_band_rings(ctx, g)) return 1;
+      if (multi && swap_u(0)) return 1;
+    }
+    if (flowamok_band_move(ctx, g)) return 1;
+  }
+  if (rounds) *rounds = g->band_rounds;
+  return 0;
+}
+
+/* like flowamok_grid_upload for the car state only: heading, colour, preference and rng of the OWNED rows from
+ * whole-grid host arrays; roads, cycles and halo rows are left alone (halo rows are refreshed by the next tick's swap) */
+int flowamok_grid_upload_cars(flowamok_context *ctx, flowamok_grid *g, const int8_t *dy, const int8_t *dx, const uint32_t *color,
+                              const uint8_t *pref, const uint64_t *rng_state) {
+  if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
+  if (!g || !dy || !dx || !color || !pref || !rng_state) return fail(ctx, "upload_cars needs every field");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int lo = g->row0 + g->own0, owned = g->own1 - g->own0;
+  const size_t n = (size_t)owned * g->gw, cp = (size_t)g->pitch * 32;
+  int8_t *tmp = nullptr;
+  CU(cudaMalloc(&tmp, n * 3));
+  const void *src[3] = {dy, dx, pref};
+  for (int k = 0; k < 3; k++) CU(cudaMemcpyAsync(tmp + n * k, (const int8_t *)src[k] + (size_t)lo * g->gw, n, cudaMemcpyHostToDevice, st));
+  k_pack<<<nblk((long long)g->nwords * 32, 256), 256, 0, st>>>(g->gh, g->gw, g->pitch, -g->own0, owned, nullptr, nullptr, tmp, tmp + n,
+                                                              (const uint8_t *)(tmp + 2 * n), nullptr, g->head[g->cur], g->pref[g->cur]);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy2DAsync(g->color[g->cur] + (size_t)g->own0 * cp, cp * 4, color + (size_t)lo * g->gw, (size_t)g->gw * 4,
+                       (size_t)g->gw * 4, owned, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpy2DAsync(g->rng + (size_t)g->own0 * cp, cp * 8, rng_state + (size_t)lo * g->gw, (size_t)g->gw * 8,
+                       (size_t)g->gw * 8, owned, cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaFree(tmp));
+  return 0;
+}
+
 int flowamok_band_leaks(flowamok_context *ctx, flowamok_grid *g, int64_t *n_leaks) {
   if (!g) return fail(ctx, "null grid");
   CU(cudaSetDevice(ctx->device));

@@ -140,6 +140,16 @@ int flowamok_band_u_resume(flowamok_context *ctx, flowamok_grid *g);
 int flowamok_band_rings(flowamok_context *ctx, flowamok_grid *g);
 int flowamok_band_move(flowamok_context *ctx, flowamok_grid *g);
 int flowamok_band_leaks(flowamok_context *ctx, flowamok_grid *g, int64_t *n_leaks);
+/* The same protocol driven natively: NCCL send/recv + one all-reduced word on the context's stream, no host code
+ * per phase.  comm_id (rank 0) produces the 128-byte NCCL unique id to broadcast; comm_init joins the communicator;
+ * band_step runs n_ticks (rounds: total convergence rounds so far, may be NULL). */
+int flowamok_band_comm_id(void *id128);
+int flowamok_band_comm_init(flowamok_context *ctx, const void *id128, int rank, int world);
+int flowamok_band_step(flowamok_context *ctx, flowamok_grid *g, int perfect, int64_t n_ticks, int64_t *rounds);
+/* car state only (heading, colour, preference, rng) of the owned rows from whole-grid host arrays; roads, cycles
+ * and halo rows are left alone.  Synchronous. */
+int flowamok_grid_upload_cars(flowamok_context *ctx, flowamok_grid *g, const int8_t *dy, const int8_t *dx, const uint32_t *color,
+                              const uint8_t *pref, const uint64_t *rng_state);
 
 /* library identification */
 const char *flowamok_version(void);

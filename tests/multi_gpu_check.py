@@ -30,6 +30,8 @@ def main():
             lo, hi = split_rows(S, world, 16)[rank]
             band = DeviceBand(ctx, S, S, lo, hi)
             band.grid.generate_synthetic(seed=5)
+            if os.environ.get("CHECK_NATIVE", "1") == "1":
+                band.comm_init(rank, world)          # ticks driven inside the library over its own NCCL communicator
             run = BandRunner(band, rank, world)
             run.step(perfect, T)
             d = band.grid.download(fields=("dy", "dx", "color", "pref", "rng_state"))
