@@ -4,8 +4,9 @@ plumbing (NCCL over NVLink on the GPUs, gloo in the CPU tests), the stepping its
 The reference is single-device; the decomposition follows from its stencil radius of exactly one cell in
 both phases (steppers.fut:19,33-34,66,77-79).  Per tick each band
   1. swaps two heading/preference rows and one colour row with each neighbour        (state message)
-  2. runs its local fixpoint (k_u_init + k_u_iter)
-  3. swaps its boundary row of calc / my|mx, ORs the neighbour's row into its ghost row and wakes the owned
+  2. runs k_u_init, swaps its boundary row of calc / my|mx (so the ghost rows hold the neighbours' rows after
+     their block-local sweeps) and runs the frontier iterations (k_u_iter)
+  3. swaps its boundary row of calc / my|mx again, ORs the neighbour's row into its ghost row and wakes the owned
      words next to every ghost word that changed; all bands all-reduce (MAX) the number of woken words and
      resume k_u_iter until nobody was woken -- a waiting chain that crosses a cut costs one extra round
   4. [perfect mode] resolves its rings and swaps the boundary my|mx once more
@@ -93,8 +94,11 @@ class DeviceBand:
         self._fence()
         self._c(self.L.flowamok_band_unpack_state(self.ctx.h, self.grid.h, side, buf.data_ptr()))
 
-    def u_begin(self):
-        self._c(self.L.flowamok_band_u_begin(self.ctx.h, self.grid.h))
+    def u_init(self):
+        self._c(self.L.flowamok_band_u_init(self.ctx.h, self.grid.h))
+
+    def u_iter(self):
+        self._c(self.L.flowamok_band_u_iter(self.ctx.h, self.grid.h))
 
     def pack_u(self, side, buf):
         self._c(self.L.flowamok_band_pack_u(self.ctx.h, self.grid.h, side, buf.data_ptr()))
@@ -174,7 +178,10 @@ class BandRunner:
     def tick(self, perfect: bool):
         if self.world > 1:
             self.exchange_state()
-        self.b.u_begin()
+        self.b.u_init()
+        if self.world > 1:
+            self.exchange_u(wake=False)      # ghost rows := the neighbours' rows after their block-local sweeps
+        self.b.u_iter()
         if self.world > 1:
             while True:
                 self.exchange_u(wake=True)
@@ -229,7 +236,14 @@ class LocalBands:
             for r, side, q, qs in self._pairs():
                 B[q].unpack_state(qs, self.s[r][side])
         for b in B:
-            b.u_begin()
+            b.u_init()
+        if self.n > 1:
+            for r, side, _q, _qs in self._pairs():
+                B[r].pack_u(side, self.u[r][side])
+            for r, side, q, qs in self._pairs():
+                B[q].merge_u(qs, self.u[r][side], False)
+        for b in B:
+            b.u_iter()
         while self.n > 1:
             for r, side, _q, _qs in self._pairs():
                 B[r].pack_u(side, self.u[r][side])

@@ -65,6 +65,8 @@ def lib():
         "flowamok_band_pack_state": (C.c_int, [P, P, C.c_int, P]),
         "flowamok_band_unpack_state": (C.c_int, [P, P, C.c_int, P]),
         "flowamok_band_u_begin": (C.c_int, [P, P]),
+        "flowamok_band_u_init": (C.c_int, [P, P]),
+        "flowamok_band_u_iter": (C.c_int, [P, P]),
         "flowamok_band_pack_u": (C.c_int, [P, P, C.c_int, P]),
         "flowamok_band_merge_u": (C.c_int, [P, P, C.c_int, P, C.c_int, P]),
         "flowamok_band_woken": (C.c_int, [P, P, P]),

@@ -94,6 +94,8 @@ struct flowamok_grid {
   char *msg_u_send[2] = {nullptr, nullptr}, *msg_u_recv[2] = {nullptr, nullptr};
   unsigned int *d_woken = nullptr, *h_woken = nullptr;
   long long band_rounds = 0;
+  int ring_touch = 1;   // some ring cell lies on a boundary row of this band (1 = unknown/assume yes)
+  int ring_swap = -1;   // collective decision (max over ranks of ring_touch); -1 = not agreed yet
 };
 
 static int fail(flowamok_context *ctx, const char *fmt, ...) {
@@ -454,6 +456,9 @@ static int install_rings(flowamok_context *ctx, flowamok_grid *g, int64_t n, con
   CU(cudaMemcpy(g->ring_cells, cells.data(), (size_t)tot * 8, cudaMemcpyHostToDevice));
   CU(cudaMemcpy(g->ring_off, offs.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice));
   g->n_rings = n; g->n_ring_cells = tot;
+  g->ring_touch = 0; g->ring_swap = -1;
+  for (int64_t t = 0; t < tot; t++)
+    if (y[t] == g->row0 + g->own0 || y[t] == g->row0 + g->own1 - 1) { g->ring_touch = 1; break; }
   g->h_off.assign(off, off + n + 1); g->h_y.assign(y, y + tot); g->h_x.assign(x, x + tot);
   g->h_cy.assign(cy, cy + tot); g->h_cx.assign(cx, cx + tot);
   return 0;
@@ -840,13 +845,25 @@ int flowamok_band_unpack_state(flowamok_context *ctx, flowamok_grid *g, int side
   CU(cudaMemcpyAsync(g->color[g->cur] + (size_t)rc * P * 32, b + 2 * P * 20, P * 128, cudaMemcpyDeviceToDevice, st));
   return 0;
 }
-int flowamok_band_u_begin(flowamok_context *ctx, flowamok_grid *g) {
+/* u_init: k_u_init only (statics, block-local sweeps, ghost rows seeded with this band's view of the neighbour's
+ * boundary row); u_iter: the frontier iterations.  u_begin = both.  Swapping the boundary rows BETWEEN the two lets
+ * the frontier run against the neighbour's post-sweep rows, so the first convergence check usually passes. */
+int flowamok_band_u_init(flowamok_context *ctx, flowamok_grid *g) {
   if (band_check(ctx, g, 0)) return 1;
   CU(cudaSetDevice(ctx->device));
   // a tick always starts with empty frontier counters, whatever the host did with the previous round
   CU(cudaMemsetAsync(g->is->qn, 0, sizeof(g->is->qn), ctx->stream));
   GridView v = make_view(g);
-  return launch_u_init(ctx, g, v) || launch_u_iter(ctx, g, v, g->ntx * g->nty);
+  return launch_u_init(ctx, g, v);
+}
+int flowamok_band_u_iter(flowamok_context *ctx, flowamok_grid *g) {
+  if (band_check(ctx, g, 0)) return 1;
+  CU(cudaSetDevice(ctx->device));
+  GridView v = make_view(g);
+  return launch_u_iter(ctx, g, v, g->ntx * g->nty);
+}
+int flowamok_band_u_begin(flowamok_context *ctx, flowamok_grid *g) {
+  return flowamok_band_u_init(ctx, g) || flowamok_band_u_iter(ctx, g);
 }
 int flowamok_band_pack_u(flowamok_context *ctx, flowamok_grid *g, int side, void *dev_buf) {
   if (band_check(ctx, g, side)) return 1;
@@ -954,6 +971,14 @@ int flowamok_band_step(flowamok_context *ctx, flowamok_grid *g, int perfect, int
     CU(cudaMallocHost(&g->h_woken, 4));
   }
   auto has = [&](int side) { int peer = side == 0 ? ctx->rank - 1 : ctx->rank + 1; return multi && peer >= 0 && peer < ctx->world; };
+  if (multi && g->ring_swap < 0) {   // all bands agree once whether the post-ring swap is needed at all
+    unsigned int f = g->n_rings > 0 ? (unsigned)g->ring_touch : 0u;
+    CU(cudaMemcpyAsync(g->d_woken, &f, 4, cudaMemcpyHostToDevice, st));
+    NC(g_nccl.AllReduce(g->d_woken, g->d_woken, 1, ncclUint32, ncclMax, ctx->comm, st));
+    CU(cudaMemcpyAsync(g->h_woken, g->d_woken, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    g->ring_swap = *g->h_woken ? 1 : 0;
+  }
   auto swap_u = [&](int wake) -> int {
     for (int side = 0; side < 2; side++)
       if (has(side) && flowamok_band_pack_u(ctx, g, side, g->msg_u_send[side])) return 1;
@@ -970,7 +995,9 @@ int flowamok_band_step(flowamok_context *ctx, flowamok_grid *g, int perfect, int
       for (int side = 0; side < 2; side++)
         if (has(side) && flowamok_band_unpack_state(ctx, g, side, g->msg_s_recv[side])) return 1;
     }
-    if (flowamok_band_u_begin(ctx, g)) return 1;
+    if (flowamok_band_u_init(ctx, g)) return 1;
+    if (multi && swap_u(0)) return 1;            // ghost rows := the neighbour's rows after ITS local sweeps
+    if (flowamok_band_u_iter(ctx, g)) return 1;
     while (multi) {
       if (swap_u(1)) return 1;
       CU(cudaMemcpyAsync(g->d_woken, &g->is->qn[1], 4, cudaMemcpyDeviceToDevice, st));
@@ -983,7 +1010,7 @@ int flowamok_band_step(flowamok_context *ctx, flowamok_grid *g, int perfect, int
     }
     if (perfect) {
       if (flowamok_band_rings(ctx, g)) return 1;
-      if (multi && swap_u(0)) return 1;
+      if (multi && g->ring_swap && swap_u(0)) return 1;   // ring marks on a boundary row must reach the neighbour
     }
     if (flowamok_band_move(ctx, g)) return 1;
   }
@@ -1070,6 +1097,7 @@ int flowamok_generate_synthetic(flowamok_context *ctx, flowamok_grid *g, uint64_
     CU(cudaFree(cnt));
     if (n[1]) return fail(ctx, "%u synthetic rings straddle this row band: choose band boundaries that are multiples of 16", n[1]);
     g->n_rings = n[0]; g->n_ring_cells = (long long)n[0] * 48; g->ring_stride = 48;
+    g->ring_touch = 0; g->ring_swap = -1;   // a listed ring lies at least two rows inside the band (k_synth_rings)
   }
   CU(cudaStreamSynchronize(st));
   g->tick = 0;

@@ -299,6 +299,8 @@ struct UInitTile {
     if ((~o.cur.R & ~o.st.T & o.valid) == 0u) return 0;
     int tr = t / TW, tc = t - tr * TW;
     bool border = tr == 0 || tr == TR - 1 || tc == 0 || tc == TW - 1;
+    // a band's first/last owned row looks at a ghost row that the neighbour refines after this kernel
+    if (g.gh != g.gh_global && (o.y == g.own0 || o.y == g.own1 - 1)) border = true;
     return (border || !converged) ? 2 : 1;
   }
 };

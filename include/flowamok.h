@@ -123,7 +123,7 @@ int flowamok_generate_synthetic(flowamok_context *ctx, flowamok_grid *g, uint64_
  * WHOLE-grid host arrays (upload reads the rows the band holds, download writes the rows it owns); edits and cycle
  * lists take global coordinates.  One tick of a band, driven by the host (flowamok_b200/bands.py):
  *     pack_state -> send/recv with both neighbours -> unpack_state          (heading, preference, colour rows)
- *     u_begin                                                                (local fixpoint)
+ *     u_init; pack_u -> send/recv -> merge_u(wake=0); u_iter                 (local fixpoint against the neighbours' post-sweep rows)
  *     repeat: pack_u -> send/recv -> merge_u(wake=1); all-reduce(max) of the woken count; u_resume   until 0
  *     [perfect: rings; pack_u -> send/recv -> merge_u(wake=0)]
  *     move
@@ -132,7 +132,9 @@ int flowamok_band_new(flowamok_context *ctx, flowamok_grid **out, int64_t gh_glo
 int flowamok_band_msg_bytes(flowamok_context *ctx, const flowamok_grid *g, int64_t *state_bytes, int64_t *u_bytes);
 int flowamok_band_pack_state(flowamok_context *ctx, flowamok_grid *g, int side, void *dev_buf);
 int flowamok_band_unpack_state(flowamok_context *ctx, flowamok_grid *g, int side, const void *dev_buf);
-int flowamok_band_u_begin(flowamok_context *ctx, flowamok_grid *g);
+int flowamok_band_u_begin(flowamok_context *ctx, flowamok_grid *g);   /* = u_init then u_iter */
+int flowamok_band_u_init(flowamok_context *ctx, flowamok_grid *g);
+int flowamok_band_u_iter(flowamok_context *ctx, flowamok_grid *g);
 int flowamok_band_pack_u(flowamok_context *ctx, flowamok_grid *g, int side, void *dev_buf);
 int flowamok_band_merge_u(flowamok_context *ctx, flowamok_grid *g, int side, const void *dev_buf, int wake, void *dev_woken);
 int flowamok_band_woken(flowamok_context *ctx, flowamok_grid *g, void *dev_woken);

@@ -290,11 +290,10 @@ void emul_band_unpack_state(void *p, int side, const void *buf) {
   memcpy(h->pref[h->cur].data() + (size_t)r2 * P, b + 2 * P * 16, 2 * P * 4);
   memcpy(h->color[h->cur].data() + (size_t)rc * P * 32, b + 2 * P * 20, P * 128);
 }
-void emul_band_u_begin(void *p, int chooser, uint32_t tape_bit) {
+void emul_band_u_init(void *p, int chooser, uint32_t tape_bit) {   // k_u_init only; emul_band_u_resume runs the frontier
   HostGrid *h = (HostGrid *)p;
   GridView g = view(h, chooser, tape_bit);
   v_u_init(h, g);
-  u_iter(h, g, v_order(h));
 }
 void emul_band_pack_u(void *p, int side, void *buf) {
   HostGrid *h = (HostGrid *)p;

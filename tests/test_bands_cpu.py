@@ -26,7 +26,7 @@ class EmulBand:
         for f, at in (("emul_band_msg_bytes", [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
                       ("emul_band_pack_state", [C.c_void_p, C.c_int, C.c_void_p]),
                       ("emul_band_unpack_state", [C.c_void_p, C.c_int, C.c_void_p]),
-                      ("emul_band_u_begin", [C.c_void_p, C.c_int, C.c_uint32]),
+                      ("emul_band_u_init", [C.c_void_p, C.c_int, C.c_uint32]),
                       ("emul_band_pack_u", [C.c_void_p, C.c_int, C.c_void_p]),
                       ("emul_band_merge_u", [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
                       ("emul_band_u_resume", [C.c_void_p]), ("emul_band_rings", [C.c_void_p]),
@@ -75,8 +75,11 @@ class EmulBand:
     def unpack_state(self, side, buf):
         self.L.emul_band_unpack_state(self.p, side, buf.data_ptr())
 
-    def u_begin(self):
-        self.L.emul_band_u_begin(self.p, self.chooser, self._tb())
+    def u_init(self):
+        self.L.emul_band_u_init(self.p, self.chooser, self._tb())
+
+    def u_iter(self):
+        self.L.emul_band_u_resume(self.p)
 
     def pack_u(self, side, buf):
         self.L.emul_band_pack_u(self.p, side, buf.data_ptr())
