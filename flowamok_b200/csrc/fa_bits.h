@@ -57,14 +57,14 @@ FA_HD Heading heading(u32 DYN, u32 DYS, u32 DXN, u32 DXS) {
 struct Edge {
   u32 rowFirst, rowLast, colFirst, colLast, valid;
 };
-FA_HD Edge edge_masks(int64_t y, int64_t w, int64_t gh, int64_t gw) {
+FA_HD Edge edge_masks(int y, int w, int gh, int gw) {
   Edge e;
   e.rowFirst = (y == 0) ? 0xFFFFFFFFu : 0u;
   e.rowLast = (y == gh - 1) ? 0xFFFFFFFFu : 0u;
   e.colFirst = (w == 0) ? 1u : 0u;
-  int64_t lastw = (gw - 1) >> 5;
+  int lastw = (gw - 1) >> 5;
   e.colLast = (w == lastw) ? (1u << ((gw - 1) & 31)) : 0u;
-  int64_t x0 = w * 32;
+  int x0 = w * 32;
   if (y < 0 || y >= gh || x0 >= gw || w < 0) e.valid = 0u;
   else if (x0 + 32 <= gw) e.valid = 0xFFFFFFFFu;
   else e.valid = (1u << (gw - x0)) - 1u;
@@ -141,6 +141,18 @@ FA_HD UState u_relax(const UStatic &s, const W3 &R_up, const W3 &R, const W3 &R_
          (s.LSW & (west(MY_dn) | west(MX_dn))) | (s.LSE & (east(MY_dn) | east(MX_dn)));
   }
   u32 free_ = r & b;  // base only counts once the successor is calculated
+  o.R = r;
+  o.MY = free_ & s.GYr;
+  o.MX = free_ & s.GXr;
+  return o;
+}
+
+// The same step for a word without diagonal headings: only 10 neighbour words are needed.
+FA_HD UState u_relax_card(const UStatic &s, u32 R_up, const W3 &R, u32 R_dn, u32 MY_up, u32 MY_dn, const W3 &MX) {
+  UState o;
+  u32 r = s.T | (s.LN & R_up) | (s.LS & R_dn) | (s.LW & west(R)) | (s.LE & east(R));
+  u32 b = s.T | (s.LN & MY_up) | (s.LS & MY_dn) | (s.LW & west(MX)) | (s.LE & east(MX));
+  u32 free_ = r & b;
   o.R = r;
   o.MY = free_ & s.GYr;
   o.MX = free_ & s.GXr;

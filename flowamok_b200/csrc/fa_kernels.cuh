@@ -116,12 +116,13 @@ __device__ __forceinline__ bool grid_barrier(IterState *is, unsigned int nblocks
 // with one global atomic per CTA-chunk.  Ends when an iteration produces an empty list.
 // ---------------------------------------------------------------------------------------------
 constexpr int UIT_SEG = 256;   // init-blocks whose frontier segments one CTA flattens at a time
+constexpr unsigned int UIT_TAIL = 512;    // frontier length below which CTA 0 finishes the fixpoint alone
 
 __global__ void __launch_bounds__(UIT_THREADS, 2)
 k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *qlist0, unsigned int *qlist1,
          const unsigned int *qcnt, int n_init_blocks, IterState *is, Diag *diag) {
   __shared__ unsigned int stage[UIT_THREADS * 9];
-  __shared__ unsigned int pre[UIT_SEG + 1];
+  __shared__ unsigned int pre[UIT_SEG + 1], wtot[UIT_SEG / 32];
   __shared__ unsigned int scnt, gbase;
   const int tid = threadIdx.x, nt = blockDim.x, b = blockIdx.x, nb = gridDim.x, lane = tid & 31;
   volatile IterState *vis = is;
@@ -166,11 +167,20 @@ k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *
     for (int s0 = blk_lo; s0 < blk_hi; s0 += UIT_SEG) {
       const int ns = min(UIT_SEG, blk_hi - s0);
       // exclusive prefix of the segment lengths (ns <= 256: one warp-scan pass per 32, tiny)
-      if (tid < ns) pre[tid + 1] = qcnt[s0 + tid];
-      if (tid == 0) pre[0] = 0;
-      __syncthreads();
-      if (tid == 0) for (int k = 1; k <= ns; k++) pre[k] += pre[k - 1];
-      __syncthreads();
+      {  // block-wide inclusive scan of the ns <= UIT_SEG segment lengths (warp shuffles + 8 warp totals)
+        unsigned v = tid < ns ? qcnt[s0 + tid] : 0u;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { unsigned u = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= d) v += u; }
+        if (tid < UIT_SEG && lane == 31) wtot[tid >> 5] = v;
+        __syncthreads();
+        if (tid < UIT_SEG) {
+          unsigned add = 0;
+          for (int k = 0; k < (tid >> 5); k++) add += wtot[k];
+          pre[tid + 1] = v + add;
+        }
+        if (tid == 0) pre[0] = 0;
+        __syncthreads();
+      }
       const unsigned int tot = pre[ns];
       for (unsigned int k0 = 0; k0 < tot; k0 += nt) {
         const unsigned int k = k0 + tid;
@@ -190,19 +200,26 @@ k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *
   }
   // ---- iterations 1, 2, ...
   unsigned int it = 1;
+  bool tail = false;   // once the frontier is short, CTA 0 finishes alone: no more grid-wide barriers
   for (;; it++) {
     const unsigned int n = vis->qn[it % 3u];
     if (n == 0) break;                       // same value in every CTA: uniform exit
+    if (!tail && n <= UIT_TAIL) {            // uniform decision: every CTA read the same n after the barrier
+      if (b != 0) break;
+      tail = true;
+    }
     const unsigned int *src = ql[it & 1];
     unsigned int *dst = ql[(it + 1) & 1];
     unsigned int *out_cnt = &is->qn[(it + 1) % 3u];
     if (b == 0 && tid == 0) is->qn[(it + 2) % 3u] = 0;   // output slot of iteration it+1; idle since barrier(it-1)
-    for (unsigned int k0 = (unsigned)b * nt; k0 < n; k0 += (unsigned)nb * nt) {
+    const unsigned int stride = tail ? (unsigned)nt : (unsigned)nb * nt;
+    for (unsigned int k0 = tail ? 0u : (unsigned)b * nt; k0 < n; k0 += stride) {
       const unsigned int k = k0 + tid;
       visit_and_flush(k < n, k < n ? src[k] : 0u, dst, out_cnt);
       relaxed += min((unsigned)nt, n - k0);
     }
-    if (!grid_barrier(is, nb)) return;
+    if (tail) { __threadfence(); __syncthreads(); }
+    else if (!grid_barrier(is, nb)) return;
   }
   if (tid == 0) {
     atomicAdd(&diag->sweeps, relaxed);

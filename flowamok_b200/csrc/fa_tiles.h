@@ -65,7 +65,7 @@ inline unsigned int fa_host_cas(unsigned int *p, unsigned int c, unsigned int v)
 
 // local row y exists in the planes AND lies inside the global grid
 FA_HD bool row_in(const GridView &g, int y) { return y >= 0 && y < g.gh && y + g.row0 >= 0 && y + g.row0 < g.gh_global; }
-FA_HD Edge edge_of(const GridView &g, int y, int w) { return edge_masks((int64_t)y + g.row0, w, g.gh_global, g.gw); }
+FA_HD Edge edge_of(const GridView &g, int y, int w) { return edge_masks(y + g.row0, w, g.gh_global, g.gw); }
 
 FA_HD int popc32(u32 v) {
 #if defined(__CUDA_ARCH__)
@@ -257,10 +257,16 @@ struct UInitTile {
   // one sweep: compute from shared memory (no writes) ...
   FA_HD bool sweep_compute(Own &o, UState &n) const {
     n = o.cur;
-    if (!o.in || (~o.st.T & o.valid) == 0u) return false;
+    // nothing to do unless an owned link cell is still uncalculated: a calculated cell is final (commit is atomic
+    // with respect to the sweep barrier, so R = 1 always comes with its final MY/MX)
+    if (!o.in || (~o.cur.R & ~o.st.T & o.valid) == 0u) return false;
     int r = o.si / SW, c = o.si - r * SW;
-    n = u_relax(o.st, w3(s.R, r - 1, c), w3(s.R, r, c), w3(s.R, r + 1, c), w3(s.MY, r - 1, c), w3(s.MY, r + 1, c),
-                w3(s.MX, r, c), w3(s.MX, r - 1, c), w3(s.MX, r + 1, c));
+    if ((o.st.LNW | o.st.LNE | o.st.LSW | o.st.LSE) == 0u)
+      n = u_relax_card(o.st, s.R[idx(r - 1, c)], w3(s.R, r, c), s.R[idx(r + 1, c)], s.MY[idx(r - 1, c)], s.MY[idx(r + 1, c)],
+                       w3(s.MX, r, c));
+    else
+      n = u_relax(o.st, w3(s.R, r - 1, c), w3(s.R, r, c), w3(s.R, r + 1, c), w3(s.MY, r - 1, c), w3(s.MY, r + 1, c),
+                  w3(s.MX, r, c), w3(s.MX, r - 1, c), w3(s.MX, r + 1, c));
     n.R &= o.valid; n.MY &= o.valid; n.MX &= o.valid;
     return n.R != o.cur.R || n.MY != o.cur.MY || n.MX != o.cur.MX;
   }
