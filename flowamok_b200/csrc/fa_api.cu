@@ -74,8 +74,9 @@ struct flowamok_grid {
   std::vector<uint8_t> tape;
   long long tick;
   // cycles (sparse)
-  unsigned long long *ring_cells, *ring_off;
-  long long n_rings, n_ring_cells;
+  RingWord *ring_words;             // per ring: one entry per plane word it touches
+  unsigned long long *ring_off;     // CSR offsets into ring_words, or nullptr with a uniform ring_stride
+  long long n_rings, n_ring_cells, n_ring_words;
   int ring_stride;  // >0: uniform rings, ring_off == nullptr
   std::vector<int64_t> h_off, h_y, h_x;  // host copy for flowamok_get_cycles_dense
   std::vector<int8_t> h_cy, h_cx;
@@ -204,7 +205,7 @@ static int grid_new_impl(flowamok_context *ctx, flowamok_grid **out, int64_t gh_
   if (g->nwords >= (1ull << 32)) { delete g; return fail(ctx, "grid too large for 32-bit word indices"); }
   g->cur = 0; g->chooser = CHOOSE_RANDOM; g->tick = 0;
   g->rng_inc = (0xda3e39cb94b95bdbULL << 1) | 1ULL;
-  g->ring_cells = g->ring_off = nullptr; g->n_rings = g->n_ring_cells = 0; g->ring_stride = 0;
+  g->ring_words = nullptr; g->ring_off = nullptr; g->n_rings = g->n_ring_cells = g->n_ring_words = 0; g->ring_stride = 0;
   g->leak_plane = nullptr;
   *out = g;
   CU(cudaMalloc(&g->road, g->nwords * sizeof(U4)));
@@ -271,7 +272,7 @@ int flowamok_grid_free(flowamok_context *ctx, flowamok_grid *g) {
   for (int k = 0; k < 2; k++) { cudaFree(g->msg_s_send[k]); cudaFree(g->msg_s_recv[k]); cudaFree(g->msg_u_send[k]); cudaFree(g->msg_u_recv[k]); }
   cudaFree(g->d_woken); if (g->h_woken) cudaFreeHost(g->h_woken);
   cudaFree(g->table); cudaFree(g->qlist[0]); cudaFree(g->qlist[1]); cudaFree(g->qcnt); cudaFree(g->ustate);
-  cudaFree(g->ring_cells); cudaFree(g->ring_off); cudaFree(g->leak_plane);
+  cudaFree(g->ring_words); cudaFree(g->ring_off); cudaFree(g->leak_plane);
   cudaFreeHost(g->h_diag);
   delete g;
   return 0;
@@ -433,29 +434,38 @@ static int install_rings(flowamok_context *ctx, flowamok_grid *g, int64_t n, con
                          const int64_t *x, const int8_t *cy, const int8_t *cx, const uint8_t *grant) {
   CU(cudaSetDevice(ctx->device));
   CU(cudaStreamSynchronize(ctx->stream));
-  CU(cudaFree(g->ring_cells)); CU(cudaFree(g->ring_off));
-  g->ring_cells = g->ring_off = nullptr; g->n_rings = 0; g->n_ring_cells = 0; g->ring_stride = 0;
+  CU(cudaFree(g->ring_words)); CU(cudaFree(g->ring_off));
+  g->ring_words = nullptr; g->ring_off = nullptr; g->n_rings = 0; g->n_ring_cells = 0; g->n_ring_words = 0; g->ring_stride = 0;
   g->h_off.clear(); g->h_y.clear(); g->h_x.clear(); g->h_cy.clear(); g->h_cx.clear();
   if (n <= 0) return 0;
   int64_t tot = off[n];
-  std::vector<unsigned long long> cells((size_t)tot), offs((size_t)n + 1);
-  for (int64_t k = 0; k <= n; k++) offs[(size_t)k] = (unsigned long long)off[k];
-  for (int64_t t = 0; t < tot; t++) {
-    if (y[t] < 0 || y[t] >= g->gh_global || x[t] < 0 || x[t] >= g->gw) return fail(ctx, "cycle cell out of bounds");
-    if (y[t] < g->row0 + g->own0 || y[t] >= g->row0 + g->own1)
-      return fail(ctx, "cycle cell outside this device's row band (rings must not straddle bands)");
-    bool single = (cy[t] != 0) != (cx[t] != 0);
-    if (!single) return fail(ctx, "cycle check direction must be single-axis (steppers.fut:239-294)");
-    unsigned int dir = cy[t] < 0 ? 0u : cy[t] > 0 ? 1u : cx[t] < 0 ? 2u : 3u;
-    if (grant[t] != 1 && grant[t] != 2) return fail(ctx, "grant must be 1 (y) or 2 (x)");
-    cells[(size_t)t] = (unsigned long long)((size_t)(y[t] - g->row0) * g->pitch + (x[t] >> 5)) | ((unsigned long long)(x[t] & 31) << 32) |
-                       ((unsigned long long)dir << 37) | ((unsigned long long)(grant[t] == 2 ? 1 : 0) << 39);
+  std::vector<RingWord> words;
+  std::vector<unsigned long long> offs((size_t)n + 1);
+  for (int64_t k = 0; k < n; k++) {
+    offs[(size_t)k] = words.size();
+    const size_t first = words.size();
+    for (int64_t t = off[k]; t < off[k + 1]; t++) {
+      if (y[t] < 0 || y[t] >= g->gh_global || x[t] < 0 || x[t] >= g->gw) return fail(ctx, "cycle cell out of bounds");
+      if (y[t] < g->row0 + g->own0 || y[t] >= g->row0 + g->own1)
+        return fail(ctx, "cycle cell outside this device's row band (rings must not straddle bands)");
+      bool single = (cy[t] != 0) != (cx[t] != 0);
+      if (!single) return fail(ctx, "cycle check direction must be single-axis (steppers.fut:239-294)");
+      if (grant[t] != 1 && grant[t] != 2) return fail(ctx, "grant must be 1 (y) or 2 (x)");
+      const u32 wi = (u32)((size_t)(y[t] - g->row0) * g->pitch + (x[t] >> 5)), bit = 1u << (x[t] & 31);
+      size_t j = first;
+      while (j < words.size() && words[j].wi != wi) j++;
+      if (j == words.size()) { RingWord e = {wi, 0, 0, 0, 0, 0, 0, 0}; words.push_back(e); }
+      RingWord &e = words[j];
+      if (cy[t] < 0) e.mN |= bit; else if (cy[t] > 0) e.mS |= bit; else if (cx[t] < 0) e.mW |= bit; else e.mE |= bit;
+      if (grant[t] == 2) e.gX |= bit; else e.gY |= bit;
+    }
   }
-  CU(cudaMalloc(&g->ring_cells, std::max<size_t>(1, (size_t)tot) * 8));
+  offs[(size_t)n] = words.size();
+  CU(cudaMalloc(&g->ring_words, std::max<size_t>(1, words.size()) * sizeof(RingWord)));
   CU(cudaMalloc(&g->ring_off, ((size_t)n + 1) * 8));
-  CU(cudaMemcpy(g->ring_cells, cells.data(), (size_t)tot * 8, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(g->ring_words, words.data(), words.size() * sizeof(RingWord), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(g->ring_off, offs.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice));
-  g->n_rings = n; g->n_ring_cells = tot;
+  g->n_rings = n; g->n_ring_cells = tot; g->n_ring_words = (long long)words.size();
   g->ring_touch = 0; g->ring_swap = -1;
   for (int64_t t = 0; t < tot; t++)
     if (y[t] == g->row0 + g->own0 || y[t] == g->row0 + g->own1 - 1) { g->ring_touch = 1; break; }
@@ -620,7 +630,7 @@ static int launch_u_iter(flowamok_context *ctx, flowamok_grid *g, GridView &v, i
 }
 static int launch_rings(flowamok_context *ctx, flowamok_grid *g, const GridView &v) {
   if (g->n_rings > 0) {
-    k_rings<<<nblk(g->n_rings, 128), 128, 0, ctx->stream>>>(v, g->ring_cells, g->ring_off, g->n_rings, g->ring_stride);
+    k_rings<<<nblk(g->n_rings, RINGS_PER_BLOCK), RINGS_PER_BLOCK, 0, ctx->stream>>>(v, g->ring_words, g->ring_off, g->n_rings, g->ring_stride);
     KCHECK("k_rings");
   }
   return 0;
@@ -788,13 +798,14 @@ int flowamok_grid_clone(flowamok_context *ctx, const flowamok_grid *src, flowamo
   CU(cudaMemcpyAsync(g->rng, src->rng, src->ncells_p * 8, cudaMemcpyDeviceToDevice, st));
   g->cur = 0; g->rng_inc = src->rng_inc; g->chooser = src->chooser; g->tape = src->tape; g->tick = src->tick;
   if (src->n_rings > 0) {
-    CU(cudaMalloc(&g->ring_cells, (size_t)src->n_ring_cells * 8));
-    CU(cudaMemcpyAsync(g->ring_cells, src->ring_cells, (size_t)src->n_ring_cells * 8, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMalloc(&g->ring_words, std::max<size_t>(1, (size_t)src->n_ring_words) * sizeof(RingWord)));
+    CU(cudaMemcpyAsync(g->ring_words, src->ring_words, (size_t)src->n_ring_words * sizeof(RingWord), cudaMemcpyDeviceToDevice, st));
     if (src->ring_off) {
       CU(cudaMalloc(&g->ring_off, ((size_t)src->n_rings + 1) * 8));
       CU(cudaMemcpyAsync(g->ring_off, src->ring_off, ((size_t)src->n_rings + 1) * 8, cudaMemcpyDeviceToDevice, st));
     }
-    g->n_rings = src->n_rings; g->n_ring_cells = src->n_ring_cells; g->ring_stride = src->ring_stride;
+    g->n_rings = src->n_rings; g->n_ring_cells = src->n_ring_cells; g->n_ring_words = src->n_ring_words; g->ring_stride = src->ring_stride;
+    g->ring_touch = src->ring_touch;
     g->h_off = src->h_off; g->h_y = src->h_y; g->h_x = src->h_x; g->h_cy = src->h_cy; g->h_cx = src->h_cx;
   }
   *out = g;
@@ -1076,8 +1087,8 @@ int flowamok_generate_synthetic(flowamok_context *ctx, flowamok_grid *g, uint64_
                                                                g->color[g->cur], g->rng);
   CU(cudaGetLastError());
   g->rng_inc = (0xda3e39cb94b95bdbULL << 1) | 1ULL;
-  CU(cudaFree(g->ring_cells)); CU(cudaFree(g->ring_off));
-  g->ring_cells = g->ring_off = nullptr; g->n_rings = g->n_ring_cells = 0; g->ring_stride = 0;
+  CU(cudaFree(g->ring_words)); CU(cudaFree(g->ring_off));
+  g->ring_words = nullptr; g->ring_off = nullptr; g->n_rings = g->n_ring_cells = g->n_ring_words = 0; g->ring_stride = 0;
   g->h_off.clear(); g->h_y.clear(); g->h_x.clear(); g->h_cy.clear(); g->h_cx.clear();
   const int ghg = g->gh_global;
   int nby = ghg >= 15 ? (ghg - 15) / 16 + 1 : 0, nbx = g->gw >= 23 ? (g->gw - 23) / 16 + 1 : 0;
@@ -1087,16 +1098,17 @@ int flowamok_generate_synthetic(flowamok_context *ctx, flowamok_grid *g, uint64_
     CU(cudaMemsetAsync(cnt, 0, 8, st));
     const int lo = g->row0 + g->own0, hi = g->row0 + g->own1;
     const long long my_blocks = ((long long)(hi - lo) / 16 + 2) * nbx;   // ring blocks that can lie in this band
-    CU(cudaMalloc(&g->ring_cells, (size_t)my_blocks * 48 * 8));
+    CU(cudaMalloc(&g->ring_words, (size_t)my_blocks * SYNTH_RING_WORDS * sizeof(RingWord)));
     k_synth_rings<<<nblk((long long)nby * nbx, 128), 128, 0, st>>>(ghg, g->gw, g->pitch, g->row0, lo, hi, seed, nby, nbx,
-                                                                   g->ring_cells, cnt, cnt + 1);
+                                                                   g->ring_words, cnt, cnt + 1);
     CU(cudaGetLastError());
     unsigned int n[2] = {0, 0};
     CU(cudaMemcpyAsync(n, cnt, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     CU(cudaFree(cnt));
     if (n[1]) return fail(ctx, "%u synthetic rings straddle this row band: choose band boundaries that are multiples of 16", n[1]);
-    g->n_rings = n[0]; g->n_ring_cells = (long long)n[0] * 48; g->ring_stride = 48;
+    g->n_rings = n[0]; g->n_ring_cells = (long long)n[0] * 48; g->n_ring_words = (long long)n[0] * SYNTH_RING_WORDS;
+    g->ring_stride = SYNTH_RING_WORDS;
     g->ring_touch = 0; g->ring_swap = -1;   // a listed ring lies at least two rows inside the band (k_synth_rings)
   }
   CU(cudaStreamSynchronize(st));

@@ -252,34 +252,60 @@ __global__ void k_band_merge(const __grid_constant__ GridView g, int ghost_row, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// resolve_cycles on sparse rings (steppers.fut:189-224; disjointness argument SURVEY 8a-R)
-// ring cell encoding: [31:0] plane word index, [36:32] bit, [38:37] check direction
-// (0 N, 1 S, 2 W, 3 E), [39] grant (0: direction.y, 1: direction.x)
+// resolve_cycles on sparse rings (steppers.fut:189-224; disjointness argument SURVEY 8a-R).
+// A ring is stored per plane word it touches: the ring's cells in that word by check direction, and which
+// of them are granted along y / x if the whole ring passes (the outcome of steppers.fut:206-211).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool ring_cell_ok(const GridView &g, unsigned long long e) {
-  unsigned int wi = (unsigned int)e, bit = 1u << ((e >> 32) & 31u), dir = (unsigned int)(e >> 37) & 3u;
-  if (g.calc[wi] & bit) return false;
-  U4 h = g.head_in[wi];
-  bool dyn = h.x & bit, dys = h.y & bit, dxn = h.z & bit, dxs = h.w & bit;
-  switch (dir) {
-  case 0: return dyn && dys && !dxn;
-  case 1: return dyn && !dys && !dxn;
-  case 2: return dxn && dxs && !dyn;
-  default: return dxn && !dxs && !dyn;
-  }
+struct alignas(32) RingWord {
+  u32 wi;                 // plane word index
+  u32 mN, mS, mW, mE;     // ring cells of this word whose check direction is N / S / W / E
+  u32 gY, gX;             // cells granted direction.y / direction.x when the ring passes
+  u32 pad;
+};
+// every ring cell of the word is uncalculated and holds a car heading exactly the check direction (:197-200)
+__device__ __forceinline__ bool ring_word_ok(const GridView &g, const RingWord &e) {
+  const u32 m = e.mN | e.mS | e.mW | e.mE;
+  if (m == 0u) return true;   // padding entry
+  if (g.calc[e.wi] & m) return false;
+  const U4 h = g.head_in[e.wi];
+  const u32 n = h.x & h.y & ~h.z, s_ = h.x & ~h.y & ~h.z, w = h.z & h.w & ~h.x, ea = h.z & ~h.w & ~h.x;
+  return (n & e.mN) == e.mN && (s_ & e.mS) == e.mS && (w & e.mW) == e.mW && (ea & e.mE) == e.mE;
 }
-__global__ void k_rings(const __grid_constant__ GridView g, const unsigned long long *cells,
-                        const unsigned long long *off, long long n, int stride) {
-  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  unsigned long long b = off ? off[k] : (unsigned long long)k * stride;
-  unsigned long long e = off ? off[k + 1] : b + stride;
-  for (unsigned long long t = b; t < e; t++)
-    if (!ring_cell_ok(g, cells[t])) return;
-  for (unsigned long long t = b; t < e; t++) {
-    unsigned long long c = cells[t];
-    unsigned int wi = (unsigned int)c, bit = 1u << ((c >> 32) & 31u);
-    atomicOr(reinterpret_cast<unsigned int *>(&g.mymx[wi]) + ((c >> 39) & 1ull), bit);  // low word my, high word mx
+constexpr int RINGS_PER_BLOCK = 256;
+// Phase 1: one thread per ring tests the ring's first word (almost every ring that is not completely full fails
+// here); survivors are compacted in shared memory.  Phase 2: one warp per survivor tests all words in parallel
+// and, if the ring passes, ORs the grants into my|mx (one 64-bit atomic per word).
+__global__ void __launch_bounds__(RINGS_PER_BLOCK)
+k_rings(const __grid_constant__ GridView g, const RingWord *words, const unsigned long long *off, long long n, int stride) {
+  __shared__ unsigned int surv[RINGS_PER_BLOCK];
+  __shared__ unsigned int wbase[RINGS_PER_BLOCK / 32 + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long k = (long long)blockIdx.x * RINGS_PER_BLOCK + tid;
+  bool pass0 = false;
+  if (k < n) {
+    const unsigned long long b = off ? off[k] : (unsigned long long)k * stride;
+    const unsigned long long e = off ? off[k + 1] : b + stride;
+    pass0 = e > b && ring_word_ok(g, words[b]);
+  }
+  const unsigned m = __ballot_sync(0xFFFFFFFFu, pass0);
+  if (lane == 0) wbase[warp + 1] = __popc(m);
+  __syncthreads();
+  if (tid == 0) { wbase[0] = 0; for (int i = 1; i <= RINGS_PER_BLOCK / 32; i++) wbase[i] += wbase[i - 1]; }
+  __syncthreads();
+  if (pass0) surv[wbase[warp] + __popc(m & ((1u << lane) - 1u))] = (unsigned int)tid;
+  __syncthreads();
+  const int nsurv = (int)wbase[RINGS_PER_BLOCK / 32];
+  for (int si = warp; si < nsurv; si += RINGS_PER_BLOCK / 32) {
+    const long long r = (long long)blockIdx.x * RINGS_PER_BLOCK + surv[si];
+    const unsigned long long b = off ? off[r] : (unsigned long long)r * stride;
+    const unsigned long long e = off ? off[r + 1] : b + stride;
+    bool ok = true;
+    for (unsigned long long t = b + lane; t < e; t += 32) ok = ok && ring_word_ok(g, words[t]);
+    if (!__all_sync(0xFFFFFFFFu, ok)) continue;
+    for (unsigned long long t = b + lane; t < e; t += 32) {
+      const RingWord w = words[t];
+      if (w.gY | w.gX) atomicOr((unsigned long long *)&g.mymx[w.wi], (unsigned long long)w.gY | ((unsigned long long)w.gX << 32));
+    }
   }
 }
 
@@ -547,49 +573,54 @@ __global__ void k_synth(int gh, int gw, int pitch, int row0, int gh_global, u64 
   color[ci] = c.color;   // pad cells get 0
   rng[ci] = c.rng;
 }
-// analytic ring list of the generator: every ring has exactly 48 cells
+// analytic ring list of the generator: 48 cells per ring, stored as SYNTH_RING_WORDS word entries (unused ones empty)
+constexpr int SYNTH_RING_WORDS = 26;
 // rows [lo, hi) (global) are the band this device owns: a ring is listed by the device that owns ALL its rows
 __global__ void k_synth_rings(int gh, int gw, int pitch, int row0, int lo, int hi, u64 seed, int nby, int nbx,
-                              unsigned long long *cells, unsigned int *nrings, unsigned int *nstraddle) {
+                              RingWord *words, unsigned int *nrings, unsigned int *nstraddle) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nby * nbx) return;
   int by = b / nbx, bx = b % nbx;
   if (!((16 * by + 14 <= gh - 1) && (16 * bx + 22 <= gw - 1))) return;
+  u64 hb = synth_hash(seed, 1, (u64)by, (u64)bx);
+  if (!(hb & 1)) return;
   {
     int r_lo = 16 * by + 2, r_hi = 16 * by + 14;
     if (r_hi < lo || r_lo >= hi) return;                       // another band's ring
-    if (r_lo < lo || r_hi >= hi) {                             // cut by a band boundary
-      u64 hb0 = synth_hash(seed, 1, (u64)by, (u64)bx);
-      if (hb0 & 1) atomicAdd(nstraddle, 1u);
-      return;
-    }
+    if (r_lo < lo || r_hi >= hi) { atomicAdd(nstraddle, 1u); return; }   // cut by a band boundary
   }
-  u64 hb = synth_hash(seed, 1, (u64)by, (u64)bx);
-  if (!(hb & 1)) return;
   bool cw = (hb >> 1) & 1;
   unsigned int slot = atomicAdd(nrings, 1u);
-  unsigned long long *out = cells + (size_t)slot * 48;
-  int n = 0;
-  for (int ly = 0; ly <= 12; ly++)
-    for (int lx = 0; lx <= 12; lx++) {
-      if (!(ly == 0 || ly == 12 || lx == 0 || lx == 12)) continue;
-      int y = 16 * by + 2 + ly, x = 16 * bx + 10 + lx;
-      int hy = 0, hx = 0;
-      if (cw) {
-        if (ly == 0 && lx < 12) hx = 1; else if (lx == 12 && ly < 12) hy = 1;
-        else if (ly == 12 && lx > 0) hx = -1; else hy = -1;
-      } else {
-        if (ly == 0 && lx > 0) hx = -1; else if (lx == 0 && ly < 12) hy = 1;
-        else if (ly == 12 && lx < 12) hx = 1; else hy = -1;
+  RingWord *out = words + (size_t)slot * SYNTH_RING_WORDS;
+  const int x0 = 16 * bx + 10, wa = x0 >> 5, wb = (x0 + 12) >> 5;
+  for (int i = 0; i < SYNTH_RING_WORDS; i++) {
+    // entries 2*ly and 2*ly+1: the part of ring row ly lying in word wa / in word wb (empty if wa == wb)
+    int ly = i >> 1, w = (i & 1) ? wb : wa;
+    RingWord e = {0, 0, 0, 0, 0, 0, 0, 0};
+    int y = 16 * by + 2 + ly;
+    e.wi = (u32)((size_t)(y - row0) * pitch + w);
+    if (!((i & 1) && wa == wb))
+      for (int lx = 0; lx <= 12; lx++) {
+        if (!(ly == 0 || ly == 12 || lx == 0 || lx == 12)) continue;
+        int x = x0 + lx;
+        if ((x >> 5) != w) continue;
+        int hy = 0, hx = 0;
+        if (cw) {
+          if (ly == 0 && lx < 12) hx = 1; else if (lx == 12 && ly < 12) hy = 1;
+          else if (ly == 12 && lx > 0) hx = -1; else hy = -1;
+        } else {
+          if (ly == 0 && lx > 0) hx = -1; else if (lx == 0 && ly < 12) hy = 1;
+          else if (ly == 12 && lx < 12) hx = 1; else hy = -1;
+        }
+        u32 bit = 1u << (x & 31);
+        if (hy < 0) e.mN |= bit; else if (hy > 0) e.mS |= bit; else if (hx < 0) e.mW |= bit; else e.mE |= bit;
+        // grant (steppers.fut:206-211): a corner is entered along the axis it does NOT leave on
+        bool corner = (ly == 0 || ly == 12) && (lx == 0 || lx == 12);
+        bool grant_x = corner ? (hy != 0) : (hx != 0);
+        if (grant_x) e.gX |= bit; else e.gY |= bit;
       }
-      // grant (steppers.fut:206-211): a corner is entered along the axis it does NOT leave on
-      bool corner = (ly == 0 || ly == 12) && (lx == 0 || lx == 12);
-      bool grant_x = corner ? (hy != 0) : (hx != 0);
-      unsigned int dir = hy < 0 ? 0u : hy > 0 ? 1u : hx < 0 ? 2u : 3u;
-      unsigned long long e = (unsigned long long)((size_t)(y - row0) * pitch + (x >> 5)) | ((unsigned long long)(x & 31) << 32) |
-                             ((unsigned long long)dir << 37) | ((unsigned long long)(grant_x ? 1 : 0) << 39);
-      out[n++] = e;
-    }
+    out[i] = e;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
