@@ -326,3 +326,39 @@ def test_row_bands_on_one_gpu_equal_single_grid(ctx, n_bands, perfect):
             assert_state_equal(want, got, f"{n_bands} bands tick {t}")
     assert sum(b.leaks() for b in bands) == leaks
     assert run.rounds >= 12
+
+
+def _oracle_synth(gh, gw, seed=1):
+    og = O.Grid(gh, gw)
+    rings = og.generate_synthetic(seed=seed)
+    return og, rings
+
+
+def test_config3_4096_vs_oracle_first_ticks(ctx):
+    """BASELINE config 3 (4096^2, seed 1, 10 % density): quick and perfect vs the oracle at ticks 1, 2, 3, 10."""
+    for perfect in (False, True):
+        og, rings = _oracle_synth(4096, 4096)
+        g = ctx.grid(4096, 4096)
+        g.generate_synthetic(seed=1)
+        ch = O.Chooser(O.CHOOSE_RANDOM)
+        for t in range(1, 11):
+            nl, _ = og.step_perfect_sparse(ch, rings) if perfect else og.step_quick(ch)
+            assert g.step(perfect, 1) == nl
+            if t in (1, 2, 3, 10):
+                assert_state_equal(state_of(og), dev_state(g), f"4096^2 perfect={perfect} tick {t}")
+        g.free()
+
+
+def test_config4_16384_vs_oracle_first_ticks(ctx):
+    """BASELINE config 4 (the roofline headline, 16384^2 quick): the first 3 ticks of the full grid vs the oracle."""
+    og, _rings = _oracle_synth(16384, 16384)
+    g = ctx.grid(16384, 16384)
+    g.generate_synthetic(seed=1)
+    ch = O.Chooser(O.CHOOSE_RANDOM)
+    for t in range(3):
+        nl, _ = og.step_quick(ch)
+        assert g.step(False, 1) == nl
+    want = state_of(og)
+    del og
+    assert_state_equal(want, dev_state(g), "16384^2 tick 3")
+    g.free()
