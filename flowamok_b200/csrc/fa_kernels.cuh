@@ -121,18 +121,15 @@ constexpr unsigned int UIT_TAIL = 512;    // frontier length below which CTA 0 f
 __global__ void __launch_bounds__(UIT_THREADS, 2)
 k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *qlist0, unsigned int *qlist1,
          const unsigned int *qcnt, int n_init_blocks, IterState *is, Diag *diag) {
-  __shared__ unsigned int stage[UIT_THREADS * 9];
   __shared__ unsigned int pre[UIT_SEG + 1], wtot[UIT_SEG / 32];
-  __shared__ unsigned int scnt, gbase;
   const int tid = threadIdx.x, nt = blockDim.x, b = blockIdx.x, nb = gridDim.x, lane = tid & 31;
   volatile IterState *vis = is;
   unsigned int *ql[2] = {qlist0, qlist1};
   unsigned long long relaxed = 0;
 
-  // process one chunk: thread handles entry index `idx` if `has`
+  // visit entry `idx` (if `has`) and append what it wakes to dst: warp-aggregated, one global atomic per warp and
+  // push slot -- no block barrier anywhere in a visit
   auto visit_and_flush = [&](bool has, unsigned int idx, unsigned int *dst, unsigned int *out_cnt) {
-    if (tid == 0) scnt = 0;
-    __syncthreads();
     unsigned int push[9];
     int np = 0;
     if (has) {
@@ -140,24 +137,17 @@ k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *
       np = u_iter_entry(g, e, idx, push);
     }
 #pragma unroll
-    for (int j = 0; j < 9; j++) {  // warp-aggregated append to the CTA's staging buffer
+    for (int j = 0; j < 9; j++) {
       const bool p = j < np;
       const unsigned m = __ballot_sync(0xFFFFFFFFu, p);
       if (m) {
+        const int leader = __ffs(m) - 1;
         unsigned bs = 0;
-        if (lane == 0) bs = atomicAdd(&scnt, (unsigned)__popc(m));
-        bs = __shfl_sync(0xFFFFFFFFu, bs, 0);
-        if (p) stage[bs + __popc(m & ((1u << lane) - 1u))] = push[j];
+        if (lane == leader) bs = atomicAdd(out_cnt, (unsigned)__popc(m));
+        bs = __shfl_sync(0xFFFFFFFFu, bs, leader);
+        if (p) dst[bs + __popc(m & ((1u << lane) - 1u))] = push[j];
       }
     }
-    __syncthreads();
-    const unsigned int sc = scnt;
-    if (sc) {
-      if (tid == 0) gbase = atomicAdd(out_cnt, sc);
-      __syncthreads();
-      for (unsigned int i = tid; i < sc; i += nt) dst[gbase + i] = stage[i];
-    }
-    __syncthreads();
   };
 
   // ---- iteration 0: the per-block frontier segments; output goes to qlist1 / qn[1]

@@ -393,8 +393,8 @@ FA_HD int u_iter_entry(const GridView &g, const UEntry &e, u32 idx, u32 *push) {
   W3 R_up = {ul.R, up.R, ur.R}, R_c = {l.R, c.R, r.R}, R_dn = {dl.R, dn.R, dr.R};
   W3 MY_up = {ul.MY, up.MY, ur.MY}, MY_dn = {dl.MY, dn.MY, dr.MY};
   W3 MX_c = {l.MX, c.MX, r.MX}, MX_up = {ul.MX, up.MX, ur.MX}, MX_dn = {dl.MX, dn.MX, dr.MX};
-  UState n = u_relax(st, R_up, R_c, R_dn, MY_up, MY_dn, MX_c, MX_up, MX_dn);
   const u32 valid = edge_of(g, y, w).valid;
+  UState n = u_relax(st, R_up, R_c, R_dn, MY_up, MY_dn, MX_c, MX_up, MX_dn);
   n.R = (n.R & valid) | c.R; n.MY = (n.MY & valid) | c.MY; n.MX = (n.MX & valid) | c.MX;   // monotone
   bool changed = n.R != c.R || n.MY != c.MY || n.MX != c.MX;
   bool unready = (~n.R & ~e.T) != 0u;
