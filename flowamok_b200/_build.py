@@ -11,8 +11,8 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 SO = PKG / "libflowamok_b200.so"
 SOURCES = [CSRC / "fa_api.cu"]
-DEPS = [CSRC / "fa_api.cu", CSRC / "fa_kernels.cuh", CSRC / "fa_tiles.h", CSRC / "fa_bits.h",
-        PKG.parent / "include" / "flowamok.h"]
+DEPS = [CSRC / f for f in ("fa_api.cu", "fa_kernels.cuh", "fa_stream.h", "fa_simt.h", "fa_tiles.h", "fa_bits.h",
+                           "fa_futhark.inc")] + [PKG.parent / "include" / "flowamok.h"]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared", "-ldl"]

@@ -4,6 +4,7 @@ library or a missing CUDA device is a hard error (there is no CPU path)."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 from . import _build
@@ -24,7 +25,10 @@ def lib():
     if _lib is not None:
         return _lib
     so = _build.SO
-    if _build.needs_build():
+    override = os.environ.get("FLOWAMOK_B200_LIB")   # kernel-tuning builds (tools/tune_variants.py); never a CPU path
+    if override:
+        so = Path(override)
+    elif _build.needs_build():
         try:
             _build.build()
         except Exception as e:  # pragma: no cover

@@ -56,6 +56,7 @@ struct flowamok_context {
   bool own_stream;
   int num_sms;
   int iter_blocks; // co-resident CTAs of k_u_iter
+  size_t smem_optin = 0;   // largest dynamic shared memory a CTA may ask for
   std::string err;
 };
 
@@ -84,11 +85,11 @@ struct flowamok_grid {
   IterState *is;
   Diag *diag;
   Diag *h_diag;  // pinned
-  UEntry *table;          // worklist entries of the tick: k_u_init block b, thread t -> table[b*512 + t]
-  unsigned int *qlist[2]; // frontier lists (entry indices), ping-pong; qlist[0] first holds the per-block segments
-  unsigned int *qcnt;     // per k_u_init block: length of its frontier segment
+  UEntry *table;          // worklist entries of the tick, indexed by plane word
+  unsigned int *qlist[2]; // frontier lists (entry indices), ping-pong; k_u_local appends the first one to qlist[0]
   u32 *ustate;            // per word: U_NONE or entry index (| U_QUEUED)
-  int ntx, nty, mtx, mty;
+  int nsx, nsy, rs;       // strips across / down, rows per strip (k_u_local)
+  int mtx, mty, rs_m;     // k_move tiles (M_WARPS strips wide, rs_m rows)
   Diag base;  // diag values already reported
   // native band stepping: message buffers [side] and the all-reduced convergence word
   char *msg_s_send[2] = {nullptr, nullptr}, *msg_s_recv[2] = {nullptr, nullptr};
@@ -115,6 +116,18 @@ static int fail(flowamok_context *ctx, const char *fmt, ...) {
   } while (0)
 
 static inline unsigned int nblk(long long n, int b) { return (unsigned int)((n + b - 1) / b); }
+// rows per strip: long strips amortise the halo rows every strip re-reads, but there must be enough strips (warps)
+// to fill the machine several times over.  FLOWAMOK_STRIP_ROWS overrides (tuning).
+static int strip_rows(const flowamok_context *ctx, int owned_rows, int pitch) {
+  if (const char *e = getenv("FLOWAMOK_STRIP_ROWS")) { int v = atoi(e); if (v >= 1) return v; }
+  const long long nsx = (pitch + STRIP_W - 1) / STRIP_W;
+  const long long want = (long long)ctx->num_sms * 16 * 4;   // warps: 4 waves of 16 resident warps per SM
+  int rs = 64;
+  while (rs > 8 && nsx * ((owned_rows + rs - 1) / rs) < want) rs >>= 1;
+  return rs;
+}
+struct flowamok_grid;
+static int sync_color_buffers(flowamok_context *ctx, flowamok_grid *g);
 
 // FLOWAMOK_DEBUG_SYNC=1: synchronise after every kernel so that a fault is reported at its launch site
 static bool debug_sync() {
@@ -155,7 +168,8 @@ int flowamok_context_new(flowamok_context **out, int device, void *stream) {
   ctx->num_sms = prop.multiProcessorCount;
   if (stream) ctx->stream = (cudaStream_t)stream;
   else { CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
-  CU(cudaFuncSetAttribute(k_move, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MoveSmem)));
+  CU(cudaFuncSetAttribute(k_move, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+  ctx->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_u_iter, UIT_THREADS, 0));
   if (per_sm < 1) return fail(ctx, "k_u_iter does not fit on an SM");
@@ -218,16 +232,19 @@ static int grid_new_impl(flowamok_context *ctx, flowamok_grid **out, int64_t gh_
   CU(cudaMalloc(&g->mymx, g->nwords * 8));
   CU(cudaMalloc(&g->rng, g->ncells_p * 8));
   const int owned = g->own1 - g->own0;
-  g->ntx = (g->pitch + UIT::TW - 1) / UIT::TW; g->nty = (owned + UIT::TR - 1) / UIT::TR;
-  g->mtx = (g->pitch + MT::TW - 1) / MT::TW; g->mty = (owned + MT::TR - 1) / MT::TR;
-  {
-    size_t nslots = (size_t)g->ntx * g->nty * UIT::NT;   // >= nwords (tiles are padded)
-    CU(cudaMalloc(&g->table, nslots * sizeof(UEntry)));
+  g->rs = strip_rows(ctx, owned, g->pitch);
+  g->nsx = (g->pitch + STRIP_W - 1) / STRIP_W; g->nsy = (owned + g->rs - 1) / g->rs;
+  g->rs_m = 16;   // k_move tile rows: 54 KB of shared memory per CTA (descriptors + lists), 4 CTAs per SM
+  if (const char *e = getenv("FLOWAMOK_MOVE_ROWS")) { int v = atoi(e); if (v >= 1 && v <= 128) g->rs_m = v; }
+  while (g->rs_m > 1 && MTL::Smem::bytes(g->rs_m) > ctx->smem_optin) g->rs_m--;
+  g->mtx = (g->nsx + M_WARPS - 1) / M_WARPS; g->mty = (owned + g->rs_m - 1) / g->rs_m;
+  CU(cudaMalloc(&g->table, g->nwords * sizeof(UEntry)));
+  {   // frontier lists; qlist[1] doubles as the per-strip staging area of k_u_local (STRIP_W * rs slots per strip)
+    const size_t nslots = std::max(g->nwords, (size_t)g->nsx * g->nsy * STRIP_W * g->rs);
     CU(cudaMalloc(&g->qlist[0], nslots * 4));
     CU(cudaMalloc(&g->qlist[1], nslots * 4));
-    CU(cudaMalloc(&g->qcnt, (size_t)g->ntx * g->nty * 4));
-    CU(cudaMalloc(&g->ustate, g->nwords * 4));
   }
+  CU(cudaMalloc(&g->ustate, g->nwords * 4));
   CU(cudaMalloc(&g->is, sizeof(IterState)));
   CU(cudaMalloc(&g->diag, sizeof(Diag)));
   CU(cudaMallocHost(&g->h_diag, sizeof(Diag)));
@@ -246,6 +263,13 @@ static int grid_new_impl(flowamok_context *ctx, flowamok_grid **out, int64_t gh_
   CU(cudaMemsetAsync(g->ustate, 0xFF, g->nwords * 4, st));   // U_NONE: halo rows never get entries
   CU(cudaMemsetAsync(g->diag, 0, sizeof(Diag), st));
   CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// After the colour plane of the current buffer was (re)written from outside, make the other buffer identical: the
+// lazy double buffer's invariant (k_move only rewrites the 32-byte sectors that hold a car or an arrival).
+static int sync_color_buffers(flowamok_context *ctx, flowamok_grid *g) {
+  CU(cudaMemcpyAsync(g->color[g->cur ^ 1], g->color[g->cur], g->ncells_p * 4, cudaMemcpyDeviceToDevice, ctx->stream));
   return 0;
 }
 
@@ -271,7 +295,7 @@ int flowamok_grid_free(flowamok_context *ctx, flowamok_grid *g) {
   cudaFree(g->calc); cudaFree(g->mymx); cudaFree(g->rng); cudaFree(g->is); cudaFree(g->diag);
   for (int k = 0; k < 2; k++) { cudaFree(g->msg_s_send[k]); cudaFree(g->msg_s_recv[k]); cudaFree(g->msg_u_send[k]); cudaFree(g->msg_u_recv[k]); }
   cudaFree(g->d_woken); if (g->h_woken) cudaFreeHost(g->h_woken);
-  cudaFree(g->table); cudaFree(g->qlist[0]); cudaFree(g->qlist[1]); cudaFree(g->qcnt); cudaFree(g->ustate);
+  cudaFree(g->table); cudaFree(g->qlist[0]); cudaFree(g->qlist[1]); cudaFree(g->ustate);
   cudaFree(g->ring_words); cudaFree(g->ring_off); cudaFree(g->leak_plane);
   cudaFreeHost(g->h_diag);
   delete g;
@@ -300,6 +324,7 @@ int flowamok_create_grid(flowamok_context *ctx, flowamok_grid *g, int32_t seed, 
   long long n = (long long)g->gh * g->gw;
   k_create<<<nblk(n, 256), 256, 0, st>>>(g->gh, g->gw, g->pitch, g->row0, g->gh_global, g->color[g->cur], g->rng, s0, inc);
   CU(cudaGetLastError());
+  if (sync_color_buffers(ctx, g)) return 1;
   CU(cudaStreamSynchronize(st));
   if (joined_state || joined_inc) {  // join_rng (utils.fut:17): product of states, OR of incs
     u64 js = 1;
@@ -344,6 +369,7 @@ int flowamok_grid_upload(flowamok_context *ctx, flowamok_grid *g, const int8_t *
     CU(cudaMemcpy2DAsync(g->rng + (size_t)l0 * cp, cp * 8, rng_state + (size_t)lo * g->gw, (size_t)g->gw * 8,
                          (size_t)g->gw * 8, nrow, cudaMemcpyHostToDevice, st));
   g->rng_inc = rng_inc;
+  if (sync_color_buffers(ctx, g)) return 1;
   CU(cudaStreamSynchronize(st));
   CU(cudaFree(tmp));
   return 0;
@@ -411,7 +437,7 @@ int flowamok_add_cell(flowamok_context *ctx, flowamok_grid *g, int64_t y, int64_
   if (y < 0 || y >= g->gh_global || x < 0 || x >= g->gw) return fail(ctx, "add_cell: index out of bounds");
   CU(cudaSetDevice(ctx->device));
   if (y < g->row0 || y >= (int64_t)g->row0 + g->gh) return 0;   // not held by this band
-  k_add_cell<<<1, 1, 0, ctx->stream>>>(g->pitch, g->head[g->cur], g->color[g->cur], (int)(y - g->row0), (int)x, color, dy, dx);
+  k_add_cell<<<1, 1, 0, ctx->stream>>>(g->pitch, g->head[g->cur], g->color[g->cur], g->color[g->cur ^ 1], (int)(y - g->row0), (int)x, color, dy, dx);
   CU(cudaGetLastError());
   return 0;
 }
@@ -616,14 +642,15 @@ static GridView make_view(flowamok_grid *g) {
 }
 
 static int launch_u_init(flowamok_context *ctx, flowamok_grid *g, const GridView &v) {
-  k_u_init<<<g->ntx * g->nty, UIT::NT, 0, ctx->stream>>>(v, g->ntx, g->table, g->qlist[0], g->qcnt);
-  KCHECK("k_u_init");
+  k_u_local<<<nblk((long long)g->nsx * g->nsy, STRIP_THREADS / 32), STRIP_THREADS, 0, ctx->stream>>>(v, g->nsx, g->nsy, g->rs, g->table,
+                                                                                                    g->qlist[0], g->qlist[1], g->is);
+  KCHECK("k_u_local");
   return 0;
 }
-// n_init_blocks > 0: iteration 0 takes the frontier segments k_u_init left; 0: resume from qlist[1] (band merge)
-static int launch_u_iter(flowamok_context *ctx, flowamok_grid *g, GridView &v, int n_init_blocks) {
-  void *args[] = {(void *)&v, (void *)&g->table, (void *)&g->qlist[0], (void *)&g->qlist[1], (void *)&g->qcnt,
-                  (void *)&n_init_blocks, (void *)&g->is, (void *)&g->diag};
+// first_it = 0: start from the frontier k_u_local left in qlist[0]; 1: resume from qlist[1] (band merge)
+static int launch_u_iter(flowamok_context *ctx, flowamok_grid *g, GridView &v, unsigned int first_it) {
+  void *args[] = {(void *)&v, (void *)&g->table, (void *)&g->qlist[0], (void *)&g->qlist[1],
+                  (void *)&first_it, (void *)&g->is, (void *)&g->diag};
   CU(cudaLaunchCooperativeKernel((void *)k_u_iter, dim3(ctx->iter_blocks), dim3(UIT_THREADS), args, 0, ctx->stream));
   KCHECK("k_u_iter");
   return 0;
@@ -636,7 +663,7 @@ static int launch_rings(flowamok_context *ctx, flowamok_grid *g, const GridView 
   return 0;
 }
 static int launch_move(flowamok_context *ctx, flowamok_grid *g, const GridView &v, u32 *leak_plane) {
-  k_move<<<g->mtx * g->mty, M_THREADS, sizeof(MoveSmem), ctx->stream>>>(v, g->mtx, g->diag, leak_plane);
+  k_move<<<g->mtx * g->mty, M_WARPS * 32, MTL::Smem::bytes(g->rs_m), ctx->stream>>>(v, g->nsx, g->mtx, g->rs_m, g->diag, leak_plane);
   KCHECK("k_move");
   g->cur ^= 1;
   g->tick++;
@@ -650,7 +677,7 @@ static int enqueue_tick(flowamok_context *ctx, flowamok_grid *g, bool perfect, u
   if (ev) CU(cudaEventRecord(ev[0], st));
   if (launch_u_init(ctx, g, v)) return 1;
   if (ev) CU(cudaEventRecord(ev[1], st));
-  if (launch_u_iter(ctx, g, v, g->ntx * g->nty)) return 1;
+  if (launch_u_iter(ctx, g, v, 0u)) return 1;
   if (ev) CU(cudaEventRecord(ev[2], st));
   if (perfect && launch_rings(ctx, g, v)) return 1;
   if (ev) CU(cudaEventRecord(ev[3], st));
@@ -796,7 +823,8 @@ int flowamok_grid_clone(flowamok_context *ctx, const flowamok_grid *src, flowamo
   CU(cudaMemcpyAsync(g->pref[0], src->pref[src->cur], src->nwords * 4, cudaMemcpyDeviceToDevice, st));
   CU(cudaMemcpyAsync(g->color[0], src->color[src->cur], src->ncells_p * 4, cudaMemcpyDeviceToDevice, st));
   CU(cudaMemcpyAsync(g->rng, src->rng, src->ncells_p * 8, cudaMemcpyDeviceToDevice, st));
-  g->cur = 0; g->rng_inc = src->rng_inc; g->chooser = src->chooser; g->tape = src->tape; g->tick = src->tick;
+  g->cur = 0;
+  if (sync_color_buffers(ctx, g)) return 1; g->rng_inc = src->rng_inc; g->chooser = src->chooser; g->tape = src->tape; g->tick = src->tick;
   if (src->n_rings > 0) {
     CU(cudaMalloc(&g->ring_words, std::max<size_t>(1, (size_t)src->n_ring_words) * sizeof(RingWord)));
     CU(cudaMemcpyAsync(g->ring_words, src->ring_words, (size_t)src->n_ring_words * sizeof(RingWord), cudaMemcpyDeviceToDevice, st));
@@ -871,7 +899,7 @@ int flowamok_band_u_iter(flowamok_context *ctx, flowamok_grid *g) {
   if (band_check(ctx, g, 0)) return 1;
   CU(cudaSetDevice(ctx->device));
   GridView v = make_view(g);
-  return launch_u_iter(ctx, g, v, g->ntx * g->nty);
+  return launch_u_iter(ctx, g, v, 0u);
 }
 int flowamok_band_u_begin(flowamok_context *ctx, flowamok_grid *g) {
   return flowamok_band_u_init(ctx, g) || flowamok_band_u_iter(ctx, g);
@@ -911,7 +939,7 @@ int flowamok_band_u_resume(flowamok_context *ctx, flowamok_grid *g) {
   if (band_check(ctx, g, 0)) return 1;
   CU(cudaSetDevice(ctx->device));
   GridView v = make_view(g);
-  return launch_u_iter(ctx, g, v, 0);
+  return launch_u_iter(ctx, g, v, 1u);
 }
 int flowamok_band_rings(flowamok_context *ctx, flowamok_grid *g) {
   if (band_check(ctx, g, 0)) return 1;
@@ -1050,6 +1078,7 @@ int flowamok_grid_upload_cars(flowamok_context *ctx, flowamok_grid *g, const int
                        (size_t)g->gw * 4, owned, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpy2DAsync(g->rng + (size_t)g->own0 * cp, cp * 8, rng_state + (size_t)lo * g->gw, (size_t)g->gw * 8,
                        (size_t)g->gw * 8, owned, cudaMemcpyHostToDevice, st));
+  if (sync_color_buffers(ctx, g)) return 1;
   CU(cudaStreamSynchronize(st));
   CU(cudaFree(tmp));
   return 0;
@@ -1087,6 +1116,7 @@ int flowamok_generate_synthetic(flowamok_context *ctx, flowamok_grid *g, uint64_
                                                                g->color[g->cur], g->rng);
   CU(cudaGetLastError());
   g->rng_inc = (0xda3e39cb94b95bdbULL << 1) | 1ULL;
+  if (sync_color_buffers(ctx, g)) return 1;
   CU(cudaFree(g->ring_words)); CU(cudaFree(g->ring_off));
   g->ring_words = nullptr; g->ring_off = nullptr; g->n_rings = g->n_ring_cells = g->n_ring_words = 0; g->ring_stride = 0;
   g->h_off.clear(); g->h_y.clear(); g->h_x.clear(); g->h_cy.clear(); g->h_cx.clear();

@@ -1,26 +1,36 @@
 // flowamok_b200 -- CUDA kernels (sm_100a) of the per-tick grid update.
 //
-// Kernel list (one tick = k_u_init, k_u_iter, [k_rings], k_move):
-//   k_u_init  : streaming, one thread per plane word (32 cells): statics and initial state of
-//               update_can_be_moved_to_from (steppers.fut:9-56) and compaction of the words that hold
-//               a waiting car into per-CTA worklists.
-//   k_u_iter  : cooperative persistent kernel; relaxes the worklists under a grid-wide barrier and
-//               a device-side changed flag until the global fixpoint (steppers.fut:147-164) -- no
+// Kernel list (one tick = k_u_local, k_u_iter, [k_rings], k_move):
+//   k_u_local : streaming, one warp per strip of 30 plane words x RS rows (fa_stream.h, UStrip): statics
+//               and the first two Jacobi levels of update_can_be_moved_to_from (steppers.fut:9-56) in
+//               registers, worklist entries for the words that still hold a waiting car, frontier.
+//   k_u_iter  : cooperative persistent kernel; relaxes the frontier under a grid-wide barrier and
+//               device-side list lengths until the global fixpoint (steppers.fut:147-164) -- no
 //               host round trip per iteration, and each iteration touches only unresolved words.
 //   k_rings   : resolve_cycles (steppers.fut:189-224) on the sparse ring list, one thread per ring.
-//   k_move    : move_cell + reset_cells (steppers.fut:58-145): new car planes, colour payload moved
-//               by TMA bulk copies, per-cell pcg32 draws at forks, leak count.
+//   k_move    : streaming like k_u_local (MStrip): move_cell + reset_cells (steppers.fut:58-145): new car
+//               planes, colour payload through a lazy double buffer (only 32-byte sectors that hold a car or
+//               an arrival are rewritten), per-cell pcg32 draws at forks, leak count.
 // plus packing / unpacking / generator / render helpers.
 #pragma once
 #include <cuda_runtime.h>
 
+#include "fa_stream.h"
 #include "fa_tiles.h"
 
 namespace fa {
 
-typedef MTile<8, 32> MT;
-constexpr int M_THREADS = 256;
-typedef UInitTile<16, 32> UIT;             // k_u_init block: 16 rows x 32 words, one owned word per thread
+constexpr int STRIP_W = 30;                // owned plane words per strip (lanes 0 and 31 carry the neighbours)
+constexpr int STRIP_THREADS = 128;         // k_u_local / k_move block: 4 warps = 4 strips side by side
+#ifndef FA_U_LEVELS
+#define FA_U_LEVELS 3                      // Jacobi levels k_u_local resolves in registers (queues of <= 3 cars)
+#endif
+#ifndef FA_U_MINB
+#define FA_U_MINB 1                        // resident CTAs per SM the register allocation of k_u_local aims for
+#endif
+#ifndef FA_M_MINB
+#define FA_M_MINB 1                        // the same for k_move
+#endif
 constexpr int UIT_THREADS = 512;           // k_u_iter block
 
 struct IterState {
@@ -38,47 +48,19 @@ struct Diag {
 };
 
 // ---------------------------------------------------------------------------------------------
-// k_u_init: no global atomics.  Block b owns table[b*NT .. b*NT+NT) (entry of thread t at b*NT+t) and
-// the frontier segment qseg[b*NT .. ) of length qcnt[b].
+// k_u_local / k_move: warp `wg` of the grid takes strip (wg / nsx, wg % nsx): rows [own0 + sy*rs, +rs), words
+// [sx*STRIP_W, +STRIP_W).  The four warps of a CTA are four strips side by side, so the halo words they share hit L1.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(UIT::NT, 3)
-k_u_init(const __grid_constant__ GridView g, int ntx, UEntry *table, unsigned int *qseg, unsigned int *qcnt) {
-  __shared__ UIT::Smem s;
-  __shared__ unsigned int wq[UIT::TR];
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  UIT tile(g, s, blockIdx.x / ntx, blockIdx.x % ntx);
-  UIT::Raw own, ring;
-  tile.p0(t, own, ring);
-  __syncthreads();
-  UIT::Own o;
-  tile.pA(t, own, ring, o);
-  __syncthreads();
-  bool converged = false;
-  for (int k = 0; k < UIT::NS; k++) {
-    UState n;
-    const bool ch = tile.sweep_compute(o, n);
-    if (!__syncthreads_or(ch)) { converged = true; break; }   // also: every read of this sweep is done
-    tile.sweep_commit(o, n);
-    __syncthreads();
-  }
-  UEntry e = {0, 0, 0, 0};
-  const int kind = tile.pC(t, o, converged, e);
-  if (g.gh != g.gh_global) tile.ghost_publish(t);   // row bands only
-  const unsigned pos = blockIdx.x * (unsigned)UIT::NT + (unsigned)t;
-  if (kind >= 1) {
-    table[pos] = e;
-    g.ustate[e.wi] = kind == 2 ? (pos | U_QUEUED) : pos;
-  } else if (o.in) {
-    g.ustate[(size_t)o.y * g.pitch + o.w] = U_NONE;
-  }
-  const unsigned m2 = __ballot_sync(0xFFFFFFFFu, kind == 2);
-  if (lane == 0) wq[warp] = __popc(m2);
-  __syncthreads();
-  unsigned before = 0, total = 0;
-#pragma unroll
-  for (int k = 0; k < UIT::TR; k++) { unsigned c = wq[k]; if (k < warp) before += c; total += c; }
-  if (kind == 2) qseg[(size_t)blockIdx.x * UIT::NT + before + __popc(m2 & ((1u << lane) - 1u))] = pos;
-  if (t == 0) qcnt[blockIdx.x] = total;
+__global__ void __launch_bounds__(STRIP_THREADS, FA_U_MINB)
+k_u_local(const __grid_constant__ GridView g, int nsx, int nsy, int rs, UEntry *table, unsigned int *qlist0,
+          unsigned int *qstage, IterState *is) {
+  const int wg = (int)(blockIdx.x * (STRIP_THREADS / 32) + (threadIdx.x >> 5));
+  if (wg >= nsx * nsy) return;   // whole warp
+  const int sy = wg / nsx, sx = wg - sy * nsx;
+  const int ya = g.own0 + sy * rs, yb = min(g.own1, ya + rs);
+  // staging segment of this strip: qstage is the second frontier list, idle until k_u_iter starts
+  UStrip<STRIP_W, FA_U_LEVELS>::run(g, sx, ya, yb, (int)(threadIdx.x & 31), table, qstage + (size_t)wg * STRIP_W * rs, qlist0,
+                                    &is->qn[0]);
 }
 
 // Sense-reversing grid barrier; co-residency is guaranteed by the cooperative launch.  A watchdog
@@ -110,18 +92,16 @@ __device__ __forceinline__ bool grid_barrier(IterState *is, unsigned int nblocks
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_u_iter: frontier iterations.  Iteration 0 visits the per-block frontier segments k_u_init left in
-// qlist0 (each CTA flattens the segments of its share of blocks); iteration it >= 1 visits the entry
-// indices iteration it-1 appended to qlist[it & 1].  Pushes are staged in shared memory and appended
-// with one global atomic per CTA-chunk.  Ends when an iteration produces an empty list.
+// k_u_iter: frontier iterations.  Iteration `it` visits the entry indices in qlist[it & 1] (iteration 0: the
+// frontier k_u_local appended to qlist0) and appends the words it wakes to the other list, warp-aggregated with one
+// global atomic per warp and push slot.  Ends when an iteration produces an empty list.
 // ---------------------------------------------------------------------------------------------
-constexpr int UIT_SEG = 256;   // init-blocks whose frontier segments one CTA flattens at a time
 constexpr unsigned int UIT_TAIL = 512;    // frontier length below which CTA 0 finishes the fixpoint alone
 
+// first_it = 0: start from the frontier k_u_local left in qlist0 / qn[0]; 1: resume from qlist1 / qn[1] (band merge)
 __global__ void __launch_bounds__(UIT_THREADS, 2)
 k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *qlist0, unsigned int *qlist1,
-         const unsigned int *qcnt, int n_init_blocks, IterState *is, Diag *diag) {
-  __shared__ unsigned int pre[UIT_SEG + 1], wtot[UIT_SEG / 32];
+         unsigned int first_it, IterState *is, Diag *diag) {
   const int tid = threadIdx.x, nt = blockDim.x, b = blockIdx.x, nb = gridDim.x, lane = tid & 31;
   volatile IterState *vis = is;
   unsigned int *ql[2] = {qlist0, qlist1};
@@ -150,46 +130,8 @@ k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *
     }
   };
 
-  // ---- iteration 0: the per-block frontier segments; output goes to qlist1 / qn[1]
-  {
-    const int per = (n_init_blocks + nb - 1) / nb;
-    const int blk_lo = b * per, blk_hi = min(n_init_blocks, blk_lo + per);
-    for (int s0 = blk_lo; s0 < blk_hi; s0 += UIT_SEG) {
-      const int ns = min(UIT_SEG, blk_hi - s0);
-      // exclusive prefix of the segment lengths (ns <= 256: one warp-scan pass per 32, tiny)
-      {  // block-wide inclusive scan of the ns <= UIT_SEG segment lengths (warp shuffles + 8 warp totals)
-        unsigned v = tid < ns ? qcnt[s0 + tid] : 0u;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { unsigned u = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= d) v += u; }
-        if (tid < UIT_SEG && lane == 31) wtot[tid >> 5] = v;
-        __syncthreads();
-        if (tid < UIT_SEG) {
-          unsigned add = 0;
-          for (int k = 0; k < (tid >> 5); k++) add += wtot[k];
-          pre[tid + 1] = v + add;
-        }
-        if (tid == 0) pre[0] = 0;
-        __syncthreads();
-      }
-      const unsigned int tot = pre[ns];
-      for (unsigned int k0 = 0; k0 < tot; k0 += nt) {
-        const unsigned int k = k0 + tid;
-        bool has = k < tot;
-        unsigned int idx = 0;
-        if (has) {
-          int lo = 0, hi = ns;   // largest lo with pre[lo] <= k
-          while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (pre[mid] <= k) lo = mid; else hi = mid; }
-          idx = qlist0[(size_t)(s0 + lo) * UIT::NT + (k - pre[lo])];
-        }
-        visit_and_flush(has, idx, qlist1, &is->qn[1]);
-      }
-      relaxed += tot;
-      __syncthreads();
-    }
-    if (!grid_barrier(is, nb)) return;
-  }
-  // ---- iterations 1, 2, ...
-  unsigned int it = 1;
+  // iteration `it` visits the entry indices in qlist[it & 1] (length qn[it % 3]) and appends to qlist[(it + 1) & 1]
+  unsigned int it = first_it;
   bool tail = false;   // once the frontier is short, CTA 0 finishes alone: no more grid-wide barriers
   for (;; it++) {
     const unsigned int n = vis->qn[it % 3u];
@@ -212,10 +154,10 @@ k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *
     else if (!grid_barrier(is, nb)) return;
   }
   if (tid == 0) {
-    atomicAdd(&diag->sweeps, relaxed);
+    if (relaxed) atomicAdd(&diag->sweeps, relaxed);
     if (b == 0) {
       is->qn[0] = 0; is->qn[1] = 0; is->qn[2] = 0;   // the slot everyone just read is 0 already
-      atomicAdd(&diag->passes, (unsigned long long)it);
+      atomicAdd(&diag->passes, (unsigned long long)(it - first_it));
     }
   }
 }
@@ -300,101 +242,28 @@ k_rings(const __grid_constant__ GridView g, const RingWord *words, const unsigne
 }
 
 // ---------------------------------------------------------------------------------------------
-// TMA (bulk async copy) + mbarrier wrappers.  The colour payload is pure data movement, so it is
-// handed to the copy engine: global -> shared -> global in 4 KB rows, no per-thread LDG/STG.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t done = 0;
-  do {
-    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-               ::"l"(dst_gmem), "r"(smem_addr(src_smem)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit_wait_all() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
-
-// ---------------------------------------------------------------------------------------------
 // move + reset
 // ---------------------------------------------------------------------------------------------
-struct MoveSmem {
-  MT::Smem m;
-  alignas(128) u32 color[MT::TR][MT::TW * 32];  // the tile's colour payload, staged by TMA
-  alignas(8) uint64_t bar;
-};
-
-__global__ void __launch_bounds__(M_THREADS, 4)
-k_move(const __grid_constant__ GridView g, int mtx, Diag *diag, unsigned int *leak_plane) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  MoveSmem &sm = *reinterpret_cast<MoveSmem *>(smem_raw);
-  MT::Smem &s = sm.m;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int ty = blockIdx.x / mtx, tx = blockIdx.x % mtx;
-  const int y0 = g.own0 + ty * MT::TR, w0 = tx * MT::TW;
-  const int rows = min(MT::TR, g.own1 - y0), words = min(MT::TW, g.pitch - w0);
-  const size_t cpitch = (size_t)g.pitch * 32;
-  const uint32_t row_bytes = (uint32_t)words * 128u;
-  // 1. kick off the colour tile: one bulk copy per row, completion counted on the mbarrier
-  if (tid == 0) mbar_init(&sm.bar, 1);
+constexpr int M_WARPS = 4;                 // k_move CTA: 4 strips side by side
+typedef MTile<STRIP_W, M_WARPS> MTL;
+__global__ void __launch_bounds__(M_WARPS * 32, FA_M_MINB)
+k_move(const __grid_constant__ GridView g, int nsx, int ntx, int rs, Diag *diag, unsigned int *leak_plane) {
+  extern __shared__ __align__(16) u32 smem_raw[];
+  const MTL::Smem sm = {smem_raw, rs};
+  const int tid = threadIdx.x, nt = M_WARPS * 32, wi = tid >> 5, lane = tid & 31;
+  const int ty = blockIdx.x / ntx, tx = blockIdx.x - ty * ntx;
+  const int ya = g.own0 + ty * rs, yb = min(g.own1, ya + rs);
+  const int sx = tx * M_WARPS + wi;
+  if (blockIdx.x == 0 && tid == 0) atomicAdd(&diag->ticks, 1ull);
+  MTL::phaseB_clear(sm, tid);
+  const unsigned int nleak = MTL::phaseA(g, sx < nsx, sx, wi, ya, yb, lane, leak_plane, sm);
+  if (nleak) atomicAdd(&diag->leaks, (unsigned long long)nleak);
   __syncthreads();
-  if (tid == 0) {
-    mbar_expect_tx(&sm.bar, row_bytes * (uint32_t)rows);
-    for (int r = 0; r < rows; r++)
-      bulk_g2s(&sm.color[r][0], g.color_in + (size_t)(y0 + r) * cpitch + (size_t)w0 * 32, row_bytes, &sm.bar);
-  }
-  // 2. control planes while the payload is in flight
-  MT t(g, s, ty, tx);
-  t.p0(tid, nt);
+  MTL::phaseB0(sm, yb - ya, tid, nt);
   __syncthreads();
-  t.p1(tid, nt, leak_plane);
-  __syncthreads();
-  // 3. payload landed -> stream it out unchanged, then overwrite the few cells a car arrived in
-  mbar_wait(&sm.bar, 0);
-  if (tid == 0) {
-    for (int r = 0; r < rows; r++)
-      bulk_s2g(g.color_out + (size_t)(y0 + r) * cpitch + (size_t)w0 * 32, &sm.color[r][0], row_bytes);
-    bulk_commit_wait_all();   // writes performed before any patch store is issued
-  }
-  __syncthreads();
-  for (int i = tid; i < MT::TR * MT::TW; i += nt) {
-    u32 ay = s.AY[i], ax = s.AX[i];
-    u32 m = ay | ax;
-    if (!m) continue;
-    int tr = i / MT::TW, tc = i - tr * MT::TW;
-    int si = MT::idx(tr + 1, tc + 1);
-    u32 uys = s.UYS[si], uxs = s.UXS[si];
-    size_t base = (size_t)(y0 + tr) * cpitch + (size_t)(w0 + tc) * 32;
-    while (m) {  // steppers.fut:109: the arriving car brings its colour
-      int b = __ffs(m) - 1;
-      u32 bit = 1u << b;
-      m &= m - 1;
-      int sr = tr, sx = tc * 32 + b;  // source cell in tile coordinates
-      if (ay & bit) sr += (uys & bit) ? 1 : -1; else sx += (uxs & bit) ? 1 : -1;
-      u32 col;
-      if (sr >= 0 && sr < rows && sx >= 0 && sx < words * 32) col = sm.color[sr][sx];
-      else col = g.color_in[(size_t)(y0 + sr) * cpitch + (size_t)w0 * 32 + sx];
-      g.color_out[base + b] = col;
-    }
-  }
-  if (tid == 0 && s.leaks) atomicAdd(&diag->leaks, (unsigned long long)s.leaks);
-  if (tid == 0 && blockIdx.x == 0) atomicAdd(&diag->ticks, 1ull);
+  MTL::phaseB1(g, sm, tx * M_WARPS, ya, tid, nt);
+  __syncthreads();   // the sector copies are ordered before the arrival patches
+  MTL::phaseB2(g, sm, tx * M_WARPS, ya, yb - ya, tid, nt);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -475,7 +344,7 @@ __global__ void k_line_h(int pitch, U4 *road, int y, int x0, int x1, int flow) {
   if (flow != 0) road[o].z |= m; else road[o].z &= ~m;
   if (flow < 0) road[o].w |= m; else road[o].w &= ~m;
 }
-__global__ void k_add_cell(int pitch, U4 *head, u32 *color, int y, int x, u32 col, int dy, int dx) {
+__global__ void k_add_cell(int pitch, U4 *head, u32 *color, u32 *color_other, int y, int x, u32 col, int dy, int dx) {
   size_t o = (size_t)y * pitch + (x >> 5);
   u32 bit = 1u << (x & 31);
   U4 h = head[o];
@@ -483,6 +352,7 @@ __global__ void k_add_cell(int pitch, U4 *head, u32 *color, int y, int x, u32 co
   h.z = dx != 0 ? (h.z | bit) : (h.z & ~bit); h.w = dx < 0 ? (h.w | bit) : (h.w & ~bit);
   head[o] = h;
   color[(size_t)y * pitch * 32 + x] = col;
+  color_other[(size_t)y * pitch * 32 + x] = col;   // keep the lazy double buffer's invariant
 }
 
 // ---------------------------------------------------------------------------------------------

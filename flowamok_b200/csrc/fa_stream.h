@@ -1,0 +1,513 @@
+// flowamok_b200 -- streaming strip programs of the per-tick update (the bodies of k_u_local and k_move).
+//
+// One WARP walks a strip of the grid top to bottom: lane l holds plane word w0 - 1 + l of the current row, so lanes
+// 1..SW own SW consecutive words (32*SW cells) and lanes 0 and SW+1 carry the neighbouring words read-only.  A row's
+// x-neighbours are one warp shuffle away, its y-neighbours are the previous / next row, which the lane itself still
+// holds in registers (sliding window): every plane word is loaded once per strip with fully coalesced 128-bit
+// accesses, nothing is staged in shared memory and there is no block barrier.  The bit logic is the one of fa_bits.h.
+//
+//   UStrip : update_can_be_moved_to_from (steppers.fut:9-56), first two Jacobi levels of the fixpoint (:147-164) in a
+//            three-stage row pipeline, publication of calc / my|mx, and the worklist entries + frontier for k_u_iter.
+//   MTile  : move_cell + reset_cells (steppers.fut:58-145), per-cell RNG draws at forks, leak count (phase A, a warp
+//            per strip) and the colour payload through the lazy double buffer (phase B, the whole CTA).
+//
+// Written once for device and host: tests/emul runs these very functions on the CPU with the lanes of a warp as
+// coroutines (fa_simt.h) and compares every tick with the oracle.
+#pragma once
+#include "fa_simt.h"
+#include "fa_tiles.h"
+
+namespace fa {
+
+// per-lane column constants of a strip
+struct StripCol {
+  int w;            // plane word of this lane (may lie outside [0, pitch): then it reads as zeros)
+  bool w_ok;        // 0 <= w < pitch
+  bool owner;       // lane owns the word: it is inside the strip and w_ok
+  u32 colFirst, colLast, colValid;   // Edge masks that depend on the column only
+};
+template <int SW>
+FA_HD StripCol strip_col(const GridView &g, int sx, int lane) {
+  StripCol c;
+  c.w = sx * SW - 1 + lane;
+  c.w_ok = c.w >= 0 && c.w < g.pitch;
+  c.owner = lane >= 1 && lane <= SW && c.w_ok;
+  Edge e = edge_masks(0, c.w, 1, g.gw);
+  c.colFirst = e.colFirst; c.colLast = e.colLast; c.colValid = c.w_ok ? e.valid : 0u;
+  return c;
+}
+// Edge of (local row y, this lane's word); rows outside the global grid have no valid cell
+FA_HD Edge strip_edge(const GridView &g, const StripCol &c, int y) {
+  Edge e;
+  const int yg = y + g.row0;
+  e.rowFirst = (yg == 0) ? 0xFFFFFFFFu : 0u;
+  e.rowLast = (yg == g.gh_global - 1) ? 0xFFFFFFFFu : 0u;
+  e.colFirst = c.colFirst; e.colLast = c.colLast;
+  e.valid = row_in(g, y) ? c.colValid : 0u;
+  return e;
+}
+FA_HD W3 simt_w3(u32 v) {
+  W3 r;
+  r.l = simt_up1(v); r.c = v; r.r = simt_dn1(v);
+  return r;
+}
+FA_HD W3 w3_c(u32 v) {
+  W3 r = {0u, v, 0u};
+  return r;
+}
+
+// =============================================================================================
+// U strip.  Levels (pure Jacobi, so every level is a function of the raw planes only and a strip can recompute its
+// neighbours' rows exactly):
+//   L0(y)   = terminals:              R = T, MY = T & GY, MX = T & GX                  needs raw rows y-1 .. y+1
+//   Lk(y)   = relax(Lk-1(y-1..y+1))   k = 1..K; LK is published as calc / my|mx         needs raw rows y-k-1 .. y+k+1
+//   LK+1(y) = relax(LK(y-1..y+1))     only compared with LK(y): a word with an unresolved waiting car goes on the
+//           frontier iff LK+1 != LK; otherwise it is DORMANT -- consistent with all its neighbours' published values,
+//           it can only change after one of them does, and that neighbour's visit will wake it (k_u_iter).
+// A queue of c cars behind a free cell is resolved here for c <= K; only longer queues (and cars behind a full ring)
+// reach k_u_iter.  The row pipeline has K + 2 stages: when raw row j arrives, the statics and L0 of row j-1, Lk of
+// row j-1-k and the verdict on row j-2-K are computed.
+// Cars with a diagonal heading (utils.fut:35 allows them) are never relaxed here: their word always starts on the
+// frontier.  Row bands: the ghost rows own0-1 / own1 stay at L0 (the raw rows beyond are not held), which is
+// published as this band's lower bound of the neighbour's row; the first / last owned row then always starts on the
+// frontier.
+// Frontier: the strip collects its entries in a private segment (qseg) and appends them to the device-wide list
+// with ONE atomic at its end -- per-row atomics on one counter serialise in L2 and dominate the kernel.
+// =============================================================================================
+template <int SW, int K>
+struct UStrip {
+  struct Raw {
+    U4 road, head;
+    u32 pref;
+  };
+  struct Stat {
+    u32 T, GY, GX, LN, LS, LW, LE, DG;
+  };
+  struct Env {
+    const GridView &g;
+    StripCol col;
+    int lane;
+    bool band;
+    int ya, yb;     // owned rows of the strip
+    int ylo, yhi;   // local rows that exist in the planes and lie inside the global grid
+    UEntry *table;
+    unsigned int *qseg;   // this strip's private frontier segment (SW * (yb - ya) slots)
+  };
+  FA_HD static void load_raw(const Env &E, int y, Raw &q) {
+    const U4 z = {0, 0, 0, 0};
+    q.road = z; q.head = z; q.pref = 0u;
+    if (E.col.w_ok && y >= E.ylo && y < E.yhi) {
+      const u32 o = (u32)y * (u32)E.g.pitch + (u32)E.col.w;
+      q.road = E.g.road[o]; q.head = E.g.head_in[o]; q.pref = E.g.pref_in[o];
+    }
+  }
+  FA_HD static void prefetch_raw(const Env &E, int y) {
+    if (E.col.w_ok && y >= E.ylo && y < E.yhi) {
+      const u32 o = (u32)y * (u32)E.g.pitch + (u32)E.col.w;
+      fa_prefetch_l2(&E.g.road[o]); fa_prefetch_l2(&E.g.head_in[o]);
+      if ((E.lane & 7) == 1) fa_prefetch_l2(&E.g.pref_in[o]);   // 4-byte words: one prefetch per 32-byte sector
+    }
+  }
+  FA_HD static UState relax(const Stat &s, u32 valid, const UState &a, const UState &b, const UState &c) {
+    UStatic st;
+    st.T = s.T; st.GYr = s.GY; st.GXr = s.GX; st.LN = s.LN; st.LS = s.LS; st.LW = s.LW; st.LE = s.LE;
+    st.LNW = st.LNE = st.LSW = st.LSE = 0u;
+    UState n = u_relax_card(st, a.R, simt_w3(b.R), c.R, a.MY, c.MY, simt_w3(b.MX));
+    n.R &= valid; n.MY &= valid; n.MX &= valid;
+    return n;
+  }
+
+  // One pipeline step: raw row j has arrived.  rA / rB = raw rows j-1 / j; roadc2 / dyn2 = road presence and DYN of
+  // row j-2.  S[i] = statics of row j-1-i (shifted here).  Lv[k] holds level k of three consecutive rows in a ring
+  // whose slots rotate with the step's phase P = (step number) mod 3: N is written now (row j-1-k), M and O hold rows
+  // j-2-k and j-3-k -- the callers unroll three phases, so the rings are pure register renaming.
+  // Rows outside the grid hold zeros and produce values nobody reads (a car heading out of the grid is a terminal).
+  template <int P>
+  FA_HD static void step(const Env &E, int j, const Raw &rA, const Raw &rB, u32 &roadc2, u32 &dyn2, Stat (&S)[K + 2],
+                         UState (&Lv)[K + 1][3], u32 &nq) {
+    constexpr int N = (3 - P) % 3, M = (N + 1) % 3, O = (N + 2) % 3;
+    const GridView &g = E.g;
+    const u32 valid = E.col.colValid;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = K + 1; i >= 1; i--) S[i] = S[i - 1];
+    // ---- statics and L0 of row j-1
+    {
+      const int yg = j - 1 + g.row0;
+      const u32 roadc1 = rA.road.x | rA.road.z, roadc0 = rB.road.x | rB.road.z;
+      W3 road_up = w3_c(roadc2), road_dn = w3_c(roadc0);
+      if (simt_any((rA.head.x & rA.head.z) != 0u)) {   // a diagonal heading looks at the corner cells
+        road_up = simt_w3(roadc2); road_dn = simt_w3(roadc0);
+      }
+      Edge e;
+      e.rowFirst = (yg == 0) ? 0xFFFFFFFFu : 0u;
+      e.rowLast = (yg == g.gh_global - 1) ? 0xFFFFFFFFu : 0u;
+      e.colFirst = E.col.colFirst; e.colLast = E.col.colLast; e.valid = valid;
+      const UStatic st = u_statics(rA.road.x, rA.road.y, rA.road.z, rA.road.w, rA.head.x, rA.head.y, rA.head.z, rA.head.w,
+                                   rA.pref, road_up, simt_w3(roadc1), road_dn, dyn2, rB.head.x, simt_w3(rA.head.z), e);
+      Stat &sN = S[0];
+      sN.T = st.T; sN.GY = st.GYr; sN.GX = st.GXr; sN.LN = st.LN; sN.LS = st.LS; sN.LW = st.LW; sN.LE = st.LE;
+      sN.DG = st.LNW | st.LNE | st.LSW | st.LSE;
+      UState &a = Lv[0][N];
+      a.R = st.T & valid; a.MY = a.R & st.GYr; a.MX = a.R & st.GXr;
+      roadc2 = roadc1; dyn2 = rA.head.x;
+    }
+    // ---- level k of row j-1-k; a band's ghost rows stay at L0 (the raw rows beyond are not held)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 1; k <= K; k++) {
+      const int y = j - 1 - k;
+      const UState n = relax(S[k], valid, Lv[k - 1][O], Lv[k - 1][M], Lv[k - 1][N]);
+      const bool ghost = E.band && (y < g.own0 || y >= g.own1);
+      UState &b = Lv[k][N];
+      b.R = ghost ? Lv[k - 1][M].R : n.R; b.MY = ghost ? Lv[k - 1][M].MY : n.MY; b.MX = ghost ? Lv[k - 1][M].MX : n.MX;
+    }
+    if (E.band) {   // ghost row: this band's lower bound of the neighbour's row
+      const int y = j - 1 - K;
+      if (((y == g.own0 - 1 && E.ya == g.own0) || (y == g.own1 && E.yb == g.own1)) && E.col.owner && y >= E.ylo && y < E.yhi) {
+        const u32 o = (u32)y * (u32)g.pitch + (u32)E.col.w;
+        g.mymx[o] = pack_mymx(Lv[K][N].MY, Lv[K][N].MX);
+        g.calc[o] = Lv[K][N].R;
+      }
+    }
+    // ---- publish row j-2-K and decide its worklist status
+    {
+      const int y = j - 2 - K;
+      const Stat &sO = S[K + 1];
+      const UState &pub = Lv[K][M];
+      const UState n = relax(sO, valid, Lv[K][O], pub, Lv[K][N]);
+      const u32 unresolved = ~pub.R & ~sO.T & valid;
+      bool front = false;
+      const u32 o = (u32)y * (u32)g.pitch + (u32)E.col.w;
+      if (E.col.owner && y >= E.ya && y < E.yb) {
+        g.mymx[o] = pack_mymx(pub.MY, pub.MX);
+        g.calc[o] = pub.R;
+        u32 us = U_NONE;
+        if (unresolved) {
+          front = n.R != pub.R || n.MY != pub.MY || n.MX != pub.MX || (sO.DG & unresolved) != 0u ||
+                  (E.band && (y == g.own0 || y == g.own1 - 1));
+          UEntry en;
+          en.wi = o; en.T = sO.T; en.GY = sO.GY; en.GX = sO.GX;
+          E.table[o] = en;
+          us = front ? (o | U_QUEUED) : o;
+        }
+        g.ustate[o] = us;
+      }
+      const u32 fm = simt_ballot(front);
+      if (front) E.qseg[nq + (u32)popc32(fm & ((1u << E.lane) - 1u))] = o;
+      nq += (u32)popc32(fm);
+    }
+  }
+
+  // rows [ya, yb) of strip column sx.  qseg: private staging of SW * (yb - ya) slots; qlist / qn: the device-wide
+  // frontier list and its length.
+  FA_HD static void run(const GridView &g, int sx, int ya, int yb, int lane, UEntry *table, unsigned int *qseg,
+                        unsigned int *qlist, unsigned int *qn) {
+    const int ylo = g.row0 < 0 ? -g.row0 : 0;
+    const int yhi = g.gh < g.gh_global - g.row0 ? g.gh : g.gh_global - g.row0;
+    const Env E = {g, strip_col<SW>(g, sx, lane), lane, g.gh != g.gh_global, ya, yb, ylo, yhi, table, qseg};
+    // Raw rows ya-K-2 .. yb+K+1 are read.  Slots rotate with period 3: at step j, R0/R1/R2 hold raw rows j-1, j, j+1.
+    const int j0 = ya - K - 1, jend = yb + K + 1;   // the step at jend publishes row yb-1
+    Raw R0, R1, R2;
+    load_raw(E, j0 - 1, R0); load_raw(E, j0, R1); load_raw(E, j0 + 1, R2);
+    u32 roadc2 = 0u, dyn2 = 0u, nq = 0u;
+    Stat S[K + 2];
+    UState Lv[K + 1][3];
+    {
+      const Stat zs = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+      const UState z3 = {0u, 0u, 0u};
+      for (int i = 0; i < K + 2; i++) S[i] = zs;
+      for (int k = 0; k <= K; k++)
+        for (int i = 0; i < 3; i++) Lv[k][i] = z3;
+    }
+    constexpr int AHEAD = 6;   // rows between the L2 prefetch and the register load of a row
+    for (int y = j0 + 2; y < j0 + 2 + AHEAD; y++) prefetch_raw(E, y);
+    // the last one or two steps of the last trip may run past jend: they publish nothing (the stores check y < yb)
+    for (int j = j0; j <= jend; j += 3) {
+      step<0>(E, j, R0, R1, roadc2, dyn2, S, Lv, nq);
+      load_raw(E, j + 2, R0); prefetch_raw(E, j + 2 + AHEAD);
+      step<1>(E, j + 1, R1, R2, roadc2, dyn2, S, Lv, nq);
+      load_raw(E, j + 3, R1); prefetch_raw(E, j + 3 + AHEAD);
+      step<2>(E, j + 2, R2, R0, roadc2, dyn2, S, Lv, nq);
+      load_raw(E, j + 4, R2); prefetch_raw(E, j + 4 + AHEAD);
+    }
+    // ---- append the strip's frontier to the device-wide list: one atomic per strip
+    if (nq) {   // warp-uniform
+      u32 base = 0u;
+      if (lane == 0) base = FA_ATOMIC_ADD_U32(qn, nq);
+      base = simt_bcast(base, 0);
+      simt_sync();   // the staging stores of all lanes are visible to all lanes
+      for (u32 k = (u32)lane; k < nq; k += 32u) qlist[base + k] = qseg[k];
+    }
+  }
+};
+
+// =============================================================================================
+// M tile: move_cell + reset_cells (steppers.fut:58-145).  A CTA of NWARP warps takes NWARP strips side by side.
+//
+//   phase A (one warp per strip, sliding window like UStrip): new car planes, next_preference_flow_x, per-cell RNG
+//            draws at forks, leak count -- and, per plane word, a 16-byte colour descriptor {T, A, V, S} in shared
+//            memory: T = cells whose 32-byte colour sector must be rewritten, A = arrival cells, V = arrival comes
+//            along y, S = the predecessor sits on the + side (row y+1 / column x+1).
+//   phase B (all threads of the CTA, after a block barrier): the colour payload (steppers.fut:109).
+//            B0 scans the descriptors and compacts the touched sectors and the arrivals into two shared-memory lists;
+//            B1 copies the listed sectors color_in -> color_out, a lane pair per sector, eight independent 16-byte
+//               loads in flight per thread; B2 gives every listed arrival the predecessor's colour.
+//            Dense lists keep every load slot useful: the phase is bound by memory latency, and the bytes in flight
+//            per SM (Little's law) are what sets its speed.  While one CTA waits in phase B, the others compute.
+//
+// LAZY double buffer.  Invariant at the start of a tick: color_out equals color_in everywhere except, possibly, at
+// cells that are occupied now (a car arrived there during the previous tick, when color_out was that tick's input).
+// So a sector of color_out is rewritten iff it holds an occupied cell or an arrival of this tick; all other sectors
+// are already right and cost no traffic.  An arrival reads color_in, which nobody writes during the tick.
+// =============================================================================================
+template <int SW, int NWARP, int CAP = 2048>
+struct MTile {
+  static constexpr int TW = SW * NWARP;        // plane words per tile row
+  static constexpr int ARR_CAP = CAP;          // arrival list capacity; a tile with more falls back to a direct pass
+  struct Row {
+    U4 road, head;
+    u32 my, mx;
+  };
+  struct Aux {
+    u32 calc, pref;
+  };
+  // shared memory of one tile of `rs` rows (all offsets in 32-bit words)
+  struct Smem {
+    u32 *base;
+    int rs;
+    FA_HD U4 *desc() const { return reinterpret_cast<U4 *>(base); }                       // [rs][TW]
+    FA_HD unsigned short *sect() const { return reinterpret_cast<unsigned short *>(base + (size_t)rs * TW * 4); }   // [rs*TW*4]
+    FA_HD u32 *arrl() const { return base + (size_t)rs * TW * 4 + (size_t)rs * TW * 2; }   // [ARR_CAP]
+    FA_HD u32 *cnt() const { return arrl() + ARR_CAP; }                                   // nsect, narr
+    static size_t bytes(int rs) { return ((size_t)rs * TW * 6 + ARR_CAP + 4) * 4; }
+  };
+  struct Env {
+    const GridView &g;
+    StripCol col;
+    int sx, lane, wi;   // strip column, lane, warp index inside the CTA
+    int ya;
+    int ylo, yhi;       // local rows that exist in the planes and lie inside the global grid
+    u32 *leak_plane;
+    Smem sm;
+  };
+  FA_HD static void load_row(const Env &E, int y, Row &q) {
+    const U4 z = {0, 0, 0, 0};
+    q.road = z; q.head = z; q.my = 0u; q.mx = 0u;
+    if (E.col.w_ok && y >= E.ylo && y < E.yhi) {
+      const u32 o = (u32)y * (u32)E.g.pitch + (u32)E.col.w;
+      q.road = E.g.road[o]; q.head = E.g.head_in[o];
+      const u64 m = E.g.mymx[o];
+      q.my = (u32)m; q.mx = (u32)(m >> 32);
+    }
+  }
+  FA_HD static void load_aux(const Env &E, int y, Aux &a) {
+    a.calc = 0u; a.pref = 0u;
+    if (E.col.owner && y < E.g.own1) {
+      const u32 o = (u32)y * (u32)E.g.pitch + (u32)E.col.w;
+      a.calc = E.g.calc[o]; a.pref = E.g.pref_in[o];
+    }
+  }
+  FA_HD static void prefetch_row(const Env &E, int y) {
+    if (E.col.w_ok && y >= E.ylo && y < E.yhi) {
+      const u32 o = (u32)y * (u32)E.g.pitch + (u32)E.col.w;
+      fa_prefetch_l2(&E.g.road[o]); fa_prefetch_l2(&E.g.head_in[o]);
+      if ((E.lane & 3) == 1) fa_prefetch_l2(&E.g.mymx[o]);
+      if ((E.lane & 7) == 1) { fa_prefetch_l2(&E.g.calc[o]); fa_prefetch_l2(&E.g.pref_in[o]); }
+    }
+  }
+  FA_HD static MRow side_row(const Row &q, bool diag) {
+    MRow m;
+    m.UYN = w3_c(q.road.x); m.UYS = w3_c(q.road.y); m.UXN = w3_c(q.road.z); m.UXS = w3_c(q.road.w);
+    m.DYN = w3_c(q.head.x); m.DYS = w3_c(q.head.y); m.DXN = w3_c(q.head.z); m.DXS = w3_c(q.head.w);
+    m.MY = w3_c(q.my); m.MX = w3_c(q.mx);
+    if (diag) {   // warp-uniform: a diagonal heading looks at the corner cells
+      m.UYN = simt_w3(q.road.x); m.UXN = simt_w3(q.road.z); m.MY = simt_w3(q.my); m.MX = simt_w3(q.mx);
+    }
+    return m;
+  }
+
+  // one owned row y: up / c / dn = rows y-1, y, y+1; ax = calc and pref of row y; live = false: a padding step past
+  // the strip's last row (warp-uniform), which must not store anything
+  FA_HD static void step(const Env &E, int y, bool live, const Row &up, const Row &c, const Row &dn, const Aux &ax, unsigned int &nleak) {
+    const GridView &g = E.g;
+    const StripCol &col = E.col;
+    const bool diag = simt_any((c.head.x & c.head.z) != 0u);
+    MRow mc;
+    mc.UYN = simt_w3(c.road.x); mc.UYS = w3_c(c.road.y); mc.UXN = simt_w3(c.road.z); mc.UXS = simt_w3(c.road.w);
+    mc.DYN = simt_w3(c.head.x); mc.DYS = simt_w3(c.head.y); mc.DXN = simt_w3(c.head.z); mc.DXS = simt_w3(c.head.w);
+    mc.MY = simt_w3(c.my); mc.MX = simt_w3(c.mx);
+    const MRow mu = side_row(up, diag), md = side_row(dn, diag);
+    Edge e;
+    const int yg = y + g.row0;
+    e.rowFirst = (yg == 0) ? 0xFFFFFFFFu : 0u;
+    e.rowLast = (yg == g.gh_global - 1) ? 0xFFFFFFFFu : 0u;
+    e.colFirst = col.colFirst; e.colLast = col.colLast; e.valid = col.colValid;   // y is an owned row: inside the grid
+    const MPre p = m_pre(mu, mc, md, e);
+    U4 d = {0u, 0u, 0u, 0u};
+    if (col.owner && live) {   // lanes 0 and SW+1 (and lanes past the planes) only feed their neighbours
+      const u32 o = (u32)y * (u32)g.pitch + (u32)col.w;
+      // RNG draws at forks (flowamok.fut:10-14) on the destination cell's own state (steppers.fut:103,112)
+      u32 CH = 0u;
+      const u32 fk = p.fork & e.valid;
+      if (fk) {
+        if (g.chooser == CHOOSE_X) CH = fk;
+        else if (g.chooser == CHOOSE_TAPE) CH = g.tape_bit ? fk : 0u;
+        else if (g.chooser == CHOOSE_RANDOM) {
+          u32 m = fk;
+          while (m) {
+            const int b = ffs32(m);
+            m &= m - 1;
+            const size_t ci = (size_t)o * 32 + b;
+            u64 st = g.rng[ci];
+            if (draw_choice01(st, g.rng_inc)) CH |= 1u << b;
+            g.rng[ci] = st;
+          }
+        }
+      }
+      const MOut out = m_post(p, CH);
+      // next_preference_flow_x (steppers.fut:41-50): decided by the fixpoint's own grants only; cells a ring
+      // resolution marked (steppers.fut:189-224) have calc = 0 and keep their preference
+      const UState f = {ax.calc, c.my & ax.calc, c.mx & ax.calc};
+      const UStatic dummy = {};
+      g.pref_out[o] = u_pref_next(c.road.x | c.road.z, ax.pref, f, dummy) & e.valid;
+      const U4 hd = {out.DYN, out.DYS, out.DXN, out.DXS};
+      g.head_out[o] = hd;
+      if (E.leak_plane) E.leak_plane[o] = out.leak;
+      nleak += (unsigned int)popc32(out.leak);
+      d.y = out.AY | out.AX;
+      d.x = d.y | c.head.x | c.head.z;
+      d.z = out.AY;
+      d.w = (out.AY & p.UYS) | (out.AX & p.UXS);
+    }
+    if (E.lane >= 1 && E.lane <= SW && live) E.sm.desc()[(size_t)(y - E.ya) * TW + E.wi * SW + (E.lane - 1)] = d;
+  }
+
+  // ---- phase A: rows [ya, yb) of strip column sx, by one warp; returns this lane's number of leaked cars.
+  // has_strip = false (warp-uniform): the CTA's tile is wider than the grid here; the warp only clears its descriptors.
+  FA_HD static unsigned int phaseA(const GridView &g, bool has_strip, int sx, int wi, int ya, int yb, int lane, u32 *leak_plane, Smem sm) {
+    if (!has_strip) {
+      const U4 z = {0u, 0u, 0u, 0u};
+      if (lane >= 1 && lane <= SW)
+        for (int r = 0; r < yb - ya; r++) sm.desc()[(size_t)r * TW + wi * SW + (lane - 1)] = z;
+      return 0u;
+    }
+    const int ylo = g.row0 < 0 ? -g.row0 : 0;
+    const int yhi = g.gh < g.gh_global - g.row0 ? g.gh : g.gh_global - g.row0;
+    const Env E = {g, strip_col<SW>(g, sx, lane), sx, lane, wi, ya, ylo, yhi, leak_plane, sm};
+    unsigned int nleak = 0;
+    // Slots rotate with period 4: at the start of step y, R0/R1/R2 hold rows y-1, y, y+1 and R3 is loaded with row y+2
+    Row R0, R1, R2, R3;
+    Aux X0, X1;
+    load_row(E, ya - 1, R0); load_row(E, ya, R1); load_row(E, ya + 1, R2);
+    load_aux(E, ya, X0);
+    constexpr int AHEAD = 6;   // rows between the L2 prefetch and the register load of a row
+    for (int y = ya + 2; y < ya + 2 + AHEAD && y <= yb; y++) prefetch_row(E, y);
+    // the last trip may run up to three rows past yb: those steps compute but store nothing (live = false)
+    for (int y = ya; y < yb; y += 4) {
+      load_row(E, y + 2, R3); load_aux(E, y + 1, X1); if (y + 2 + AHEAD <= yb) prefetch_row(E, y + 2 + AHEAD);
+      step(E, y, true, R0, R1, R2, X0, nleak);
+      load_row(E, y + 3, R0); load_aux(E, y + 2, X0); if (y + 3 + AHEAD <= yb) prefetch_row(E, y + 3 + AHEAD);
+      step(E, y + 1, y + 1 < yb, R1, R2, R3, X1, nleak);
+      load_row(E, y + 4, R1); load_aux(E, y + 3, X1); if (y + 4 + AHEAD <= yb) prefetch_row(E, y + 4 + AHEAD);
+      step(E, y + 2, y + 2 < yb, R2, R3, R0, X0, nleak);
+      load_row(E, y + 5, R2); load_aux(E, y + 4, X0); if (y + 5 + AHEAD <= yb) prefetch_row(E, y + 5 + AHEAD);
+      step(E, y + 3, y + 3 < yb, R3, R0, R1, X1, nleak);
+    }
+    return nleak;
+  }
+
+  // ---- phase B.  tsx = first strip column of the tile, rows = yb - ya; tid in [0, nt).  Block barriers separate
+  // clear | A | B0 | B1 | B2 (the caller places them).
+  FA_HD static void phaseB_clear(Smem sm, int tid) {
+    if (tid < 2) sm.cnt()[tid] = 0u;
+  }
+  // arrival list entry: row (10 bits) | cell inside the tile row (17 bits) | vertical (1) | plus side (1)
+  FA_HD static u32 arr_entry(int row, int wd, int b, const U4 &d) {
+    const u32 bit = 1u << b;
+    return ((u32)row << 19) | ((u32)(wd * 32 + b) << 2) | ((d.z & bit) ? 2u : 0u) | ((d.w & bit) ? 1u : 0u);
+  }
+  FA_HD static void patch(const GridView &g, int tsx, int ya, u32 en) {
+    const size_t cpitch = (size_t)g.pitch * 32;
+    const size_t dst = ((size_t)(ya + (int)(en >> 19)) * g.pitch + (size_t)tsx * SW) * 32 + ((en >> 2) & 0x1FFFFu);
+    size_t src = dst;
+    if (en & 2u) src = (en & 1u) ? dst + cpitch : dst - cpitch;
+    else src = (en & 1u) ? dst + 1 : dst - 1;
+    g.color_out[dst] = g.color_in[src];
+  }
+  FA_HD static void phaseB0(Smem sm, int rows, int tid, int nt) {
+    const U4 *desc = sm.desc();
+    unsigned short *sect = sm.sect();
+    u32 *arrl = sm.arrl();
+    for (int idx = tid; idx < rows * TW; idx += nt) {
+      const U4 d = desc[idx];
+      if (d.x == 0u) continue;
+      const int row = idx / TW, wd = idx - row * TW;
+      u32 smk = 0u;
+      for (int k = 0; k < 4; k++) smk |= ((d.x >> (8 * k)) & 0xFFu) ? (1u << k) : 0u;
+      u32 at = FA_ATOMIC_ADD_U32(&sm.cnt()[0], (u32)popc32(smk));
+      for (int k = 0; k < 4; k++)
+        if (smk & (1u << k)) sect[at++] = (unsigned short)(row * (TW * 4) + wd * 4 + k);
+      if (d.y) {
+        u32 aa = FA_ATOMIC_ADD_U32(&sm.cnt()[1], (u32)popc32(d.y));
+        u32 m = d.y;
+        while (m) {
+          const int b = ffs32(m);
+          m &= m - 1;
+          if (aa < (u32)ARR_CAP) arrl[aa] = arr_entry(row, wd, b, d);
+          aa++;
+        }
+      }
+    }
+  }
+  // copy the listed sectors: thread pair (2p, 2p+1) moves the two 16-byte halves of sector entries p, p + nt/2, ...
+  FA_HD static void phaseB1(const GridView &g, Smem sm, int tsx, int ya, int tid, int nt) {
+    const unsigned short *sect = sm.sect();
+    const int ns = (int)sm.cnt()[0], half = tid & 1, np = nt >> 1;
+    constexpr int UN = 8;
+    for (int e0 = tid >> 1; e0 < ns; e0 += np * UN) {
+      U4 v[UN];
+      size_t off[UN];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int k = 0; k < UN; k++) {
+        const int e = e0 + k * np;
+        if (e < ns) {
+          const int id = sect[e], row = id / (TW * 4), sc = id - row * (TW * 4);
+          off[k] = ((size_t)(ya + row) * g.pitch + (size_t)tsx * SW) * 32 + (size_t)sc * 8 + half * 4;
+          v[k] = *reinterpret_cast<const U4 *>(g.color_in + off[k]);
+        }
+      }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int k = 0; k < UN; k++)
+        if (e0 + k * np < ns) *reinterpret_cast<U4 *>(g.color_out + off[k]) = v[k];
+    }
+  }
+  // every arrival cell takes the predecessor's colour (steppers.fut:109)
+  FA_HD static void phaseB2(const GridView &g, Smem sm, int tsx, int ya, int rows, int tid, int nt) {
+    const int na = (int)sm.cnt()[1];
+    if (na <= ARR_CAP) {
+      const u32 *arrl = sm.arrl();
+      for (int a = tid; a < na; a += nt) patch(g, tsx, ya, arrl[a]);
+    } else {   // more arrivals than the list holds (a jam dissolving everywhere at once): straight from the descriptors
+      const U4 *desc = sm.desc();
+      for (int idx = tid; idx < rows * TW; idx += nt) {
+        const U4 d = desc[idx];
+        const int row = idx / TW, wd = idx - row * TW;
+        u32 m = d.y;
+        while (m) {
+          const int b = ffs32(m);
+          m &= m - 1;
+          patch(g, tsx, ya, arr_entry(row, wd, b, d));
+        }
+      }
+    }
+  }
+};
+
+}  // namespace fa

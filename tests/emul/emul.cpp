@@ -1,16 +1,18 @@
-// CPU emulation of the CUDA tile programs (TEST INFRASTRUCTURE).
+// CPU emulation of the CUDA kernels' programs (TEST INFRASTRUCTURE).
 //
-// Compiles flowamok_b200/csrc/fa_tiles.h for the host and runs the very same phase functions the
-// kernels run, with a loop over "thread ids" in place of a thread block, the same frontier worklist
-// discipline as k_u_init / k_u_iter, and the same row-band protocol as the flowamok_band_* calls of
-// fa_api.cu.  tests/test_emul.py and tests/test_bands_cpu.py compare it with the oracle.  It is never
-// part of the product library.
+// Compiles flowamok_b200/csrc/fa_stream.h and fa_tiles.h for the host and runs the very same functions the
+// kernels run: the warp strip programs of k_u_local / k_move with the 32 lanes of a warp as coroutines
+// (simt_host.h), the frontier visit of k_u_iter with a loop over the list, and the same row-band protocol
+// as the flowamok_band_* calls of fa_api.cu.  tests/test_emul.py and tests/test_bands_cpu.py compare it
+// with the oracle.  It is never part of the product library.
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
-#include "../../flowamok_b200/csrc/fa_tiles.h"
+#include "../../flowamok_b200/csrc/fa_stream.h"
+#include "simt_host.h"
 
 using namespace fa;
 
@@ -67,40 +69,27 @@ GridView view(HostGrid *h, int chooser, u32 tape_bit) {
   return g;
 }
 
-// k_u_init: one "block" per UIT tile, NT threads emulated in lock step
-template <class UIT>
-void u_init(HostGrid *h, const GridView &g) {
-  h->table.clear(); h->frontier.clear();
-  typename UIT::Smem *sm = new typename UIT::Smem();
-  std::vector<typename UIT::Own> own(UIT::NT);
-  std::vector<typename UIT::Raw> rawo(UIT::NT), rawr(UIT::NT);
-  std::vector<UState> nn(UIT::NT);
-  int nty = (h->own1 - h->own0 + UIT::TR - 1) / UIT::TR, ntx = (h->pitch + UIT::TW - 1) / UIT::TW;
-  for (int ty = 0; ty < nty; ty++)
-    for (int tx = 0; tx < ntx; tx++) {
-      UIT tile(g, *sm, ty, tx);
-      for (int t = 0; t < UIT::NT; t++) tile.p0(t, rawo[t], rawr[t]);
-      for (int t = 0; t < UIT::NT; t++) tile.pA(t, rawo[t], rawr[t], own[t]);
-      bool converged = false;
-      for (int k = 0; k < UIT::NS; k++) {
-        bool any = false;
-        for (int t = 0; t < UIT::NT; t++) any |= tile.sweep_compute(own[t], nn[t]);
-        if (!any) { converged = true; break; }
-        for (int t = 0; t < UIT::NT; t++) tile.sweep_commit(own[t], nn[t]);
-      }
-      for (int t = 0; t < UIT::NT; t++) {
-        UEntry e;
-        int kind = tile.pC(t, own[t], converged, e);
-        if (g.gh != g.gh_global) tile.ghost_publish(t);
-        if (kind >= 1) {
-          u32 pos = (u32)h->table.size();
-          h->table.push_back(e);
-          g.ustate[e.wi] = kind == 2 ? (pos | U_QUEUED) : pos;
-          if (kind == 2) h->frontier.push_back(pos);
-        } else if (own[t].in) g.ustate[(size_t)own[t].y * h->pitch + own[t].w] = U_NONE;
-      }
+// k_u_local: one warp (32 coroutines) per strip
+template <int SW, int K>
+struct UArgs { HostGrid *h; const GridView *g; int sx, ya, yb; unsigned int qn; std::vector<u32> *ql, *qs; };
+template <int SW, int K>
+void u_lane(void *p, int lane) {
+  UArgs<SW, K> *a = (UArgs<SW, K> *)p;
+  UStrip<SW, K>::run(*a->g, a->sx, a->ya, a->yb, lane, a->h->table.data(), a->qs->data(), a->ql->data(), &a->qn);
+}
+template <int SW, int K>
+void u_init(HostGrid *h, const GridView &g, int rs) {
+  const size_t nw = (size_t)h->gh * h->pitch;
+  h->table.resize(nw);
+  h->frontier.clear();
+  std::vector<u32> ql(nw), qs((size_t)SW * rs);
+  const int nsx = (h->pitch + SW - 1) / SW, nsy = (h->own1 - h->own0 + rs - 1) / rs;
+  for (int sy = 0; sy < nsy; sy++)
+    for (int sx = 0; sx < nsx; sx++) {
+      UArgs<SW, K> a = {h, &g, sx, h->own0 + sy * rs, std::min(h->own1, h->own0 + (sy + 1) * rs), 0u, &ql, &qs};
+      simt_host::run_warp(u_lane<SW, K>, &a);
+      for (unsigned k = 0; k < a.qn; k++) h->frontier.push_back(ql[k]);
     }
-  delete sm;
 }
 
 // k_u_iter: frontier iterations until nothing is queued; `order` varies the visiting order
@@ -146,38 +135,55 @@ void do_rings(HostGrid *h, const GridView &g) {  // steppers.fut:189-224, sparse
       }
 }
 
-template <class MT>
-int64_t do_move(HostGrid *h, const GridView &g, int nt) {
+template <int SW, int NW, int CAP>
+struct MArgs { const GridView *g; bool has; int sx, wi, ya, yb; typename MTile<SW, NW, CAP>::Smem sm; unsigned int leaks[32]; };
+template <int SW, int NW, int CAP>
+void m_lane(void *p, int lane) {
+  MArgs<SW, NW, CAP> *a = (MArgs<SW, NW, CAP> *)p;
+  a->leaks[lane] = MTile<SW, NW, CAP>::phaseA(*a->g, a->has, a->sx, a->wi, a->ya, a->yb, lane, nullptr, a->sm);
+}
+// k_move: one "CTA" per tile: phase A warp by warp (coroutines), phase B with a loop over the thread ids
+template <int SW, int NW, int CAP>
+int64_t do_move(HostGrid *h, const GridView &g, int rs, int nt) {
+  typedef MTile<SW, NW, CAP> MTL;
   int64_t leaks = 0;
-  int mty = (h->own1 - h->own0 + MT::TR - 1) / MT::TR, mtx = (h->pitch + MT::TW - 1) / MT::TW;
-  typename MT::Smem *sm = new typename MT::Smem();
-  for (int ty = 0; ty < mty; ty++)
-    for (int tx = 0; tx < mtx; tx++) {
-      MT t(g, *sm, ty, tx);
-      for (int tid = 0; tid < nt; tid++) t.p0(tid, nt);
-      for (int tid = 0; tid < nt; tid++) t.p1(tid, nt);
-      for (int tid = 0; tid < nt; tid++) t.p2(tid, nt);
-      leaks += sm->leaks;
+  const int nsx = (h->pitch + SW - 1) / SW, ntx = (nsx + NW - 1) / NW, nty = (h->own1 - h->own0 + rs - 1) / rs;
+  std::vector<u32> smem(MTL::Smem::bytes(rs) / 4 + 4);
+  u32 *base = (u32 *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
+  for (int ty = 0; ty < nty; ty++)
+    for (int tx = 0; tx < ntx; tx++) {
+      const typename MTL::Smem sm = {base, rs};
+      const int ya = h->own0 + ty * rs, yb = std::min(h->own1, ya + rs);
+      std::fill(smem.begin(), smem.end(), 0xDEADBEEFu);   // shared memory starts undefined
+      for (int tid = 0; tid < nt; tid++) MTL::phaseB_clear(sm, tid);
+      for (int wi = 0; wi < NW; wi++) {
+        MArgs<SW, NW, CAP> a = {&g, tx * NW + wi < nsx, tx * NW + wi, wi, ya, yb, sm, {}};
+        simt_host::run_warp(m_lane<SW, NW, CAP>, &a);
+        for (int l = 0; l < 32; l++) leaks += a.leaks[l];
+      }
+      for (int tid = 0; tid < nt; tid++) MTL::phaseB0(sm, yb - ya, tid, nt);
+      for (int tid = 0; tid < nt; tid++) MTL::phaseB1(g, sm, tx * NW, ya, tid, nt);
+      for (int tid = 0; tid < nt; tid++) MTL::phaseB2(g, sm, tx * NW, ya, yb - ya, tid, nt);
     }
-  delete sm;
   h->cur ^= 1;
   return leaks;
 }
 
-// variant: 0 = production tile shapes, 1 = tiny tiles + reversed frontier order, 2 = odd tiles + scrambled order
+// variant: 0 = production strip shape, 1 = narrow strips / short rows + reversed frontier order,
+//          2 = odd strip shape + scrambled order
 void v_u_init(HostGrid *h, const GridView &g) {
   switch (h->variant) {
-  case 1: u_init<UInitTile<2, 1>>(h, g); break;
-  case 2: u_init<UInitTile<5, 3>>(h, g); break;
-  default: u_init<UInitTile<16, 32>>(h, g); break;
+  case 1: u_init<1, 1>(h, g, 2); break;
+  case 2: u_init<3, 2>(h, g, 5); break;
+  default: u_init<30, 3>(h, g, 32); break;
   }
 }
 int v_order(const HostGrid *h) { return h->variant == 1 ? 2 : h->variant == 2 ? 1 : 0; }
-int64_t v_move(HostGrid *h, const GridView &g, int nt) {
+int64_t v_move(HostGrid *h, const GridView &g, int) {
   switch (h->variant) {
-  case 1: return do_move<MTile<3, 1>>(h, g, nt);
-  case 2: return do_move<MTile<4, 2>>(h, g, nt);
-  default: return do_move<MTile<8, 32>>(h, g, nt);
+  case 1: return do_move<2, 3, 8>(h, g, 3, 6);      // tiny arrival list: the overflow path runs
+  case 2: return do_move<5, 2, 64>(h, g, 4, 64);
+  default: return do_move<30, 4, 2048>(h, g, 16, 128);
   }
 }
 
@@ -216,6 +222,7 @@ void emul_upload(void *p, const int8_t *uy, const int8_t *ux, const int8_t *dy, 
     }
   }
   h->rng_inc = rng_inc;
+  h->color[h->cur ^ 1] = h->color[h->cur];   // lazy double buffer: both identical
 }
 
 // writes the OWNED rows into whole-grid arrays

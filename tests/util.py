@@ -92,7 +92,8 @@ def emul_lib():
     global _emul
     if _emul is not None:
         return _emul
-    deps = [_EMUL_SRC, ROOT / "flowamok_b200/csrc/fa_tiles.h", ROOT / "flowamok_b200/csrc/fa_bits.h"]
+    deps = [_EMUL_SRC, ROOT / "tests/emul/simt_host.h"] + [ROOT / "flowamok_b200/csrc" / f
+                                                         for f in ("fa_tiles.h", "fa_bits.h", "fa_stream.h", "fa_simt.h")]
     if not _EMUL_SO.exists() or any(d.stat().st_mtime > _EMUL_SO.stat().st_mtime for d in deps):
         _EMUL_SO.parent.mkdir(parents=True, exist_ok=True)
         cxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
