@@ -234,7 +234,7 @@ static int grid_new_impl(flowamok_context *ctx, flowamok_grid **out, int64_t gh_
   const int owned = g->own1 - g->own0;
   g->rs = strip_rows(ctx, owned, g->pitch);
   g->nsx = (g->pitch + STRIP_W - 1) / STRIP_W; g->nsy = (owned + g->rs - 1) / g->rs;
-  g->rs_m = 16;   // k_move tile rows: 54 KB of shared memory per CTA (descriptors + lists), 4 CTAs per SM
+  g->rs_m = 8;    // k_move tile rows: 31 KB of shared memory per CTA (descriptors + lists)
   if (const char *e = getenv("FLOWAMOK_MOVE_ROWS")) { int v = atoi(e); if (v >= 1 && v <= 128) g->rs_m = v; }
   while (g->rs_m > 1 && MTL::Smem::bytes(g->rs_m) > ctx->smem_optin) g->rs_m--;
   g->mtx = (g->nsx + M_WARPS - 1) / M_WARPS; g->mty = (owned + g->rs_m - 1) / g->rs_m;

@@ -15,6 +15,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "fa_stream.h"
 #include "fa_tiles.h"
 
@@ -23,13 +25,13 @@ namespace fa {
 constexpr int STRIP_W = 30;                // owned plane words per strip (lanes 0 and 31 carry the neighbours)
 constexpr int STRIP_THREADS = 128;         // k_u_local / k_move block: 4 warps = 4 strips side by side
 #ifndef FA_U_LEVELS
-#define FA_U_LEVELS 3                      // Jacobi levels k_u_local resolves in registers (queues of <= 3 cars)
+#define FA_U_LEVELS 2                      // Jacobi levels k_u_local resolves in registers (queues of <= 2 cars)
 #endif
 #ifndef FA_U_MINB
-#define FA_U_MINB 1                        // resident CTAs per SM the register allocation of k_u_local aims for
+#define FA_U_MINB 4                        // resident CTAs per SM the register allocation of k_u_local aims for
 #endif
 #ifndef FA_M_MINB
-#define FA_M_MINB 1                        // the same for k_move
+#define FA_M_MINB 5                        // the same for k_move
 #endif
 constexpr int UIT_THREADS = 512;           // k_u_iter block
 
@@ -96,7 +98,14 @@ __device__ __forceinline__ bool grid_barrier(IterState *is, unsigned int nblocks
 // frontier k_u_local appended to qlist0) and appends the words it wakes to the other list, warp-aggregated with one
 // global atomic per warp and push slot.  Ends when an iteration produces an empty list.
 // ---------------------------------------------------------------------------------------------
-constexpr unsigned int UIT_TAIL = 512;    // frontier length below which CTA 0 finishes the fixpoint alone
+#ifndef FA_UIT_TAIL
+#define FA_UIT_TAIL 512
+#endif
+constexpr unsigned int UIT_TAIL = FA_UIT_TAIL;   // frontier length below which CTA 0 finishes the fixpoint alone
+#ifndef FA_UIT_CHASE
+#define FA_UIT_CHASE 0
+#endif
+constexpr int UIT_CHASE = FA_UIT_CHASE;   // links of a waiting queue one visit follows before it hands over to the list
 
 // first_it = 0: start from the frontier k_u_local left in qlist0 / qn[0]; 1: resume from qlist1 / qn[1] (band merge)
 __global__ void __launch_bounds__(UIT_THREADS, 2)
@@ -107,25 +116,37 @@ k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *
   unsigned int *ql[2] = {qlist0, qlist1};
   unsigned long long relaxed = 0;
 
-  // visit entry `idx` (if `has`) and append what it wakes to dst: warp-aggregated, one global atomic per warp and
-  // push slot -- no block barrier anywhere in a visit
-  auto visit_and_flush = [&](bool has, unsigned int idx, unsigned int *dst, unsigned int *out_cnt) {
-    unsigned int push[9];
-    int np = 0;
-    if (has) {
-      const UEntry e = table[idx];
-      np = u_iter_entry(g, e, idx, push);
-    }
+  // Visit entry `idx` (if `has`) and CHASE the chain of waiting cars behind it: of the words the visit wakes, the
+  // thread keeps the first for itself and visits it at once (it has claimed it: QUEUED is set), the others are
+  // appended to dst, warp-aggregated with one global atomic per warp and push slot.  A queue of cars thus resolves
+  // in one iteration, link by link, instead of one grid-wide iteration per car.  No block barrier anywhere.
+  auto visit_and_flush = [&](auto cta_scope, bool has, unsigned int idx, unsigned int *dst, unsigned int *out_cnt) {
+    for (int hop = 0; __any_sync(0xFFFFFFFFu, has); hop++) {
+      unsigned int push[9];
+      int np = 0;
+      if (has) {
+        const UEntry e = table[idx];
+        np = u_iter_entry<decltype(cta_scope)::value>(g, e, idx, push);
+        relaxed++;
+      }
+      has = np > 0 && hop < UIT_CHASE;
+      if (has) {   // keep the first woken word: shift the rest down
+        idx = push[0];
 #pragma unroll
-    for (int j = 0; j < 9; j++) {
-      const bool p = j < np;
-      const unsigned m = __ballot_sync(0xFFFFFFFFu, p);
-      if (m) {
-        const int leader = __ffs(m) - 1;
-        unsigned bs = 0;
-        if (lane == leader) bs = atomicAdd(out_cnt, (unsigned)__popc(m));
-        bs = __shfl_sync(0xFFFFFFFFu, bs, leader);
-        if (p) dst[bs + __popc(m & ((1u << lane) - 1u))] = push[j];
+        for (int j = 0; j < 8; j++) push[j] = push[j + 1];
+        np--;
+      }
+#pragma unroll
+      for (int j = 0; j < 9; j++) {
+        const bool p = j < np;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, p);
+        if (m) {
+          const int leader = __ffs(m) - 1;
+          unsigned bs = 0;
+          if (lane == leader) bs = atomicAdd(out_cnt, (unsigned)__popc(m));
+          bs = __shfl_sync(0xFFFFFFFFu, bs, leader);
+          if (p) dst[bs + __popc(m & ((1u << lane) - 1u))] = push[j];
+        }
       }
     }
   };
@@ -147,11 +168,20 @@ k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *
     const unsigned int stride = tail ? (unsigned)nt : (unsigned)nb * nt;
     for (unsigned int k0 = tail ? 0u : (unsigned)b * nt; k0 < n; k0 += stride) {
       const unsigned int k = k0 + tid;
-      visit_and_flush(k < n, k < n ? src[k] : 0u, dst, out_cnt);
-      relaxed += min((unsigned)nt, n - k0);
+      if (tail) visit_and_flush(std::true_type(), k < n, k < n ? src[k] : 0u, dst, out_cnt);
+      else visit_and_flush(std::false_type(), k < n, k < n ? src[k] : 0u, dst, out_cnt);
     }
     if (tail) { __threadfence(); __syncthreads(); }
     else if (!grid_barrier(is, nb)) return;
+  }
+  {   // visits of this CTA: warp sums, then one shared and one global atomic
+    __shared__ unsigned long long cta_relaxed;
+    if (tid == 0) cta_relaxed = 0ull;
+    __syncthreads();
+    unsigned int r32 = __reduce_add_sync(0xFFFFFFFFu, (unsigned int)relaxed);
+    if (lane == 0 && r32) atomicAdd(&cta_relaxed, (unsigned long long)r32);
+    __syncthreads();
+    relaxed = cta_relaxed;
   }
   if (tid == 0) {
     if (relaxed) atomicAdd(&diag->sweeps, relaxed);

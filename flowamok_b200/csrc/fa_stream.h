@@ -429,12 +429,15 @@ struct MTile {
     const u32 bit = 1u << b;
     return ((u32)row << 19) | ((u32)(wd * 32 + b) << 2) | ((d.z & bit) ? 2u : 0u) | ((d.w & bit) ? 1u : 0u);
   }
-  FA_HD static void patch(const GridView &g, int tsx, int ya, u32 en) {
+  FA_HD static void patch_addr(const GridView &g, int tsx, int ya, u32 en, size_t &dst, size_t &src) {
     const size_t cpitch = (size_t)g.pitch * 32;
-    const size_t dst = ((size_t)(ya + (int)(en >> 19)) * g.pitch + (size_t)tsx * SW) * 32 + ((en >> 2) & 0x1FFFFu);
-    size_t src = dst;
+    dst = ((size_t)(ya + (int)(en >> 19)) * g.pitch + (size_t)tsx * SW) * 32 + ((en >> 2) & 0x1FFFFu);
     if (en & 2u) src = (en & 1u) ? dst + cpitch : dst - cpitch;
     else src = (en & 1u) ? dst + 1 : dst - 1;
+  }
+  FA_HD static void patch(const GridView &g, int tsx, int ya, u32 en) {
+    size_t dst, src;
+    patch_addr(g, tsx, ya, en, dst, src);
     g.color_out[dst] = g.color_in[src];
   }
   FA_HD static void phaseB0(Smem sm, int rows, int tid, int nt) {
@@ -493,7 +496,25 @@ struct MTile {
     const int na = (int)sm.cnt()[1];
     if (na <= ARR_CAP) {
       const u32 *arrl = sm.arrl();
-      for (int a = tid; a < na; a += nt) patch(g, tsx, ya, arrl[a]);
+      constexpr int UN = 8;   // independent gathers in flight per thread
+      for (int a0 = tid; a0 < na; a0 += nt * UN) {
+        u32 v[UN];
+        size_t dst[UN];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < UN; k++)
+          if (a0 + k * nt < na) {
+            size_t src;
+            patch_addr(g, tsx, ya, arrl[a0 + k * nt], dst[k], src);
+            v[k] = g.color_in[src];
+          }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < UN; k++)
+          if (a0 + k * nt < na) g.color_out[dst[k]] = v[k];
+      }
     } else {   // more arrivals than the list holds (a jam dissolving everywhere at once): straight from the descriptors
       const U4 *desc = sm.desc();
       for (int idx = tid; idx < rows * TW; idx += nt) {

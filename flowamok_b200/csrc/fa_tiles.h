@@ -96,11 +96,16 @@ FA_HD int ffs32(u32 v) {  // index of lowest set bit, v != 0
 //  makes any relaxation order reach the reference's Jacobi result.  A word's state is
 // published my/mx first, calc last, and read calc first: whoever sees calc = 1 sees the final my/mx.
 // =============================================================================================
-FA_HD void fa_fence_device() {
+// CTA = true: every thread that touches the fixpoint planes right now belongs to this CTA (the single-CTA tail of
+// k_u_iter), so a block-scope fence is enough -- it costs a fraction of the device-scope one (no L1 invalidation)
+template <bool CTA>
+FA_HD void fa_fence() {
 #if defined(__CUDA_ARCH__)
-  __threadfence();
+  if (CTA) __threadfence_block();
+  else __threadfence();
 #endif
 }
+FA_HD void fa_fence_device() { fa_fence<false>(); }
 FA_HD u64 pack_mymx(u32 my, u32 mx) { return (u64)my | ((u64)mx << 32); }
 
 constexpr u32 U_NONE = 0xFFFFFFFFu;    // word has no unresolved waiting car
@@ -156,15 +161,19 @@ FA_HD u32 u_try_queue(const GridView &g, int y, int w) {
 
 // One relaxation of worklist entry `e` against the current planes (frontier discipline):
 //   clear QUEUED, re-read the neighbourhood, OR the new facts in (my/mx before calc);
-//   if anything changed, wake the eight neighbouring words (their waiting cars may point here)
-//   and this word itself while it still holds an uncalculated link cell;
+//   if anything changed, wake the neighbouring words whose waiting cars may point at a changed cell (the words above
+//   and below; the words to the left / right and the corner words only if the changed cell is the word's first /
+//   last one) and this word itself while it still holds an uncalculated link cell;
 //   a word nobody changes is left dormant -- cars queued behind a full ring cost one visit per tick.
+// The memory operations are grouped so that independent round trips to L2 overlap: a visit is a chain of about eight
+// of them, and the fixpoint's tail is bound by exactly that latency.
 // push[] receives up to 9 entry indices for the next list; returns their number.
+template <bool CTA = false>
 FA_HD int u_iter_entry(const GridView &g, const UEntry &e, u32 idx, u32 *push) {
-  int y = (int)(e.wi / (u32)g.pitch), w = (int)(e.wi - (u32)y * (u32)g.pitch);
+  const int y = (int)(e.wi / (u32)g.pitch), w = (int)(e.wi - (u32)y * (u32)g.pitch);
+  const U4 hd = g.head_in[e.wi];   // static during the fixpoint: no ordering needed
   FA_ATOMIC_AND_U32(&g.ustate[e.wi], ~U_QUEUED);
-  fa_fence_device();
-  U4 hd = g.head_in[e.wi];
+  fa_fence<CTA>();
   Heading h = heading(hd.x, hd.y, hd.z, hd.w);
   UStatic st;
   u32 link = ~e.T;
@@ -186,7 +195,7 @@ FA_HD int u_iter_entry(const GridView &g, const UEntry &e, u32 idx, u32 *push) {
     ok[k] = false; off[k] = 0;
     if (need[k]) { off[k] = u_off(g, y + k / 3 - 1, w + k % 3 - 1, ok[k]); nb[k].R = u_ld_calc(g, off[k], ok[k]); }
   }
-  fa_fence_device();
+  fa_fence<CTA>();
   for (int k = 0; k < 9; k++)
     if (need[k]) u_ld_mymx(g, off[k], ok[k], nb[k]);
   const UPlanes &ul = nb[0], &up = nb[1], &ur = nb[2], &l = nb[3], &c = nb[4], &r = nb[5], &dl = nb[6], &dn = nb[7], &dr = nb[8];
@@ -196,20 +205,36 @@ FA_HD int u_iter_entry(const GridView &g, const UEntry &e, u32 idx, u32 *push) {
   const u32 valid = edge_of(g, y, w).valid;
   UState n = u_relax(st, R_up, R_c, R_dn, MY_up, MY_dn, MX_c, MX_up, MX_dn);
   n.R = (n.R & valid) | c.R; n.MY = (n.MY & valid) | c.MY; n.MX = (n.MX & valid) | c.MX;   // monotone
-  bool changed = n.R != c.R || n.MY != c.MY || n.MX != c.MX;
+  const u32 chg = (n.R ^ c.R) | (n.MY ^ c.MY) | (n.MX ^ c.MX);
   bool unready = (~n.R & ~e.T) != 0u;
   int np = 0;
-  if (changed) {
+  if (chg) {
     FA_ATOMIC_OR_U64(&g.mymx[e.wi], pack_mymx(n.MY, n.MX));
-    fa_fence_device();
+    fa_fence<CTA>();
     FA_ATOMIC_OR_U32(&g.calc[e.wi], n.R);
-    fa_fence_device();
-    for (int dy = -1; dy <= 1; dy++)
-      for (int dx = -1; dx <= 1; dx++) {
-        if (dy == 0 && dx == 0 && !unready) continue;
-        u32 q = u_try_queue(g, y + dy, w + dx);
-        if (q != U_NONE) push[np++] = q & ~U_QUEUED;
+    fa_fence<CTA>();
+    // whom to wake: k = 3 * (dy + 1) + (dx + 1)
+    const bool first = (chg & 1u) != 0u, last = (chg >> 31) != 0u;
+    bool cand[9] = {first, true, last, first, unready, last, first, true, last};
+    u32 sv[9];
+    for (int k = 0; k < 9; k++) {
+      const int yy = y + k / 3 - 1, ww = w + k % 3 - 1;
+      cand[k] = cand[k] && yy >= g.own0 && yy < g.own1 && ww >= 0 && ww < g.pitch;   // only owned words have entries
+      sv[k] = U_NONE;
+      if (cand[k]) {
+#if defined(__CUDA_ARCH__)
+        sv[k] = *(volatile const u32 *)&g.ustate[(size_t)yy * g.pitch + ww];
+#else
+        sv[k] = g.ustate[(size_t)yy * g.pitch + ww];
+#endif
       }
+    }
+    for (int k = 0; k < 9; k++) {   // claim: whoever flips QUEUED from 0 to 1 puts the word on the list
+      cand[k] = cand[k] && sv[k] != U_NONE && !(sv[k] & U_QUEUED);
+      if (cand[k]) sv[k] = FA_ATOMIC_OR_U32(&g.ustate[(size_t)(y + k / 3 - 1) * g.pitch + (w + k % 3 - 1)], U_QUEUED);
+    }
+    for (int k = 0; k < 9; k++)
+      if (cand[k] && sv[k] != U_NONE && !(sv[k] & U_QUEUED)) push[np++] = sv[k];
   }
   // resolved for good: retire the word -- with a CAS, because a neighbour may be queueing it right now (then it
   // stays queued, gets one idle visit next iteration and is retired there)
