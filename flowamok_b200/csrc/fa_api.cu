@@ -116,14 +116,14 @@ static int fail(flowamok_context *ctx, const char *fmt, ...) {
   } while (0)
 
 static inline unsigned int nblk(long long n, int b) { return (unsigned int)((n + b - 1) / b); }
-// rows per strip: long strips amortise the halo rows every strip re-reads, but there must be enough strips (warps)
-// to fill the machine several times over.  FLOWAMOK_STRIP_ROWS overrides (tuning).
+// rows per k_u_local strip: long strips amortise the 2K+3 pipeline-fill rows every strip pays, but there must be
+// enough strips (warps) to occupy every SM.  FLOWAMOK_STRIP_ROWS overrides (tuning).
 static int strip_rows(const flowamok_context *ctx, int owned_rows, int pitch) {
   if (const char *e = getenv("FLOWAMOK_STRIP_ROWS")) { int v = atoi(e); if (v >= 1) return v; }
   const long long nsx = (pitch + STRIP_W - 1) / STRIP_W;
-  const long long want = (long long)ctx->num_sms * 16 * 4;   // warps: 4 waves of 16 resident warps per SM
-  int rs = 64;
-  while (rs > 8 && nsx * ((owned_rows + rs - 1) / rs) < want) rs >>= 1;
+  const long long want = (long long)ctx->num_sms * 12;   // about the number of resident warps per SM
+  int rs = 128;
+  while (rs > 16 && nsx * ((owned_rows + rs - 1) / rs) < want) rs >>= 1;
   return rs;
 }
 struct flowamok_grid;
@@ -642,8 +642,11 @@ static GridView make_view(flowamok_grid *g) {
 }
 
 static int launch_u_init(flowamok_context *ctx, flowamok_grid *g, const GridView &v) {
-  k_u_local<<<nblk((long long)g->nsx * g->nsy, STRIP_THREADS / 32), STRIP_THREADS, 0, ctx->stream>>>(v, g->nsx, g->nsy, g->rs, g->table,
-                                                                                                    g->qlist[0], g->qlist[1], g->is);
+  const unsigned int nb = nblk((long long)g->nsx * g->nsy, STRIP_THREADS / 32);
+  if (g->gh != g->gh_global)   // a row band: ghost rows, boundary rows always on the frontier
+    k_u_local<true><<<nb, STRIP_THREADS, 0, ctx->stream>>>(v, g->nsx, g->nsy, g->rs, g->table, g->qlist[0], g->qlist[1], g->is);
+  else
+    k_u_local<false><<<nb, STRIP_THREADS, 0, ctx->stream>>>(v, g->nsx, g->nsy, g->rs, g->table, g->qlist[0], g->qlist[1], g->is);
   KCHECK("k_u_local");
   return 0;
 }

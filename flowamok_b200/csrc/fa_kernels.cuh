@@ -25,7 +25,7 @@ namespace fa {
 constexpr int STRIP_W = 30;                // owned plane words per strip (lanes 0 and 31 carry the neighbours)
 constexpr int STRIP_THREADS = 128;         // k_u_local / k_move block: 4 warps = 4 strips side by side
 #ifndef FA_U_LEVELS
-#define FA_U_LEVELS 2                      // Jacobi levels k_u_local resolves in registers (queues of <= 2 cars)
+#define FA_U_LEVELS 3                      // Jacobi levels k_u_local resolves in registers (queues of <= 3 cars)
 #endif
 #ifndef FA_U_MINB
 #define FA_U_MINB 4                        // resident CTAs per SM the register allocation of k_u_local aims for
@@ -53,6 +53,7 @@ struct Diag {
 // k_u_local / k_move: warp `wg` of the grid takes strip (wg / nsx, wg % nsx): rows [own0 + sy*rs, +rs), words
 // [sx*STRIP_W, +STRIP_W).  The four warps of a CTA are four strips side by side, so the halo words they share hit L1.
 // ---------------------------------------------------------------------------------------------
+template <bool BAND>
 __global__ void __launch_bounds__(STRIP_THREADS, FA_U_MINB)
 k_u_local(const __grid_constant__ GridView g, int nsx, int nsy, int rs, UEntry *table, unsigned int *qlist0,
           unsigned int *qstage, IterState *is) {
@@ -61,7 +62,7 @@ k_u_local(const __grid_constant__ GridView g, int nsx, int nsy, int rs, UEntry *
   const int sy = wg / nsx, sx = wg - sy * nsx;
   const int ya = g.own0 + sy * rs, yb = min(g.own1, ya + rs);
   // staging segment of this strip: qstage is the second frontier list, idle until k_u_iter starts
-  UStrip<STRIP_W, FA_U_LEVELS>::run(g, sx, ya, yb, (int)(threadIdx.x & 31), table, qstage + (size_t)wg * STRIP_W * rs, qlist0,
+  UStrip<STRIP_W, FA_U_LEVELS, BAND>::run(g, sx, ya, yb, (int)(threadIdx.x & 31), table, qstage + (size_t)wg * STRIP_W * rs, qlist0,
                                     &is->qn[0]);
 }
 

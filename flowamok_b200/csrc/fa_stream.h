@@ -74,7 +74,7 @@ FA_HD W3 w3_c(u32 v) {
 // Frontier: the strip collects its entries in a private segment (qseg) and appends them to the device-wide list
 // with ONE atomic at its end -- per-row atomics on one counter serialise in L2 and dominate the kernel.
 // =============================================================================================
-template <int SW, int K>
+template <int SW, int K, bool BAND>
 struct UStrip {
   struct Raw {
     U4 road, head;
@@ -87,7 +87,6 @@ struct UStrip {
     const GridView &g;
     StripCol col;
     int lane;
-    bool band;
     int ya, yb;     // owned rows of the strip
     int ylo, yhi;   // local rows that exist in the planes and lie inside the global grid
     UEntry *table;
@@ -108,13 +107,19 @@ struct UStrip {
       if ((E.lane & 7) == 1) fa_prefetch_l2(&E.g.pref_in[o]);   // 4-byte words: one prefetch per 32-byte sector
     }
   }
-  FA_HD static UState relax(const Stat &s, u32 valid, const UState &a, const UState &b, const UState &c) {
+  // The statics are stored masked with the valid cells (T, GY, GX; links only exist on valid cells), so every level
+  // stays inside them without further masking.
+  FA_HD static UState relax(const Stat &s, const UState &a, const UState &b, const UState &c) {
     UStatic st;
     st.T = s.T; st.GYr = s.GY; st.GXr = s.GX; st.LN = s.LN; st.LS = s.LS; st.LW = s.LW; st.LE = s.LE;
     st.LNW = st.LNE = st.LSW = st.LSE = 0u;
-    UState n = u_relax_card(st, a.R, simt_w3(b.R), c.R, a.MY, c.MY, simt_w3(b.MX));
-    n.R &= valid; n.MY &= valid; n.MX &= valid;
-    return n;
+    return u_relax_card(st, a.R, simt_w3(b.R), c.R, a.MY, c.MY, simt_w3(b.MX));
+  }
+  // `calculated` of the next level only: a cell's my / mx can only change together with its `calculated` (they are 0
+  // until it is set and final afterwards), so this is all the dormancy test needs
+  FA_HD static u32 relax_r(const Stat &s, u32 aR, u32 bR, u32 cR) {
+    const W3 R = simt_w3(bR);
+    return s.T | (s.LN & aR) | (s.LS & cR) | (s.LW & west(R)) | (s.LE & east(R));
   }
 
   // One pipeline step: raw row j has arrived.  rA / rB = raw rows j-1 / j; roadc2 / dyn2 = road presence and DYN of
@@ -147,10 +152,11 @@ struct UStrip {
       const UStatic st = u_statics(rA.road.x, rA.road.y, rA.road.z, rA.road.w, rA.head.x, rA.head.y, rA.head.z, rA.head.w,
                                    rA.pref, road_up, simt_w3(roadc1), road_dn, dyn2, rB.head.x, simt_w3(rA.head.z), e);
       Stat &sN = S[0];
-      sN.T = st.T; sN.GY = st.GYr; sN.GX = st.GXr; sN.LN = st.LN; sN.LS = st.LS; sN.LW = st.LW; sN.LE = st.LE;
+      sN.T = st.T & valid; sN.GY = st.GYr & valid; sN.GX = st.GXr & valid;
+      sN.LN = st.LN; sN.LS = st.LS; sN.LW = st.LW; sN.LE = st.LE;
       sN.DG = st.LNW | st.LNE | st.LSW | st.LSE;
       UState &a = Lv[0][N];
-      a.R = st.T & valid; a.MY = a.R & st.GYr; a.MX = a.R & st.GXr;
+      a.R = sN.T; a.MY = sN.T & sN.GY; a.MX = sN.T & sN.GX;
       roadc2 = roadc1; dyn2 = rA.head.x;
     }
     // ---- level k of row j-1-k; a band's ghost rows stay at L0 (the raw rows beyond are not held)
@@ -159,12 +165,15 @@ struct UStrip {
 #endif
     for (int k = 1; k <= K; k++) {
       const int y = j - 1 - k;
-      const UState n = relax(S[k], valid, Lv[k - 1][O], Lv[k - 1][M], Lv[k - 1][N]);
-      const bool ghost = E.band && (y < g.own0 || y >= g.own1);
+      const UState n = relax(S[k], Lv[k - 1][O], Lv[k - 1][M], Lv[k - 1][N]);
       UState &b = Lv[k][N];
-      b.R = ghost ? Lv[k - 1][M].R : n.R; b.MY = ghost ? Lv[k - 1][M].MY : n.MY; b.MX = ghost ? Lv[k - 1][M].MX : n.MX;
+      b = n;
+      if (BAND) {
+        const bool ghost = y < g.own0 || y >= g.own1;
+        b.R = ghost ? Lv[k - 1][M].R : n.R; b.MY = ghost ? Lv[k - 1][M].MY : n.MY; b.MX = ghost ? Lv[k - 1][M].MX : n.MX;
+      }
     }
-    if (E.band) {   // ghost row: this band's lower bound of the neighbour's row
+    if (BAND) {   // ghost row: this band's lower bound of the neighbour's row
       const int y = j - 1 - K;
       if (((y == g.own0 - 1 && E.ya == g.own0) || (y == g.own1 && E.yb == g.own1)) && E.col.owner && y >= E.ylo && y < E.yhi) {
         const u32 o = (u32)y * (u32)g.pitch + (u32)E.col.w;
@@ -177,7 +186,7 @@ struct UStrip {
       const int y = j - 2 - K;
       const Stat &sO = S[K + 1];
       const UState &pub = Lv[K][M];
-      const UState n = relax(sO, valid, Lv[K][O], pub, Lv[K][N]);
+      const u32 nR = relax_r(sO, Lv[K][O].R, pub.R, Lv[K][N].R);
       const u32 unresolved = ~pub.R & ~sO.T & valid;
       bool front = false;
       const u32 o = (u32)y * (u32)g.pitch + (u32)E.col.w;
@@ -186,10 +195,9 @@ struct UStrip {
         g.calc[o] = pub.R;
         u32 us = U_NONE;
         if (unresolved) {
-          front = n.R != pub.R || n.MY != pub.MY || n.MX != pub.MX || (sO.DG & unresolved) != 0u ||
-                  (E.band && (y == g.own0 || y == g.own1 - 1));
+          front = nR != pub.R || (sO.DG & unresolved) != 0u || (BAND && (y == g.own0 || y == g.own1 - 1));
           UEntry en;
-          en.wi = o; en.T = sO.T; en.GY = sO.GY; en.GX = sO.GX;
+          en.wi = o; en.T = sO.T | ~valid; en.GY = sO.GY; en.GX = sO.GX;   // cells past the grid count as terminals
           E.table[o] = en;
           us = front ? (o | U_QUEUED) : o;
         }
@@ -207,7 +215,7 @@ struct UStrip {
                         unsigned int *qlist, unsigned int *qn) {
     const int ylo = g.row0 < 0 ? -g.row0 : 0;
     const int yhi = g.gh < g.gh_global - g.row0 ? g.gh : g.gh_global - g.row0;
-    const Env E = {g, strip_col<SW>(g, sx, lane), lane, g.gh != g.gh_global, ya, yb, ylo, yhi, table, qseg};
+    const Env E = {g, strip_col<SW>(g, sx, lane), lane, ya, yb, ylo, yhi, table, qseg};
     // Raw rows ya-K-2 .. yb+K+1 are read.  Slots rotate with period 3: at step j, R0/R1/R2 hold raw rows j-1, j, j+1.
     const int j0 = ya - K - 1, jend = yb + K + 1;   // the step at jend publishes row yb-1
     Raw R0, R1, R2;

@@ -75,7 +75,8 @@ struct UArgs { HostGrid *h; const GridView *g; int sx, ya, yb; unsigned int qn; 
 template <int SW, int K>
 void u_lane(void *p, int lane) {
   UArgs<SW, K> *a = (UArgs<SW, K> *)p;
-  UStrip<SW, K>::run(*a->g, a->sx, a->ya, a->yb, lane, a->h->table.data(), a->qs->data(), a->ql->data(), &a->qn);
+  if (a->g->gh != a->g->gh_global) UStrip<SW, K, true>::run(*a->g, a->sx, a->ya, a->yb, lane, a->h->table.data(), a->qs->data(), a->ql->data(), &a->qn);
+  else UStrip<SW, K, false>::run(*a->g, a->sx, a->ya, a->yb, lane, a->h->table.data(), a->qs->data(), a->ql->data(), &a->qn);
 }
 template <int SW, int K>
 void u_init(HostGrid *h, const GridView &g, int rs) {
