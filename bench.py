@@ -26,6 +26,11 @@ if str(ROOT) not in sys.path:
 
 B_ALG = 12.0  # algorithmic bytes per cell-update (SURVEY 8d / BASELINE.md): r+w of a u16 control word and a u32 colour
 
+# DRAM bytes per launch at BASELINE config 4 (16384^2, quick), dram__bytes_read.sum + dram__bytes_write.sum of one
+# `ncu --set full` capture per kernel (profiles/r01_k_*.txt).  Below the algorithmic 3.22 GB per tick: the colour payload
+# goes through a lazy double buffer, only the 32-byte sectors that hold a car are rewritten.
+NCU_TRAFFIC_16384_QUICK = {"k_u_local": 0.476e9, "k_u_iter": 0.001e9, "k_move": 1.585e9}
+
 
 def measured_peak():
     p = ROOT / "MEASURED_PEAKS.json"
@@ -273,15 +278,26 @@ def main():
     peak, peak_src = measured_peak()
     per_gpu_gcups = value / world
     achieved = per_gpu_gcups * B_ALG  # GB/s of algorithmic traffic per GPU
-    kernels = "k_u_init + k_u_iter" + (" + k_rings" if perfect else "") + " + k_move"
+    kernels = "k_u_local + k_u_iter" + (" + k_rings" if perfect else "") + " + k_move"
+    known_traffic = world == 1 and S == 16384 and not perfect
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
-                "what": f"whole tick ({kernels}), 12 algorithmic B per cell-update (SURVEY 8d), per GPU"}
+                "traffic": sum(NCU_TRAFFIC_16384_QUICK.values()) if known_traffic else None, "peak_source": peak_src,
+                "algorithmic_bytes": cells / world * B_ALG,
+                "what": f"whole tick ({kernels}), 12 algorithmic B per cell-update (SURVEY 8d), per GPU; traffic = DRAM "
+                        "bytes per tick summed over the kernels' ncu captures (profiles/)"}
     if prof:
         tot = sum(prof.values())
+        dom = max(prof, key=prof.get)
+        dom_ms = prof[dom] / prof_ticks
         roofline.update({"kernel_ms_per_tick": {k: v / prof_ticks for k, v in prof.items()},
-                         "dominant_kernel": max(prof, key=prof.get),
-                         "dominant_share": max(prof.values()) / tot if tot else None})
+                         "dominant_kernel": dom,
+                         "dominant_share": max(prof.values()) / tot if tot else None,
+                         # the dominant kernel alone: it moves the whole persistent state, i.e. all 12 algorithmic B
+                         "dominant": {"kernel": dom, "ms": dom_ms, "achieved": cells / world * B_ALG / (dom_ms * 1e-3) / 1e9,
+                                      "frac": cells / world * B_ALG / (dom_ms * 1e-3) / 1e9 / peak,
+                                      "traffic": NCU_TRAFFIC_16384_QUICK.get(dom) if known_traffic else None,
+                                      "dram_gbs": (NCU_TRAFFIC_16384_QUICK[dom] / (dom_ms * 1e-3) / 1e9)
+                                      if known_traffic and dom in NCU_TRAFFIC_16384_QUICK else None}})
     launches_per_tick = 3 + (1 if perfect and n_rings else 0)
     gpu_launches = launches_per_tick * args.steps
     if runner is not None:   # + per convergence round: 2 pack copies are memcpys; k_band_merge x sides, k_u_iter resumes
@@ -296,7 +312,7 @@ def main():
                        "grid": [S, S], "mode": args.mode, "rings_on_rank0": int(n_rings),
                        "parallelism": "1 grid" if world == 1 else
                        f"{world} row bands of {S // world} rows, per-tick halo rows over NCCL send/recv + 1 all-reduced convergence word",
-                       "l2": f"state {cells / world * 9.75 / 1e9:.2f} GB per GPU per tick >> 126 MB L2: inputs larger than L2, no flush"},
+                       "l2": f"planes read+written per tick {cells / world * 7.7 / 1e9:.2f} GB per GPU >> 126 MB L2: inputs larger than L2, no flush"},
             "fixpoint": {"iterations_per_tick": st["passes"] / max(1, st["ticks"]),
                          "worklist_entries_relaxed_per_tick": st["sweeps"] / max(1, st["ticks"]),
                          "band_convergence_rounds_per_tick": rounds / args.steps if runner else None},

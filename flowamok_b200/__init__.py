@@ -204,7 +204,7 @@ class Grid:
     def step_profile(self, perfect: bool, n_ticks=10):
         ms = (C.c_double * 4)()
         self.ctx.check(self.L.flowamok_step_profile(self.ctx.h, self.h, int(perfect), n_ticks, ms))
-        return dict(k_u_init=ms[0], k_u_iter=ms[1], k_rings=ms[2], k_move=ms[3])
+        return dict(k_u_local=ms[0], k_u_iter=ms[1], k_rings=ms[2], k_move=ms[3])
 
     def step_leaks(self, perfect: bool, cap=1 << 20):
         buf = np.zeros((cap, 8), np.int64)

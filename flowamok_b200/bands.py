@@ -4,7 +4,7 @@ plumbing (NCCL over NVLink on the GPUs, gloo in the CPU tests), the stepping its
 The reference is single-device; the decomposition follows from its stencil radius of exactly one cell in
 both phases (steppers.fut:19,33-34,66,77-79).  Per tick each band
   1. swaps two heading/preference rows and one colour row with each neighbour        (state message)
-  2. runs k_u_init, swaps its boundary row of calc / my|mx (so the ghost rows hold the neighbours' rows after
+  2. runs k_u_local, swaps its boundary row of calc / my|mx (so the ghost rows hold the neighbours' rows after
      their block-local sweeps) and runs the frontier iterations (k_u_iter)
   3. swaps its boundary row of calc / my|mx again, ORs the neighbour's row into its ghost row and wakes the owned
      words next to every ghost word that changed; all bands all-reduce (MAX) the number of woken words and

@@ -168,7 +168,7 @@ int flowamok_context_new(flowamok_context **out, int device, void *stream) {
   ctx->num_sms = prop.multiProcessorCount;
   if (stream) ctx->stream = (cudaStream_t)stream;
   else { CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
-  CU(cudaFuncSetAttribute(k_move, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
+  CU(cudaFuncSetAttribute(k_move<M_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
   ctx->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_u_iter, UIT_THREADS, 0));
@@ -666,7 +666,7 @@ static int launch_rings(flowamok_context *ctx, flowamok_grid *g, const GridView 
   return 0;
 }
 static int launch_move(flowamok_context *ctx, flowamok_grid *g, const GridView &v, u32 *leak_plane) {
-  k_move<<<g->mtx * g->mty, M_WARPS * 32, MTL::Smem::bytes(g->rs_m), ctx->stream>>>(v, g->nsx, g->mtx, g->rs_m, g->diag, leak_plane);
+  k_move<M_WARPS><<<g->mtx * g->mty, M_WARPS * 32, MTL::Smem::bytes(g->rs_m), ctx->stream>>>(v, g->nsx, g->mtx, g->rs_m, g->diag, leak_plane);
   KCHECK("k_move");
   g->cur ^= 1;
   g->tick++;

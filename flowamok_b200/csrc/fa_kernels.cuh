@@ -275,16 +275,20 @@ k_rings(const __grid_constant__ GridView g, const RingWord *words, const unsigne
 // ---------------------------------------------------------------------------------------------
 // move + reset
 // ---------------------------------------------------------------------------------------------
-constexpr int M_WARPS = 4;                 // k_move CTA: 4 strips side by side
+// k_move CTA: NW strips side by side (4 measured best: 2 and 3 lose memory parallelism in phase B, 6 and 8 lose
+// resident CTAs to overlap phase A of one tile with phase B of another)
+constexpr int M_WARPS = 4;
 typedef MTile<STRIP_W, M_WARPS> MTL;
-__global__ void __launch_bounds__(M_WARPS * 32, FA_M_MINB)
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, FA_M_MINB)
 k_move(const __grid_constant__ GridView g, int nsx, int ntx, int rs, Diag *diag, unsigned int *leak_plane) {
+  typedef MTile<STRIP_W, NW> MTL;   // shadows the production typedef: the kernel body is width-generic
   extern __shared__ __align__(16) u32 smem_raw[];
-  const MTL::Smem sm = {smem_raw, rs};
-  const int tid = threadIdx.x, nt = M_WARPS * 32, wi = tid >> 5, lane = tid & 31;
+  const typename MTL::Smem sm = {smem_raw, rs};
+  const int tid = threadIdx.x, nt = NW * 32, wi = tid >> 5, lane = tid & 31;
   const int ty = blockIdx.x / ntx, tx = blockIdx.x - ty * ntx;
   const int ya = g.own0 + ty * rs, yb = min(g.own1, ya + rs);
-  const int sx = tx * M_WARPS + wi;
+  const int sx = tx * NW + wi;
   if (blockIdx.x == 0 && tid == 0) atomicAdd(&diag->ticks, 1ull);
   MTL::phaseB_clear(sm, tid);
   const unsigned int nleak = MTL::phaseA(g, sx < nsx, sx, wi, ya, yb, lane, leak_plane, sm);
@@ -292,9 +296,9 @@ k_move(const __grid_constant__ GridView g, int nsx, int ntx, int rs, Diag *diag,
   __syncthreads();
   MTL::phaseB0(sm, yb - ya, tid, nt);
   __syncthreads();
-  MTL::phaseB1(g, sm, tx * M_WARPS, ya, tid, nt);
+  MTL::phaseB1(g, sm, tx * NW, ya, tid, nt);
   __syncthreads();   // the sector copies are ordered before the arrival patches
-  MTL::phaseB2(g, sm, tx * M_WARPS, ya, yb - ya, tid, nt);
+  MTL::phaseB2(g, sm, tx * NW, ya, yb - ya, tid, nt);
 }
 
 // ---------------------------------------------------------------------------------------------

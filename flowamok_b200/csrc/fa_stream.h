@@ -17,6 +17,13 @@
 #include "fa_simt.h"
 #include "fa_tiles.h"
 
+#ifndef FA_U_AHEAD
+#define FA_U_AHEAD 6
+#endif
+#ifndef FA_M_AHEAD
+#define FA_M_AHEAD 6
+#endif
+
 namespace fa {
 
 // per-lane column constants of a strip
@@ -101,7 +108,7 @@ struct UStrip {
     }
   }
   FA_HD static void prefetch_raw(const Env &E, int y) {
-    if (E.col.w_ok && y >= E.ylo && y < E.yhi) {
+    if (FA_U_AHEAD > 0 && E.col.w_ok && y >= E.ylo && y < E.yhi) {
       const u32 o = (u32)y * (u32)E.g.pitch + (u32)E.col.w;
       fa_prefetch_l2(&E.g.road[o]); fa_prefetch_l2(&E.g.head_in[o]);
       if ((E.lane & 7) == 1) fa_prefetch_l2(&E.g.pref_in[o]);   // 4-byte words: one prefetch per 32-byte sector
@@ -230,7 +237,7 @@ struct UStrip {
       for (int k = 0; k <= K; k++)
         for (int i = 0; i < 3; i++) Lv[k][i] = z3;
     }
-    constexpr int AHEAD = 6;   // rows between the L2 prefetch and the register load of a row
+    constexpr int AHEAD = FA_U_AHEAD;   // rows between the L2 prefetch and the register load of a row
     for (int y = j0 + 2; y < j0 + 2 + AHEAD; y++) prefetch_raw(E, y);
     // the last one or two steps of the last trip may run past jend: they publish nothing (the stores check y < yb)
     for (int j = j0; j <= jend; j += 3) {
@@ -319,7 +326,7 @@ struct MTile {
     }
   }
   FA_HD static void prefetch_row(const Env &E, int y) {
-    if (E.col.w_ok && y >= E.ylo && y < E.yhi) {
+    if (FA_M_AHEAD > 0 && E.col.w_ok && y >= E.ylo && y < E.yhi) {
       const u32 o = (u32)y * (u32)E.g.pitch + (u32)E.col.w;
       fa_prefetch_l2(&E.g.road[o]); fa_prefetch_l2(&E.g.head_in[o]);
       if ((E.lane & 3) == 1) fa_prefetch_l2(&E.g.mymx[o]);
@@ -411,7 +418,7 @@ struct MTile {
     Aux X0, X1;
     load_row(E, ya - 1, R0); load_row(E, ya, R1); load_row(E, ya + 1, R2);
     load_aux(E, ya, X0);
-    constexpr int AHEAD = 6;   // rows between the L2 prefetch and the register load of a row
+    constexpr int AHEAD = FA_M_AHEAD;   // rows between the L2 prefetch and the register load of a row
     for (int y = ya + 2; y < ya + 2 + AHEAD && y <= yb; y++) prefetch_row(E, y);
     // the last trip may run up to three rows past yb: those steps compute but store nothing (live = false)
     for (int y = ya; y < yb; y += 4) {

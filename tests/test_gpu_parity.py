@@ -47,7 +47,7 @@ def test_quick_random_grids_every_tick(ctx):
 
 
 def test_dense_jam_multi_pass(ctx):
-    """long queues crossing tile borders: exercises k_u_fix (extra device-side fixpoint passes)"""
+    """long queues crossing strip borders: k_u_local leaves them to k_u_iter (many frontier iterations)"""
     arrs = random_grid(7, 300, 2200, n_lines=400, car_p=0.93, weird_p=0.0, offroad_p=0.0)
     og, ch = oracle_grid(arrs), O.Chooser(O.CHOOSE_RANDOM)
     g = ctx.grid_from_arrays(**arrs)
@@ -58,6 +58,31 @@ def test_dense_jam_multi_pass(ctx):
         assert_state_equal(state_of(og), dev_state(g), f"tick {t}")
     st = g.stats()
     assert st["ticks"] == 6 and st["passes"] > 6, st
+
+
+def test_dense_free_flow_overflows_the_arrival_list(ctx):
+    """every row an avenue, every other cell a car: half of all cells receive a car each tick, far more than the
+    shared-memory arrival list of a k_move tile holds (the direct pass from the descriptors runs); the grid is wider
+    than one k_move tile and than one strip, and taller than one strip"""
+    gh, gw = 150, 4200
+    r = np.random.default_rng(5)
+    uy = np.zeros((gh, gw), np.int8)
+    ux = np.ones((gh, gw), np.int8)
+    ux[1::2] = -1                                   # alternate rows flow the other way
+    dy = np.zeros((gh, gw), np.int8)
+    dx = np.zeros((gh, gw), np.int8)
+    cars = np.zeros((gh, gw), bool)
+    cars[:, ::2] = True
+    dx[cars] = ux[cars]
+    arrs = dict(uy=uy, ux=ux, dy=dy, dx=dx, color=r.integers(0, 2**32, (gh, gw), dtype=np.uint64).astype(np.uint32),
+                pref=np.zeros((gh, gw), np.uint8), rng_state=r.integers(0, 2**63, (gh, gw), dtype=np.uint64),
+                rng_inc=np.full((gh, gw), 1, np.uint64))
+    og, ch = oracle_grid(arrs), O.Chooser(O.CHOOSE_RANDOM)
+    g = ctx.grid_from_arrays(**arrs)
+    for t in range(5):
+        nl, _ = og.step_quick(ch)
+        assert g.step(False, 1) == nl, f"leaks tick {t}"
+        assert_state_equal(state_of(og), dev_state(g), f"tick {t}")
 
 
 @pytest.mark.parametrize("mode", [O.CHOOSE_Y, O.CHOOSE_X, O.CHOOSE_TAPE])

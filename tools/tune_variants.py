@@ -33,10 +33,10 @@ def build(specs):
             if "Compiling entry function" in line:
                 cur = line.split("'")[1]
             elif "Used" in line and cur:
-                for k in ("k_u_local", "k_move", "k_u_iter"):
+                for k in ("k_u_localILb0", "k_moveILi4", "k_moveILi6", "k_moveILi8", "k_u_iter"):
                     if k in cur:
-                        regs[k] = line.split("Used")[1].split(",")[0].strip()
-            elif "spill" in line and cur and any(k in cur for k in ("k_u_local", "k_moveE")) and "0 bytes spill stores" not in line:
+                        regs[k] = line.split("Used")[1].split(",")[0].strip().split()[0]
+            elif "spill" in line and cur and any(k in cur for k in ("k_u_local", "k_move")) and "0 bytes spill stores" not in line:
                 regs[cur[:20] + "_spill"] = line.strip()
         print(name, regs)
 
