@@ -861,31 +861,22 @@ static int band_check(flowamok_context *ctx, const flowamok_grid *g, int side) {
   if (g->own1 - g->own0 < 2) return fail(ctx, "a band needs at least 2 rows");
   return 0;
 }
+static int band_state(flowamok_context *ctx, flowamok_grid *g, void *b0, void *b1, int pack) {
+  BandBufs bufs = {{(char *)b0, (char *)b1}};
+  k_band_state<<<dim3(nblk(8ll * g->pitch, 256), 2), 256, 0, ctx->stream>>>(g->pitch, g->own0, g->own1, g->head[g->cur], g->pref[g->cur],
+                                                                             g->color[g->cur], bufs, pack);
+  KCHECK("k_band_state");
+  return 0;
+}
 int flowamok_band_pack_state(flowamok_context *ctx, flowamok_grid *g, int side, void *dev_buf) {
   if (band_check(ctx, g, side)) return 1;
   CU(cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
-  const size_t P = (size_t)g->pitch;
-  const int r2 = side == 0 ? g->own0 : g->own1 - 2;          // first / last two owned rows
-  const int rc = side == 0 ? g->own0 : g->own1 - 1;          // the owned row next to the cut
-  char *b = (char *)dev_buf;
-  CU(cudaMemcpyAsync(b, g->head[g->cur] + (size_t)r2 * P, 2 * P * 16, cudaMemcpyDeviceToDevice, st));
-  CU(cudaMemcpyAsync(b + 2 * P * 16, g->pref[g->cur] + (size_t)r2 * P, 2 * P * 4, cudaMemcpyDeviceToDevice, st));
-  CU(cudaMemcpyAsync(b + 2 * P * 20, g->color[g->cur] + (size_t)rc * P * 32, P * 128, cudaMemcpyDeviceToDevice, st));
-  return 0;
+  return band_state(ctx, g, side == 0 ? dev_buf : nullptr, side == 1 ? dev_buf : nullptr, 1);
 }
 int flowamok_band_unpack_state(flowamok_context *ctx, flowamok_grid *g, int side, const void *dev_buf) {
   if (band_check(ctx, g, side)) return 1;
   CU(cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
-  const size_t P = (size_t)g->pitch;
-  const int r2 = side == 0 ? g->own0 - 2 : g->own1;          // my halo rows on that side
-  const int rc = side == 0 ? g->own0 - 1 : g->own1;
-  const char *b = (const char *)dev_buf;
-  CU(cudaMemcpyAsync(g->head[g->cur] + (size_t)r2 * P, b, 2 * P * 16, cudaMemcpyDeviceToDevice, st));
-  CU(cudaMemcpyAsync(g->pref[g->cur] + (size_t)r2 * P, b + 2 * P * 16, 2 * P * 4, cudaMemcpyDeviceToDevice, st));
-  CU(cudaMemcpyAsync(g->color[g->cur] + (size_t)rc * P * 32, b + 2 * P * 20, P * 128, cudaMemcpyDeviceToDevice, st));
-  return 0;
+  return band_state(ctx, g, side == 0 ? (void *)dev_buf : nullptr, side == 1 ? (void *)dev_buf : nullptr, 0);
 }
 /* u_init: k_u_init only (statics, block-local sweeps, ghost rows seeded with this band's view of the neighbour's
  * boundary row); u_iter: the frontier iterations.  u_begin = both.  Swapping the boundary rows BETWEEN the two lets
@@ -907,28 +898,30 @@ int flowamok_band_u_iter(flowamok_context *ctx, flowamok_grid *g) {
 int flowamok_band_u_begin(flowamok_context *ctx, flowamok_grid *g) {
   return flowamok_band_u_init(ctx, g) || flowamok_band_u_iter(ctx, g);
 }
+static int band_pack_u(flowamok_context *ctx, flowamok_grid *g, void *b0, void *b1) {
+  BandBufs bufs = {{(char *)b0, (char *)b1}};
+  k_band_pack_u<<<dim3(nblk(g->pitch, 128), 2), 128, 0, ctx->stream>>>(g->pitch, g->own0, g->own1, g->calc, g->mymx, bufs);
+  KCHECK("k_band_pack_u");
+  return 0;
+}
+static int band_merge_u(flowamok_context *ctx, flowamok_grid *g, const void *b0, const void *b1, int wake) {
+  BandBufs bufs = {{(char *)b0, (char *)b1}};
+  GridView v = make_view(g);
+  k_band_merge<<<dim3(nblk(g->pitch, 128), 2), 128, 0, ctx->stream>>>(v, bufs, wake, g->qlist[1], g->is);
+  KCHECK("k_band_merge");
+  return 0;
+}
 int flowamok_band_pack_u(flowamok_context *ctx, flowamok_grid *g, int side, void *dev_buf) {
   if (band_check(ctx, g, side)) return 1;
   CU(cudaSetDevice(ctx->device));
-  const size_t P = (size_t)g->pitch;
-  const int r = side == 0 ? g->own0 : g->own1 - 1;
-  char *b = (char *)dev_buf;
-  CU(cudaMemcpyAsync(b, g->calc + (size_t)r * P, P * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(b + P * 4, g->mymx + (size_t)r * P, P * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-  return 0;
+  return band_pack_u(ctx, g, side == 0 ? dev_buf : nullptr, side == 1 ? dev_buf : nullptr);
 }
 /* OR the neighbour's boundary row into my ghost row; wake=1 queues the owned words next to changed ghost words.
  * dev_woken (device u32, may be NULL) receives the number of entries queued so far this round. */
 int flowamok_band_merge_u(flowamok_context *ctx, flowamok_grid *g, int side, const void *dev_buf, int wake, void *dev_woken) {
   if (band_check(ctx, g, side)) return 1;
   CU(cudaSetDevice(ctx->device));
-  const size_t P = (size_t)g->pitch;
-  const int ghost = side == 0 ? g->own0 - 1 : g->own1, own = side == 0 ? g->own0 : g->own1 - 1;
-  const char *b = (const char *)dev_buf;
-  GridView v = make_view(g);
-  k_band_merge<<<nblk(g->pitch, 128), 128, 0, ctx->stream>>>(v, ghost, own, (const u32 *)b, (const u64 *)(b + P * 4), wake,
-                                                            g->qlist[1], g->is);
-  KCHECK("k_band_merge");
+  if (band_merge_u(ctx, g, side == 0 ? dev_buf : nullptr, side == 1 ? dev_buf : nullptr, wake)) return 1;
   if (dev_woken) CU(cudaMemcpyAsync(dev_woken, &g->is->qn[1], 4, cudaMemcpyDeviceToDevice, ctx->stream));
   return 0;
 }
@@ -1021,31 +1014,37 @@ int flowamok_band_step(flowamok_context *ctx, flowamok_grid *g, int perfect, int
     CU(cudaStreamSynchronize(st));
     g->ring_swap = *g->h_woken ? 1 : 0;
   }
+  void *ss[2] = {has(0) ? g->msg_s_send[0] : nullptr, has(1) ? g->msg_s_send[1] : nullptr};
+  void *sr[2] = {has(0) ? g->msg_s_recv[0] : nullptr, has(1) ? g->msg_s_recv[1] : nullptr};
+  void *us[2] = {has(0) ? g->msg_u_send[0] : nullptr, has(1) ? g->msg_u_send[1] : nullptr};
+  void *ur[2] = {has(0) ? g->msg_u_recv[0] : nullptr, has(1) ? g->msg_u_recv[1] : nullptr};
   auto swap_u = [&](int wake) -> int {
-    for (int side = 0; side < 2; side++)
-      if (has(side) && flowamok_band_pack_u(ctx, g, side, g->msg_u_send[side])) return 1;
+    if (band_pack_u(ctx, g, us[0], us[1])) return 1;
     if (band_swap(ctx, g->msg_u_send, g->msg_u_recv, ub)) return 1;
-    for (int side = 0; side < 2; side++)
-      if (has(side) && flowamok_band_merge_u(ctx, g, side, g->msg_u_recv[side], wake, nullptr)) return 1;
-    return 0;
+    return band_merge_u(ctx, g, ur[0], ur[1], wake);
   };
+  // One convergence round = swap the boundary rows, wake what they changed, resume the frontier (a no-op kernel when
+  // nothing was woken anywhere).  SPEC rounds are enqueued back to back without asking whether they are needed; only
+  // then do the bands agree (one all-reduced word, ONE host synchronisation per tick) whether the last merge still woke
+  // something -- a waiting chain that crosses cuts more than SPEC times -- and keep going in that case.
+  static const int SPEC = [] { const char *e = getenv("FLOWAMOK_BAND_SPEC"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
+  static const bool PRESWAP = [] { const char *e = getenv("FLOWAMOK_BAND_PRESWAP"); return !e || e[0] != '0'; }();
   for (int64_t t = 0; t < n_ticks; t++) {
     if (multi) {
-      for (int side = 0; side < 2; side++)
-        if (has(side) && flowamok_band_pack_state(ctx, g, side, g->msg_s_send[side])) return 1;
+      if (band_state(ctx, g, ss[0], ss[1], 1)) return 1;
       if (band_swap(ctx, g->msg_s_send, g->msg_s_recv, sb)) return 1;
-      for (int side = 0; side < 2; side++)
-        if (has(side) && flowamok_band_unpack_state(ctx, g, side, g->msg_s_recv[side])) return 1;
+      if (band_state(ctx, g, sr[0], sr[1], 0)) return 1;
     }
     if (flowamok_band_u_init(ctx, g)) return 1;
-    if (multi && swap_u(0)) return 1;            // ghost rows := the neighbour's rows after ITS local sweeps
+    if (multi && PRESWAP && swap_u(0)) return 1;   // ghost rows := the neighbour's rows after ITS local levels
     if (flowamok_band_u_iter(ctx, g)) return 1;
-    while (multi) {
+    for (int round = 0; multi; round++) {
       if (swap_u(1)) return 1;
+      if (round + 1 < SPEC) { if (flowamok_band_u_resume(ctx, g)) return 1; g->band_rounds++; continue; }
       CU(cudaMemcpyAsync(g->d_woken, &g->is->qn[1], 4, cudaMemcpyDeviceToDevice, st));
       NC(g_nccl.AllReduce(g->d_woken, g->d_woken, 1, ncclUint32, ncclMax, ctx->comm, st));
       CU(cudaMemcpyAsync(g->h_woken, g->d_woken, 4, cudaMemcpyDeviceToHost, st));
-      CU(cudaStreamSynchronize(st));            // the host round trip of this round: one 4-byte word
+      CU(cudaStreamSynchronize(st));            // the host round trip of the tick: one 4-byte word
       g->band_rounds++;
       if (*g->h_woken == 0) break;
       if (flowamok_band_u_resume(ctx, g)) return 1;

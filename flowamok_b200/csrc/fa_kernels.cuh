@@ -194,13 +194,59 @@ k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *
 }
 
 // ---------------------------------------------------------------------------------------------
-// Row bands: OR the neighbour's boundary row (calc, my|mx) into the ghost row; wake the owned words next to
-// every word that changed (their waiting cars may point into it).  One thread per word.
+// Row bands.  One launch serves both sides of the band (blockIdx.y = side; a side without a neighbour has a null
+// buffer): the per-tick protocol is latency-bound, so every launch saved shortens the tick.
+//   state message: 2 heading rows + 2 preference rows + 1 colour row     u message: 1 row of calc + 1 row of my|mx
 // ---------------------------------------------------------------------------------------------
-__global__ void k_band_merge(const __grid_constant__ GridView g, int ghost_row, int own_row, const u32 *recv_calc,
-                             const u64 *recv_mymx, int wake, unsigned int *qlist1, IterState *is) {
+struct BandBufs {
+  char *buf[2];
+};
+// pack = true: owned boundary rows -> message; false: message -> halo rows
+__global__ void k_band_state(int pitch, int own0, int own1, U4 *head, u32 *pref, u32 *color, BandBufs bufs, int pack) {
+  const int side = blockIdx.y;
+  char *b = bufs.buf[side];
+  if (!b) return;
+  const size_t P = (size_t)pitch;
+  const int r2 = pack ? (side == 0 ? own0 : own1 - 2) : (side == 0 ? own0 - 2 : own1);
+  const int rc = pack ? (side == 0 ? own0 : own1 - 1) : (side == 0 ? own0 - 1 : own1);
+  U4 *mh = reinterpret_cast<U4 *>(b);                 // [2P] headings
+  u32 *mp = reinterpret_cast<u32 *>(b + 2 * P * 16);  // [2P] preferences
+  U4 *mc = reinterpret_cast<U4 *>(b + 2 * P * 20);    // [8P] colours of one row, 16 bytes at a time
+  U4 *gh = head + (size_t)r2 * P;
+  u32 *gp = pref + (size_t)r2 * P;
+  U4 *gc = reinterpret_cast<U4 *>(color + (size_t)rc * P * 32);
+  const size_t n = 8 * P;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    if (pack) {
+      mc[i] = gc[i];
+      if (i < 2 * P) { mh[i] = gh[i]; mp[i] = gp[i]; }
+    } else {
+      gc[i] = mc[i];
+      if (i < 2 * P) { gh[i] = mh[i]; gp[i] = mp[i]; }
+    }
+  }
+}
+__global__ void k_band_pack_u(int pitch, int own0, int own1, const u32 *calc, const u64 *mymx, BandBufs bufs) {
+  const int side = blockIdx.y;
+  char *b = bufs.buf[side];
+  if (!b) return;
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= pitch) return;
+  const size_t o = (size_t)(side == 0 ? own0 : own1 - 1) * pitch + w;
+  reinterpret_cast<u32 *>(b)[w] = calc[o];
+  reinterpret_cast<u64 *>(b + (size_t)pitch * 4)[w] = mymx[o];
+}
+// OR the neighbour's boundary row (calc, my|mx) into the ghost row; wake the owned words next to every word that
+// changed (their waiting cars may point into it).  One thread per word and side.
+__global__ void k_band_merge(const __grid_constant__ GridView g, BandBufs bufs, int wake, unsigned int *qlist1, IterState *is) {
+  const int side = blockIdx.y;
+  const char *b = bufs.buf[side];
+  if (!b) return;
   int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= g.pitch) return;
+  const int ghost_row = side == 0 ? g.own0 - 1 : g.own1, own_row = side == 0 ? g.own0 : g.own1 - 1;
+  const u32 *recv_calc = reinterpret_cast<const u32 *>(b);
+  const u64 *recv_mymx = reinterpret_cast<const u64 *>(b + (size_t)g.pitch * 4);
   size_t o = (size_t)ghost_row * g.pitch + w;
   u32 oc = g.calc[o], nc = oc | recv_calc[w];
   u64 om = g.mymx[o], nm = om | recv_mymx[w];
@@ -235,12 +281,16 @@ __device__ __forceinline__ bool ring_word_ok(const GridView &g, const RingWord &
   return (n & e.mN) == e.mN && (s_ & e.mS) == e.mS && (w & e.mW) == e.mW && (ea & e.mE) == e.mE;
 }
 constexpr int RINGS_PER_BLOCK = 256;
+constexpr int RING_ITEMS = 4;   // (survivor, word) items a thread tests at once in the uniform-stride path
 // Phase 1: one thread per ring tests the ring's first word (almost every ring that is not completely full fails
-// here); survivors are compacted in shared memory.  Phase 2: one warp per survivor tests all words in parallel
-// and, if the ring passes, ORs the grants into my|mx (one 64-bit atomic per word).
+// here); survivors are compacted in shared memory.  Phase 2 tests all words of the survivors and, if a ring passes,
+// ORs its grants into my|mx (one 64-bit atomic per word).  Rings of one uniform length (off == nullptr: the synthetic
+// network) are handled as a flat list of (survivor, word) items spread over all threads, every thread holding several
+// independent loads in flight -- two memory latencies per CTA; CSR rings take one warp per survivor.
 __global__ void __launch_bounds__(RINGS_PER_BLOCK)
 k_rings(const __grid_constant__ GridView g, const RingWord *words, const unsigned long long *off, long long n, int stride) {
   __shared__ unsigned int surv[RINGS_PER_BLOCK];
+  __shared__ unsigned int okf[RINGS_PER_BLOCK];
   __shared__ unsigned int wbase[RINGS_PER_BLOCK / 32 + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long k = (long long)blockIdx.x * RINGS_PER_BLOCK + tid;
@@ -252,16 +302,47 @@ k_rings(const __grid_constant__ GridView g, const RingWord *words, const unsigne
   }
   const unsigned m = __ballot_sync(0xFFFFFFFFu, pass0);
   if (lane == 0) wbase[warp + 1] = __popc(m);
+  okf[tid] = 1u;
   __syncthreads();
   if (tid == 0) { wbase[0] = 0; for (int i = 1; i <= RINGS_PER_BLOCK / 32; i++) wbase[i] += wbase[i - 1]; }
   __syncthreads();
   if (pass0) surv[wbase[warp] + __popc(m & ((1u << lane) - 1u))] = (unsigned int)tid;
   __syncthreads();
   const int nsurv = (int)wbase[RINGS_PER_BLOCK / 32];
+  if (!off) {   // uniform ring length: flat (survivor, word) items
+    const int nitems = nsurv * stride;
+    const long long ring0 = (long long)blockIdx.x * RINGS_PER_BLOCK;
+    for (int i0 = tid; i0 < nitems; i0 += RINGS_PER_BLOCK * RING_ITEMS) {   // test: RING_ITEMS independent loads in flight
+      RingWord w[RING_ITEMS];
+      int si[RING_ITEMS];
+#pragma unroll
+      for (int q = 0; q < RING_ITEMS; q++) {
+        const int i = i0 + q * RINGS_PER_BLOCK;
+        si[q] = -1;
+        if (i < nitems) {
+          si[q] = i / stride;
+          w[q] = words[(unsigned long long)(ring0 + surv[si[q]]) * stride + (unsigned)(i - si[q] * stride)];
+        }
+      }
+      bool ok[RING_ITEMS];
+#pragma unroll
+      for (int q = 0; q < RING_ITEMS; q++) ok[q] = si[q] < 0 || ring_word_ok(g, w[q]);
+#pragma unroll
+      for (int q = 0; q < RING_ITEMS; q++)
+        if (!ok[q]) okf[si[q]] = 0u;   // benign race: everybody writes 0
+    }
+    __syncthreads();
+    for (int i = tid; i < nitems; i += RINGS_PER_BLOCK) {   // mark the rings that passed
+      const int s_ = i / stride;
+      if (!okf[s_]) continue;
+      const RingWord w = words[(unsigned long long)(ring0 + surv[s_]) * stride + (unsigned)(i - s_ * stride)];
+      if (w.gY | w.gX) atomicOr((unsigned long long *)&g.mymx[w.wi], (unsigned long long)w.gY | ((unsigned long long)w.gX << 32));
+    }
+    return;
+  }
   for (int si = warp; si < nsurv; si += RINGS_PER_BLOCK / 32) {
     const long long r = (long long)blockIdx.x * RINGS_PER_BLOCK + surv[si];
-    const unsigned long long b = off ? off[r] : (unsigned long long)r * stride;
-    const unsigned long long e = off ? off[r + 1] : b + stride;
+    const unsigned long long b = off[r], e = off[r + 1];
     bool ok = true;
     for (unsigned long long t = b + lane; t < e; t += 32) ok = ok && ring_word_ok(g, words[t]);
     if (!__all_sync(0xFFFFFFFFu, ok)) continue;
