@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Turn an ncu report (--set full, --import-source on) into the text summary committed under profiles/.
-usage: python profiles/summarize.py gpurun_out/r01_k_move.ncu-rep > profiles/r01_k_move.txt"""
+usage: python profiles/summarize.py gpurun_out/r01_kernels.ncu-rep k_move > profiles/r01_k_move.txt
+(the second argument picks one kernel of a report that holds several)"""
 import csv
 import subprocess
 import sys
@@ -17,19 +18,24 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "smsp__cycles_active.avg"]
 
 
-def main(rep):
+def main(rep, kern=None):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[2]
+    hdr, units = rows[0], rows[1]
+    ki = hdr.index("Kernel Name")
+    vals = next(r for r in rows[2:] if kern is None or kern in r[ki])
     d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}
     print(f"# {rep}")
     print(f"kernel: {d.get('Kernel Name', ('?',))[0]}   grid {d.get('Grid Size', ('?',))[0]} block {d.get('Block Size', ('?',))[0]}")
     for k in KEYS:
         if k in d:
             print(f"{k:70s} {d[k][0]:>18s} {d[k][1]}")
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    cmd = ["ncu", "-i", rep, "--page", "source", "--csv"] + (["-k", "regex:" + kern] if kern else [])
+    src = subprocess.run(cmd, capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
-    hdr = rows[1]
+    hi = next(i for i, r in enumerate(rows) if "Source" in r)
+    hdr = rows[hi]
+    rows = rows[hi - 1:]
     st = [i for i, h in enumerate(hdr) if h.startswith("stall_")]
     tot = {hdr[i]: 0 for i in st}
     for r in rows[2:]:
@@ -43,7 +49,15 @@ def main(rep):
     for k, v in sorted(tot.items(), key=lambda kv: -kv[1])[:10]:
         print(f"  {k:40s} {v / ssum * 100:5.1f} %")
     isrc, ismp, iex = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
-    data = [(r[isrc].strip(), int(r[iex]), int(r[ismp])) for r in rows[2:] if len(r) > iex]
+    seen, data = set(), []
+    for r in rows[2:]:
+        if len(r) <= iex or (r[0], r[isrc]) in seen:
+            continue
+        seen.add((r[0], r[isrc]))
+        try:
+            data.append((r[isrc].strip(), int(r[iex]), int(r[ismp])))
+        except ValueError:
+            pass
     S = sum(x[2] for x in data) or 1
     print("\nhottest SASS instructions by samples:")
     for s, c, sm in sorted(data, key=lambda t: -t[2])[:12]:
@@ -54,4 +68,4 @@ def main(rep):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)
