@@ -91,7 +91,7 @@ int flowamok_step_quick(flowamok_context *ctx, flowamok_grid *g, int64_t n_ticks
 int flowamok_step_perfect(flowamok_context *ctx, flowamok_grid *g, int64_t n_ticks, int64_t *n_leaks);
 
 /* Like flowamok_step_*, but brackets every kernel of every tick with CUDA events on the context's stream
- * and returns the summed device time in milliseconds of {k_u_init, k_u_iter, k_rings, k_move}.  Synchronous;
+ * and returns the summed device time in milliseconds of {k_u_local, k_u_iter, k_rings, k_move}.  Synchronous;
  * n_ticks <= 4096.  Measurement aid for bench.py's roofline object, not a reference operator. */
 int flowamok_step_profile(flowamok_context *ctx, flowamok_grid *g, int perfect, int64_t n_ticks, double *ms);
 

@@ -1,5 +1,5 @@
 """world_size-2/3 gloo tests of the multi-GPU row-band path on the CPU: the product's BandRunner
-(flowamok_b200/bands.py) drives bands backed by the CPU emulation of the CUDA tile programs (tests/emul), each
+(flowamok_b200/bands.py) drives bands backed by the CPU emulation of the CUDA strip programs (tests/emul), each
 rank in its own process; the gathered result must equal the oracle's single-grid run bit for bit."""
 import ctypes as C
 import os

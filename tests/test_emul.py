@@ -1,5 +1,7 @@
-"""CPU checks of the product's bit-plane tile programs (flowamok_b200/csrc/fa_tiles.h, compiled for the
-host by tests/emul) against the oracle: same code the CUDA kernels run, every tick, full state."""
+"""CPU checks of the product's bit-plane programs (flowamok_b200/csrc/fa_stream.h and fa_tiles.h, compiled for the
+host by tests/emul; the warp programs run with their 32 lanes as coroutines) against the oracle: same code the CUDA
+kernels run, every tick, full state.  The variants change the strip width / height, the number of Jacobi levels, the
+k_move tile shape, the arrival-list capacity and the frontier visiting order."""
 import numpy as np
 import pytest
 

@@ -81,7 +81,7 @@ def assert_state_equal(a, b, what=""):
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU emulation of the tile programs
+# CPU emulation of the strip programs
 # ---------------------------------------------------------------------------------------------
 _EMUL_SRC = ROOT / "tests" / "emul" / "emul.cpp"
 _EMUL_SO = ROOT / "tests" / "emul" / "_build" / "libemul.so"
