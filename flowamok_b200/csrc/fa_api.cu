@@ -67,6 +67,7 @@ struct flowamok_grid {
   size_t nwords, ncells_p;  // plane words, pitched cells
   U4 *road, *head[2];
   u32 *pref[2], *calc, *color[2], *leak_plane;
+  unsigned char *dirty[2];   // per plane word: colour sectors that received a car in the last tick (lazy double buffer)
   u64 *mymx;
   u64 *rng;
   u64 rng_inc;
@@ -227,6 +228,7 @@ static int grid_new_impl(flowamok_context *ctx, flowamok_grid **out, int64_t gh_
     CU(cudaMalloc(&g->head[k], g->nwords * sizeof(U4)));
     CU(cudaMalloc(&g->pref[k], g->nwords * 4));
     CU(cudaMalloc(&g->color[k], g->ncells_p * 4));
+    CU(cudaMalloc(&g->dirty[k], g->nwords));
   }
   CU(cudaMalloc(&g->calc, g->nwords * 4));
   CU(cudaMalloc(&g->mymx, g->nwords * 8));
@@ -255,6 +257,7 @@ static int grid_new_impl(flowamok_context *ctx, flowamok_grid **out, int64_t gh_
     CU(cudaMemsetAsync(g->head[k], 0, g->nwords * sizeof(U4), st));
     CU(cudaMemsetAsync(g->pref[k], 0, g->nwords * 4, st));
     CU(cudaMemsetAsync(g->color[k], 0, g->ncells_p * 4, st));
+    CU(cudaMemsetAsync(g->dirty[k], 0, g->nwords, st));
   }
   CU(cudaMemsetAsync(g->calc, 0, g->nwords * 4, st));
   CU(cudaMemsetAsync(g->mymx, 0, g->nwords * 8, st));
@@ -266,10 +269,13 @@ static int grid_new_impl(flowamok_context *ctx, flowamok_grid **out, int64_t gh_
   return 0;
 }
 
-// After the colour plane of the current buffer was (re)written from outside, make the other buffer identical: the
-// lazy double buffer's invariant (k_move only rewrites the 32-byte sectors that hold a car or an arrival).
+// After the colour plane of the current buffer was (re)written from outside, make the other buffer identical and
+// forget the dirty sectors: the lazy double buffer's invariant (k_move only rewrites the 32-byte sectors that received a
+// car in this tick or the previous one).
 static int sync_color_buffers(flowamok_context *ctx, flowamok_grid *g) {
   CU(cudaMemcpyAsync(g->color[g->cur ^ 1], g->color[g->cur], g->ncells_p * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemsetAsync(g->dirty[0], 0, g->nwords, ctx->stream));
+  CU(cudaMemsetAsync(g->dirty[1], 0, g->nwords, ctx->stream));
   return 0;
 }
 
@@ -291,7 +297,7 @@ int flowamok_grid_free(flowamok_context *ctx, flowamok_grid *g) {
     cudaStreamSynchronize(ctx->stream);
   }
   cudaFree(g->road);
-  for (int k = 0; k < 2; k++) { cudaFree(g->head[k]); cudaFree(g->pref[k]); cudaFree(g->color[k]); }
+  for (int k = 0; k < 2; k++) { cudaFree(g->head[k]); cudaFree(g->pref[k]); cudaFree(g->color[k]); cudaFree(g->dirty[k]); }
   cudaFree(g->calc); cudaFree(g->mymx); cudaFree(g->rng); cudaFree(g->is); cudaFree(g->diag);
   for (int k = 0; k < 2; k++) { cudaFree(g->msg_s_send[k]); cudaFree(g->msg_s_recv[k]); cudaFree(g->msg_u_send[k]); cudaFree(g->msg_u_recv[k]); }
   cudaFree(g->d_woken); if (g->h_woken) cudaFreeHost(g->h_woken);
@@ -635,6 +641,7 @@ static GridView make_view(flowamok_grid *g) {
   v.pref_in = g->pref[g->cur]; v.pref_out = g->pref[g->cur ^ 1];
   v.calc = g->calc; v.mymx = g->mymx; v.ustate = g->ustate;
   v.color_in = g->color[g->cur]; v.color_out = g->color[g->cur ^ 1];
+  v.dirty_in = g->dirty[g->cur]; v.dirty_out = g->dirty[g->cur ^ 1];
   v.rng = g->rng; v.rng_inc = g->rng_inc;
   v.chooser = g->chooser;
   v.tape_bit = (g->chooser == CHOOSE_TAPE) ? (g->tape[(size_t)(g->tick % (long long)g->tape.size())] != 0) : 0u;

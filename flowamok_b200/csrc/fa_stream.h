@@ -264,8 +264,8 @@ struct UStrip {
 //
 //   phase A (one warp per strip, sliding window like UStrip): new car planes, next_preference_flow_x, per-cell RNG
 //            draws at forks, leak count -- and, per plane word, a 16-byte colour descriptor {T, A, V, S} in shared
-//            memory: T = cells whose 32-byte colour sector must be rewritten, A = arrival cells, V = arrival comes
-//            along y, S = the predecessor sits on the + side (row y+1 / column x+1).
+//            memory: T = which of the word's four 32-byte colour sectors phase B must copy, A = arrival cells,
+//            V = arrival comes along y, S = the predecessor sits on the + side (row y+1 / column x+1).
 //   phase B (all threads of the CTA, after a block barrier): the colour payload (steppers.fut:109).
 //            B0 scans the descriptors and compacts the touched sectors and the arrivals into two shared-memory lists;
 //            B1 copies the listed sectors color_in -> color_out, a lane pair per sector, eight independent 16-byte
@@ -273,10 +273,11 @@ struct UStrip {
 //            Dense lists keep every load slot useful: the phase is bound by memory latency, and the bytes in flight
 //            per SM (Little's law) are what sets its speed.  While one CTA waits in phase B, the others compute.
 //
-// LAZY double buffer.  Invariant at the start of a tick: color_out equals color_in everywhere except, possibly, at
-// cells that are occupied now (a car arrived there during the previous tick, when color_out was that tick's input).
-// So a sector of color_out is rewritten iff it holds an occupied cell or an arrival of this tick; all other sectors
-// are already right and cost no traffic.  An arrival reads color_in, which nobody writes during the tick.
+// LAZY double buffer.  Invariant at the start of a tick: color_out equals color_in everywhere except, possibly, in
+// the sectors where a car arrived during the previous tick, when color_out was that tick's input (dirty_in, one byte
+// per plane word).  So a sector of color_out is rewritten iff it received a car in this tick or the previous one; all
+// other sectors -- the empty road and every queue of standing cars -- are already right and cost no traffic.  An
+// arrival reads color_in, which nobody writes during the tick.
 // =============================================================================================
 template <int SW, int NWARP, int CAP = 2048>
 struct MTile {
@@ -287,7 +288,7 @@ struct MTile {
     u32 my, mx;
   };
   struct Aux {
-    u32 calc, pref;
+    u32 calc, pref, dirty;
   };
   // shared memory of one tile of `rs` rows (all offsets in 32-bit words)
   struct Smem {
@@ -319,10 +320,10 @@ struct MTile {
     }
   }
   FA_HD static void load_aux(const Env &E, int y, Aux &a) {
-    a.calc = 0u; a.pref = 0u;
+    a.calc = 0u; a.pref = 0u; a.dirty = 0u;
     if (E.col.owner && y < E.g.own1) {
       const u32 o = (u32)y * (u32)E.g.pitch + (u32)E.col.w;
-      a.calc = E.g.calc[o]; a.pref = E.g.pref_in[o];
+      a.calc = E.g.calc[o]; a.pref = E.g.pref_in[o]; a.dirty = E.g.dirty_in[o];
     }
   }
   FA_HD static void prefetch_row(const Env &E, int y) {
@@ -393,7 +394,10 @@ struct MTile {
       if (E.leak_plane) E.leak_plane[o] = out.leak;
       nleak += (unsigned int)popc32(out.leak);
       d.y = out.AY | out.AX;
-      d.x = d.y | c.head.x | c.head.z;
+      u32 arrS = 0u;   // the word's 32-byte colour sectors that receive a car (bit k = cells 8k .. 8k+7)
+      for (int k = 0; k < 4; k++) arrS |= ((d.y >> (8 * k)) & 0xFFu) ? (1u << k) : 0u;
+      g.dirty_out[o] = (unsigned char)arrS;
+      d.x = arrS | ax.dirty;   // sectors phase B1 copies: color_out is stale where last tick's cars arrived
       d.z = out.AY;
       d.w = (out.AY & p.UYS) | (out.AX & p.UXS);
     }
@@ -463,8 +467,7 @@ struct MTile {
       const U4 d = desc[idx];
       if (d.x == 0u) continue;
       const int row = idx / TW, wd = idx - row * TW;
-      u32 smk = 0u;
-      for (int k = 0; k < 4; k++) smk |= ((d.x >> (8 * k)) & 0xFFu) ? (1u << k) : 0u;
+      const u32 smk = d.x;
       u32 at = FA_ATOMIC_ADD_U32(&sm.cnt()[0], (u32)popc32(smk));
       for (int k = 0; k < 4; k++)
         if (smk & (1u << k)) sect[at++] = (unsigned short)(row * (TW * 4) + wd * 4 + k);

@@ -34,10 +34,13 @@ struct GridView {
   u32 *calc;               // per-tick plane `calculated` (steppers.fut:140-145 resets it: here it is scratch)
   u64 *mymx;               // per-tick planes direction.y (low word) / direction.x (high word), one 64-bit access
   u32 *ustate;             // per word: U_NONE, or its worklist entry index (| U_QUEUED while on the next list)
-  // colour payload [gh][pitch*32], LAZY double buffer (fa_stream.h, MStrip): color_out already equals color_in
-  // everywhere except at cells that are occupied now
+  // colour payload [gh][pitch*32], LAZY double buffer (fa_stream.h, MTile): color_out already equals color_in
+  // everywhere except in the 32-byte sectors that received a car during the previous tick (dirty_in: one byte per plane
+  // word, bit k = sector k); k_move records this tick's in dirty_out
   const u32 *color_in;
   u32 *color_out;
+  const unsigned char *dirty_in;
+  unsigned char *dirty_out;
   u64 *rng;                // [gh][pitch*32] pcg32 state of each cell (inc is shared, utils.fut:15)
   u64 rng_inc;
   int chooser;             // CHOOSE_*

@@ -29,6 +29,7 @@ struct HostGrid {
   int variant;
   std::vector<U4> road, head[2];
   std::vector<u32> pref[2], calc, color[2], ustate;
+  std::vector<unsigned char> dirty[2];
   std::vector<u64> mymx, rng;
   u64 rng_inc = 0;
   int cur = 0;
@@ -49,7 +50,7 @@ HostGrid *make(int gh_global, int gw, int row_begin, int row_end, int halo, int 
   h->pitch = ((h->wvalid + 3) / 4) * 4;
   size_t nw = (size_t)h->gh * h->pitch, nc = nw * 32;
   h->road.assign(nw, U4{0, 0, 0, 0});
-  for (int k = 0; k < 2; k++) { h->head[k].assign(nw, U4{0, 0, 0, 0}); h->pref[k].assign(nw, 0); h->color[k].assign(nc, 0); }
+  for (int k = 0; k < 2; k++) { h->head[k].assign(nw, U4{0, 0, 0, 0}); h->pref[k].assign(nw, 0); h->color[k].assign(nc, 0); h->dirty[k].assign(nw, 0); }
   h->calc.assign(nw, 0); h->mymx.assign(nw, 0); h->ustate.assign(nw, U_NONE);
   h->rng.assign(nc, 0);
   return h;
@@ -64,6 +65,7 @@ GridView view(HostGrid *h, int chooser, u32 tape_bit) {
   g.pref_in = h->pref[h->cur].data(); g.pref_out = h->pref[h->cur ^ 1].data();
   g.calc = h->calc.data(); g.mymx = h->mymx.data(); g.ustate = h->ustate.data();
   g.color_in = h->color[h->cur].data(); g.color_out = h->color[h->cur ^ 1].data();
+  g.dirty_in = h->dirty[h->cur].data(); g.dirty_out = h->dirty[h->cur ^ 1].data();
   g.rng = h->rng.data(); g.rng_inc = h->rng_inc;
   g.chooser = chooser; g.tape_bit = tape_bit;
   return g;
@@ -223,7 +225,8 @@ void emul_upload(void *p, const int8_t *uy, const int8_t *ux, const int8_t *dy, 
     }
   }
   h->rng_inc = rng_inc;
-  h->color[h->cur ^ 1] = h->color[h->cur];   // lazy double buffer: both identical
+  h->color[h->cur ^ 1] = h->color[h->cur];   // lazy double buffer: both identical, nothing dirty
+  for (int k = 0; k < 2; k++) std::fill(h->dirty[k].begin(), h->dirty[k].end(), 0);
 }
 
 // writes the OWNED rows into whole-grid arrays
