@@ -88,20 +88,26 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_run(size_w, rows, ticks, warm, threads=None):
+def cpu_oracle_run(size_w, rows, ticks, warm, threads=None, perfect=False):
     """The oracle port (reference layout: record of arrays, one full-grid Jacobi pass per fixpoint iteration,
     count-based termination exactly as steppers.fut:160-163) on a band of the same synthetic network."""
     from oracle import oracle as O
     if threads:
         O.set_threads(threads)
     g = O.Grid(rows, size_w)
-    g.generate_synthetic(seed=1)
+    rings = g.generate_synthetic(seed=1)
     ch = O.Chooser(O.CHOOSE_RANDOM)
+
+    def tick():
+        if perfect:
+            g.step_perfect_sparse(ch, rings)
+        else:
+            g.step_quick(ch)
     for _ in range(warm):
-        g.step_quick(ch)
+        tick()
     t0 = time.perf_counter()
     for _ in range(ticks):
-        g.step_quick(ch)
+        tick()
     dt = time.perf_counter() - t0
     return rows * size_w * ticks / dt / 1e9, dt, O.max_threads()
 
@@ -111,18 +117,19 @@ def run_reference(args, rank):
         return 0
     size = args.size
     # calibrate on a thin band, then size the band so that (steps + warmup) ticks take about a minute
-    g1, dt1, thr = cpu_oracle_run(size, 64, 2, 1)
+    perfect = args.mode == "perfect"
+    g1, dt1, thr = cpu_oracle_run(size, 64, 2, 1, perfect=perfect)
     per_cell_tick = dt1 / (64 * size * 2)
     budget = 60.0
     rows = int(budget / (per_cell_tick * size * max(1, args.steps + args.warmup)))
     rows = max(32, min(size, (rows // 16) * 16))
-    gcups, dt, thr = cpu_oracle_run(size, rows, args.steps, args.warmup)
-    sample = f"{rows}x{size} band of the synthetic-{size} network, {args.steps} ticks, quick mode"
+    gcups, dt, thr = cpu_oracle_run(size, rows, args.steps, args.warmup, perfect=perfect)
+    sample = f"{rows}x{size} band of the synthetic-{size} network, {args.steps} ticks, {args.mode} mode"
     line = {"impl": "reference", "metric": "cell-updates/sec", "value": gcups, "unit": "GCUPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"synthetic-{size}x{size}-quick (SURVEY App. E, seed 1, 10% of road cells occupied)",
-                       "sample": sample},
+            "config": {"workload": f"synthetic-{size}x{size}-{args.mode} (SURVEY App. E, seed 1, 10% of road cells occupied)",
+                       "grid": [size, size], "mode": args.mode, "sample": sample},
             "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": thr, "kind": "port", "sample": sample},
             "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference is pure Futhark; no Futhark compiler in the image, so this is the C/OpenMP oracle port "
@@ -319,12 +326,12 @@ def main():
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(gpu_launches), "e2e": e2e}
     if rank == 0 and not args.no_cpu:
         try:
-            g1, dt1, thr = cpu_oracle_run(S, 64, 2, 1)
+            g1, dt1, thr = cpu_oracle_run(S, 64, 2, 1, perfect=perfect)
             rows_c = int(15.0 / (dt1 / (64 * S * 2) * S * 6))
             rows_c = max(32, min(S, (rows_c // 16) * 16))
-            gc, dt, thr = cpu_oracle_run(S, rows_c, 5, 1)
+            gc, dt, thr = cpu_oracle_run(S, rows_c, 5, 1, perfect=perfect)
             line["cpu_baseline"] = {"value": gc, "unit": "GCUPS", "cores": thr, "kind": "port",
-                                    "sample": f"{rows_c}x{S} band of the same network, 5 ticks, quick mode, {dt:.1f} s"}
+                                    "sample": f"{rows_c}x{S} band of the same network, 5 ticks, {args.mode} mode, {dt:.1f} s"}
         except Exception as e:  # the oracle is only a reported baseline
             line["cpu_baseline"] = {"value": None, "unit": "GCUPS", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
     if rank == 0:
