@@ -23,6 +23,12 @@
 #ifndef FA_M_AHEAD
 #define FA_M_AHEAD 6
 #endif
+#ifndef FA_B1_UN
+#define FA_B1_UN 8
+#endif
+#ifndef FA_B2_UN
+#define FA_B2_UN 8
+#endif
 
 namespace fa {
 
@@ -487,7 +493,7 @@ struct MTile {
   FA_HD static void phaseB1(const GridView &g, Smem sm, int tsx, int ya, int tid, int nt) {
     const unsigned short *sect = sm.sect();
     const int ns = (int)sm.cnt()[0], half = tid & 1, np = nt >> 1;
-    constexpr int UN = 8;
+    constexpr int UN = FA_B1_UN;
     for (int e0 = tid >> 1; e0 < ns; e0 += np * UN) {
       U4 v[UN];
       size_t off[UN];
@@ -514,7 +520,7 @@ struct MTile {
     const int na = (int)sm.cnt()[1];
     if (na <= ARR_CAP) {
       const u32 *arrl = sm.arrl();
-      constexpr int UN = 8;   // independent gathers in flight per thread
+      constexpr int UN = FA_B2_UN;   // independent gathers in flight per thread
       for (int a0 = tid; a0 < na; a0 += nt * UN) {
         u32 v[UN];
         size_t dst[UN];
