@@ -208,6 +208,13 @@ FA_HD int u_iter_entry(const GridView &g, const UEntry &e, u32 idx, u32 *push) {
   const u32 valid = edge_of(g, y, w).valid;
   UState n = u_relax(st, R_up, R_c, R_dn, MY_up, MY_dn, MX_c, MX_up, MX_dn);
   n.R = (n.R & valid) | c.R; n.MY = (n.MY & valid) | c.MY; n.MX = (n.MX & valid) | c.MX;   // monotone
+  // cars queued along x inside this word wait on cells of the word itself: relax again on the word's own new values
+  // (a few ALU operations) instead of one more grid-wide iteration per car
+  for (int again = 0; again < 4 && (n.R != R_c.c || n.MX != MX_c.c); again++) {
+    R_c.c = n.R; MX_c.c = n.MX;
+    const UState m = u_relax(st, R_up, R_c, R_dn, MY_up, MY_dn, MX_c, MX_up, MX_dn);
+    n.R |= m.R & valid; n.MY |= m.MY & valid; n.MX |= m.MX & valid;
+  }
   const u32 chg = (n.R ^ c.R) | (n.MY ^ c.MY) | (n.MX ^ c.MX);
   bool unready = (~n.R & ~e.T) != 0u;
   int np = 0;
