@@ -219,6 +219,26 @@ def test_synthetic_network_vs_oracle(ctx, perfect):
             assert_state_equal(state_of(og), dev_state(g), f"perfect={perfect} tick {t}")
 
 
+@pytest.mark.parametrize("perfect", [False, True])
+def test_1000_ticks_vs_oracle(ctx, perfect):
+    """north_star: bit-identical grids after 1000 ticks -- the synthetic network at a size the oracle steps 1000 times
+    in seconds, whole state compared at ticks 100 and 1000 (leak counts on the way), batched stepping on the device"""
+    gh, gw = 272, 1100
+    arrs, rings = synth_ref.generate(gh, gw, seed=3)
+    g = ctx.grid(gh, gw)
+    g.generate_synthetic(seed=3)
+    og, ch = oracle_grid(arrs), O.Chooser(O.CHOOSE_RANDOM)
+    done = 0
+    for stop in (100, 1000):
+        leaks = 0
+        for _ in range(stop - done):
+            nl, _ = og.step_perfect_sparse(ch, rings) if perfect else og.step_quick(ch)
+            leaks += nl
+        assert g.step(perfect, stop - done) == leaks, f"leaks up to tick {stop}"
+        done = stop
+        assert_state_equal(state_of(og), dev_state(g), f"perfect={perfect} tick {stop}")
+
+
 def _plane_digest(g):
     d = g.download(fields=("dy", "dx", "color", "pref"))
     h = hashlib.sha256()
