@@ -236,9 +236,10 @@ __global__ void k_band_pack_u(int pitch, int own0, int own1, const u32 *calc, co
   reinterpret_cast<u32 *>(b)[w] = calc[o];
   reinterpret_cast<u64 *>(b + (size_t)pitch * 4)[w] = mymx[o];
 }
-// OR the neighbour's boundary row (calc, my|mx) into the ghost row; wake the owned words next to every word that
-// changed (their waiting cars may point into it).  One thread per word and side.
-__global__ void k_band_merge(const __grid_constant__ GridView g, BandBufs bufs, int wake, unsigned int *qlist1, IterState *is) {
+// OR the neighbour's boundary row (calc, my|mx) into the ghost row; wake the owned words that hold a waiting car which
+// reads a changed cell.  One thread per word and side.
+__global__ void k_band_merge(const __grid_constant__ GridView g, BandBufs bufs, int wake, const UEntry *table, unsigned int *qlist1,
+                             IterState *is) {
   const int side = blockIdx.y;
   const char *b = bufs.buf[side];
   if (!b) return;
@@ -254,7 +255,9 @@ __global__ void k_band_merge(const __grid_constant__ GridView g, BandBufs bufs, 
   g.mymx[o] = nm;
   g.calc[o] = nc;
   if (!wake) return;
+  const u32 chg = (oc ^ nc) | (u32)(om ^ nm) | (u32)((om ^ nm) >> 32);
   for (int dx = -1; dx <= 1; dx++) {
+    if (!band_word_reads_ghost(g, table, side, own_row, w, dx, chg)) continue;
     u32 q = u_try_queue(g, own_row, w + dx);
     if (q != U_NONE) qlist1[atomicAdd(&is->qn[1], 1u)] = q & ~U_QUEUED;
   }

@@ -162,6 +162,32 @@ FA_HD u32 u_try_queue(const GridView &g, int y, int w) {
   return old;
 }
 
+// Row bands: the state of ghost word wg (the neighbour band's boundary row; side 0: the row above the band, side 1:
+// the row below) changed at the cells `chg`.  Does owned word wg + dx of the adjacent owned row hold a waiting car that
+// reads one of them?  Only cars heading towards the ghost row do: straight ones read the same bit of the same word,
+// diagonal ones the bit beside it (possibly in the next word).  Everything else in the row is unaffected by the
+// neighbour band -- waking it anyway would cost every tick one more convergence round of the band protocol.
+FA_HD bool band_word_reads_ghost(const GridView &g, const UEntry *table, int side, int own_row, int wg, int dx, u32 chg) {
+  const int w = wg + dx;
+  if (w < 0 || w >= g.pitch) return false;
+  const size_t o = (size_t)own_row * g.pitch + w;
+#if defined(__CUDA_ARCH__)
+  const u32 sv = *(volatile const u32 *)&g.ustate[o];
+#else
+  const u32 sv = g.ustate[o];
+#endif
+  if (sv == U_NONE) return false;   // no unresolved waiting car in the word
+  const U4 hd = g.head_in[o];
+  const Heading h = heading(hd.x, hd.y, hd.z, hd.w);
+  const u32 link = ~table[o].T;
+  const u32 straight = link & (side == 0 ? h.cN : h.cS);
+  const u32 dl = link & (side == 0 ? h.dNW : h.dSW);   // reads the ghost cell at x - 1
+  const u32 dr = link & (side == 0 ? h.dNE : h.dSE);   // reads the ghost cell at x + 1
+  if (dx == 0) return ((straight & chg) | (dl & (chg << 1)) | (dr & (chg >> 1))) != 0u;
+  if (dx == 1) return (dl & 1u & (chg >> 31)) != 0u;    // my first cell looks at the ghost word's last cell
+  return ((dr >> 31) & chg & 1u) != 0u;                 // my last cell looks at the ghost word's first cell
+}
+
 // One relaxation of worklist entry `e` against the current planes (frontier discipline):
 //   clear QUEUED, re-read the neighbourhood, OR the new facts in (my/mx before calc);
 //   if anything changed, wake the neighbouring words whose waiting cars may point at a changed cell (the words above

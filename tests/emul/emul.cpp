@@ -326,9 +326,11 @@ int64_t emul_band_merge_u(void *p, int side, const void *buf, int wake) {  // k_
     u32 nc = h->calc[o] | rc[w];
     u64 nm = h->mymx[o] | rm[w];
     if (nc == h->calc[o] && nm == h->mymx[o]) continue;
+    const u32 chg = (h->calc[o] ^ nc) | (u32)(h->mymx[o] ^ nm) | (u32)((h->mymx[o] ^ nm) >> 32);
     h->mymx[o] = nm; h->calc[o] = nc;
     if (!wake) continue;
     for (int dx = -1; dx <= 1; dx++) {
+      if (!band_word_reads_ghost(g, h->table.data(), side, own, w, dx, chg)) continue;
       u32 q = u_try_queue(g, own, w + dx);
       if (q != U_NONE) h->frontier.push_back(q & ~U_QUEUED);
     }
