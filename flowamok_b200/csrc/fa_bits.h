@@ -159,14 +159,13 @@ FA_HD UState u_relax_card(const UStatic &s, u32 R_up, const W3 &R, u32 R_dn, u32
   return o;
 }
 
-// next_preference_flow_x after the fixpoint (:41-50): only road cells that were calculated AND free
-// re-arbitrate; ring resolution (:189-224) never touches it.
-FA_HD u32 u_pref_next(u32 roadc, u32 PREF, const UState &f, const UStatic &s) {
-  // free cell <=> f.R and base; on a road cell MY|MX can both be 0 while free (nobody upstream), in
-  // which case pref stays (:47).  MY=1 -> 1 (:44,:45), MX=1 -> 0 (:43,:46).
-  (void)s;
-  u32 upd = roadc & (f.MY | f.MX);
-  return (~upd & PREF) | (upd & f.MY);
+// next_preference_flow_x after the fixpoint (:41-50): only road cells that were calculated AND free re-arbitrate;
+// ring resolution (:189-224) never touches it.  On a road cell my and mx exclude each other and MY | MX can both be 0
+// while free (nobody upstream), in which case pref stays (:47); MY=1 -> 1 (:44,:45), MX=1 -> 0 (:43,:46).  A cell has
+// a road iff its static grants GYr and GXr are not both set (u_statics: a cell without road accepts from both axes).
+FA_HD u32 u_pref_from_grants(u32 GYr, u32 GXr, u32 PREF, u32 MY, u32 MX) {
+  u32 upd = ~(GYr & GXr) & (MY | MX);
+  return (~upd & PREF) | (upd & MY);
 }
 
 // ---------------------------------------------------------------------------------------------

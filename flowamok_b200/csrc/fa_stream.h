@@ -23,6 +23,9 @@
 #ifndef FA_M_AHEAD
 #define FA_M_AHEAD 6
 #endif
+#ifndef FA_M_PF_AUX
+#define FA_M_PF_AUX 1
+#endif
 #ifndef FA_B1_UN
 #define FA_B1_UN 8
 #endif
@@ -142,7 +145,7 @@ struct UStrip {
   // Rows outside the grid hold zeros and produce values nobody reads (a car heading out of the grid is a terminal).
   template <int P>
   FA_HD static void step(const Env &E, int j, const Raw &rA, const Raw &rB, u32 &roadc2, u32 &dyn2, Stat (&S)[K + 2],
-                         UState (&Lv)[K + 1][3], u32 &nq) {
+                         UState (&Lv)[K + 1][3], u32 &nq, u32 &prefD) {
     constexpr int N = (3 - P) % 3, M = (N + 1) % 3, O = (N + 2) % 3;
     const GridView &g = E.g;
     const u32 valid = E.col.colValid;
@@ -206,6 +209,9 @@ struct UStrip {
       if (E.col.owner && y >= E.ya && y < E.yb) {
         g.mymx[o] = pack_mymx(pub.MY, pub.MX);
         g.calc[o] = pub.R;
+        // next_preference_flow_x (steppers.fut:41-50) as far as the grants are known now; k_u_iter rewrites the words
+        // it changes.  prefD = the row's pref, re-read one step ago (it left the registers K + 2 steps ago).
+        g.pref_out[o] = u_pref_from_grants(sO.GY, sO.GX, prefD, pub.MY, pub.MX) & valid;
         u32 us = U_NONE;
         if (unresolved) {
           front = nR != pub.R || (sO.DG & unresolved) != 0u || (BAND && (y == g.own0 || y == g.own1 - 1));
@@ -219,6 +225,9 @@ struct UStrip {
       const u32 fm = simt_ballot(front);
       if (front) E.qseg[nq + (u32)popc32(fm & ((1u << E.lane) - 1u))] = o;
       nq += (u32)popc32(fm);
+      // the next step publishes row y + 1
+      prefD = 0u;
+      if (E.col.owner && y + 1 >= E.ya && y + 1 < E.yb) prefD = g.pref_in[o + (u32)g.pitch];
     }
   }
 
@@ -233,7 +242,7 @@ struct UStrip {
     const int j0 = ya - K - 1, jend = yb + K + 1;   // the step at jend publishes row yb-1
     Raw R0, R1, R2;
     load_raw(E, j0 - 1, R0); load_raw(E, j0, R1); load_raw(E, j0 + 1, R2);
-    u32 roadc2 = 0u, dyn2 = 0u, nq = 0u;
+    u32 roadc2 = 0u, dyn2 = 0u, nq = 0u, prefD = 0u;
     Stat S[K + 2];
     UState Lv[K + 1][3];
     {
@@ -247,11 +256,11 @@ struct UStrip {
     for (int y = j0 + 2; y < j0 + 2 + AHEAD; y++) prefetch_raw(E, y);
     // the last one or two steps of the last trip may run past jend: they publish nothing (the stores check y < yb)
     for (int j = j0; j <= jend; j += 3) {
-      step<0>(E, j, R0, R1, roadc2, dyn2, S, Lv, nq);
+      step<0>(E, j, R0, R1, roadc2, dyn2, S, Lv, nq, prefD);
       load_raw(E, j + 2, R0); prefetch_raw(E, j + 2 + AHEAD);
-      step<1>(E, j + 1, R1, R2, roadc2, dyn2, S, Lv, nq);
+      step<1>(E, j + 1, R1, R2, roadc2, dyn2, S, Lv, nq, prefD);
       load_raw(E, j + 3, R1); prefetch_raw(E, j + 3 + AHEAD);
-      step<2>(E, j + 2, R2, R0, roadc2, dyn2, S, Lv, nq);
+      step<2>(E, j + 2, R2, R0, roadc2, dyn2, S, Lv, nq, prefD);
       load_raw(E, j + 4, R2); prefetch_raw(E, j + 4 + AHEAD);
     }
     // ---- append the strip's frontier to the device-wide list: one atomic per strip
@@ -268,8 +277,8 @@ struct UStrip {
 // =============================================================================================
 // M tile: move_cell + reset_cells (steppers.fut:58-145).  A CTA of NWARP warps takes NWARP strips side by side.
 //
-//   phase A (one warp per strip, sliding window like UStrip): new car planes, next_preference_flow_x, per-cell RNG
-//            draws at forks, leak count -- and, per plane word, a 16-byte colour descriptor {T, A, V, S} in shared
+//   phase A (one warp per strip, sliding window like UStrip): new car planes, per-cell RNG draws at forks, leak
+//            count -- and, per plane word, a 16-byte colour descriptor {T, A, V, S} in shared
 //            memory: T = which of the word's four 32-byte colour sectors phase B must copy, A = arrival cells,
 //            V = arrival comes along y, S = the predecessor sits on the + side (row y+1 / column x+1).
 //   phase B (all threads of the CTA, after a block barrier): the colour payload (steppers.fut:109).
@@ -294,7 +303,7 @@ struct MTile {
     u32 my, mx;
   };
   struct Aux {
-    u32 calc, pref, dirty;
+    u32 dirty;
   };
   // shared memory of one tile of `rs` rows (all offsets in 32-bit words)
   struct Smem {
@@ -326,18 +335,14 @@ struct MTile {
     }
   }
   FA_HD static void load_aux(const Env &E, int y, Aux &a) {
-    a.calc = 0u; a.pref = 0u; a.dirty = 0u;
-    if (E.col.owner && y < E.g.own1) {
-      const u32 o = (u32)y * (u32)E.g.pitch + (u32)E.col.w;
-      a.calc = E.g.calc[o]; a.pref = E.g.pref_in[o]; a.dirty = E.g.dirty_in[o];
-    }
+    a.dirty = 0u;
+    if (E.col.owner && y < E.g.own1) a.dirty = E.g.dirty_in[(u32)y * (u32)E.g.pitch + (u32)E.col.w];
   }
   FA_HD static void prefetch_row(const Env &E, int y) {
     if (FA_M_AHEAD > 0 && E.col.w_ok && y >= E.ylo && y < E.yhi) {
       const u32 o = (u32)y * (u32)E.g.pitch + (u32)E.col.w;
       fa_prefetch_l2(&E.g.road[o]); fa_prefetch_l2(&E.g.head_in[o]);
       if ((E.lane & 3) == 1) fa_prefetch_l2(&E.g.mymx[o]);
-      if ((E.lane & 7) == 1) { fa_prefetch_l2(&E.g.calc[o]); fa_prefetch_l2(&E.g.pref_in[o]); }
     }
   }
   FA_HD static MRow side_row(const Row &q, bool diag) {
@@ -351,7 +356,7 @@ struct MTile {
     return m;
   }
 
-  // one owned row y: up / c / dn = rows y-1, y, y+1; ax = calc and pref of row y; live = false: a padding step past
+  // one owned row y: up / c / dn = rows y-1, y, y+1; ax = the row's dirty colour sectors; live = false: a padding step past
   // the strip's last row (warp-uniform), which must not store anything
   FA_HD static void step(const Env &E, int y, bool live, const Row &up, const Row &c, const Row &dn, const Aux &ax, unsigned int &nleak) {
     const GridView &g = E.g;
@@ -390,11 +395,6 @@ struct MTile {
         }
       }
       const MOut out = m_post(p, CH);
-      // next_preference_flow_x (steppers.fut:41-50): decided by the fixpoint's own grants only; cells a ring
-      // resolution marked (steppers.fut:189-224) have calc = 0 and keep their preference
-      const UState f = {ax.calc, c.my & ax.calc, c.mx & ax.calc};
-      const UStatic dummy = {};
-      g.pref_out[o] = u_pref_next(c.road.x | c.road.z, ax.pref, f, dummy) & e.valid;
       const U4 hd = {out.DYN, out.DYS, out.DXN, out.DXS};
       g.head_out[o] = hd;
       if (E.leak_plane) E.leak_plane[o] = out.leak;

@@ -201,6 +201,7 @@ template <bool CTA = false>
 FA_HD int u_iter_entry(const GridView &g, const UEntry &e, u32 idx, u32 *push) {
   const int y = (int)(e.wi / (u32)g.pitch), w = (int)(e.wi - (u32)y * (u32)g.pitch);
   const U4 hd = g.head_in[e.wi];   // static during the fixpoint: no ordering needed
+  const u32 pref = g.pref_in[e.wi];
   FA_ATOMIC_AND_U32(&g.ustate[e.wi], ~U_QUEUED);
   fa_fence<CTA>();
   Heading h = heading(hd.x, hd.y, hd.z, hd.w);
@@ -245,6 +246,8 @@ FA_HD int u_iter_entry(const GridView &g, const UEntry &e, u32 idx, u32 *push) {
   bool unready = (~n.R & ~e.T) != 0u;
   int np = 0;
   if (chg) {
+    // next_preference_flow_x follows the grants (k_u_local wrote it for the grants it knew); one visitor per word
+    g.pref_out[e.wi] = u_pref_from_grants(e.GY, e.GX, pref, n.MY, n.MX) & valid;
     FA_ATOMIC_OR_U64(&g.mymx[e.wi], pack_mymx(n.MY, n.MX));
     fa_fence<CTA>();
     FA_ATOMIC_OR_U32(&g.calc[e.wi], n.R);
