@@ -29,7 +29,7 @@ B_ALG = 12.0  # algorithmic bytes per cell-update (SURVEY 8d / BASELINE.md): r+w
 # DRAM bytes per launch at BASELINE config 4 (16384^2, quick), dram__bytes_read.sum + dram__bytes_write.sum of one
 # `ncu --set full` capture per kernel (profiles/r01_k_*.txt).  Below the algorithmic 3.22 GB per tick: the colour payload
 # goes through a lazy double buffer, only the 32-byte sectors that hold a car are rewritten.
-NCU_TRAFFIC_16384_QUICK = {"k_u_local": 0.511e9, "k_u_iter": 0.008e9, "k_move": 1.457e9}
+NCU_TRAFFIC_16384_QUICK = {"k_u_local": 0.543e9, "k_u_iter": 0.008e9, "k_move": 1.342e9}
 
 
 def measured_peak():
