@@ -4,10 +4,12 @@
 // 1..SW own SW consecutive words (32*SW cells) and lanes 0 and SW+1 carry the neighbouring words read-only.  A row's
 // x-neighbours are one warp shuffle away, its y-neighbours are the previous / next row, which the lane itself still
 // holds in registers (sliding window): every plane word is loaded once per strip with fully coalesced 128-bit
-// accesses, nothing is staged in shared memory and there is no block barrier.  The bit logic is the one of fa_bits.h.
+// accesses (requested into L2 a few rows ahead), the control planes are never staged in shared memory and the strip
+// loop has no block barrier.  The bit logic is the one of fa_bits.h.
 //
-//   UStrip : update_can_be_moved_to_from (steppers.fut:9-56), first two Jacobi levels of the fixpoint (:147-164) in a
-//            three-stage row pipeline, publication of calc / my|mx, and the worklist entries + frontier for k_u_iter.
+//   UStrip : update_can_be_moved_to_from (steppers.fut:9-56), the first K Jacobi levels of the fixpoint (:147-164) in a
+//            K + 2 stage row pipeline, publication of calc / my|mx / next_preference_flow_x, and the worklist entries +
+//            frontier for k_u_iter.
 //   MTile  : move_cell + reset_cells (steppers.fut:58-145), per-cell RNG draws at forks, leak count (phase A, a warp
 //            per strip) and the colour payload through the lazy double buffer (phase B, the whole CTA).
 //
@@ -17,14 +19,12 @@
 #include "fa_simt.h"
 #include "fa_tiles.h"
 
+// tuning knobs (rows between the L2 prefetch and the register load of a row; loads in flight per thread in phase B)
 #ifndef FA_U_AHEAD
 #define FA_U_AHEAD 6
 #endif
 #ifndef FA_M_AHEAD
 #define FA_M_AHEAD 6
-#endif
-#ifndef FA_M_PF_AUX
-#define FA_M_PF_AUX 1
 #endif
 #ifndef FA_B1_UN
 #define FA_B1_UN 8
@@ -51,16 +51,6 @@ FA_HD StripCol strip_col(const GridView &g, int sx, int lane) {
   Edge e = edge_masks(0, c.w, 1, g.gw);
   c.colFirst = e.colFirst; c.colLast = e.colLast; c.colValid = c.w_ok ? e.valid : 0u;
   return c;
-}
-// Edge of (local row y, this lane's word); rows outside the global grid have no valid cell
-FA_HD Edge strip_edge(const GridView &g, const StripCol &c, int y) {
-  Edge e;
-  const int yg = y + g.row0;
-  e.rowFirst = (yg == 0) ? 0xFFFFFFFFu : 0u;
-  e.rowLast = (yg == g.gh_global - 1) ? 0xFFFFFFFFu : 0u;
-  e.colFirst = c.colFirst; e.colLast = c.colLast;
-  e.valid = row_in(g, y) ? c.colValid : 0u;
-  return e;
 }
 FA_HD W3 simt_w3(u32 v) {
   W3 r;
