@@ -22,6 +22,17 @@ def test_quick_random_grids(variant):
             assert_state_equal(state_of(og), eg.state(), f"{gh}x{gw} variant {variant} tick {t}")
 
 
+def test_wide_grid_crosses_strip_and_tile_borders():
+    """production strip shape on a grid wider than two strips (30 plane words each) and than one k_move tile: the
+    halo lanes, the tile-wide colour lists and the per-strip frontier staging all see a neighbour"""
+    arrs = random_grid(21, 40, 2300, n_lines=500, car_p=0.5)
+    og, eg, ch = oracle_grid(arrs), EmulGrid(arrs), O.Chooser(O.CHOOSE_RANDOM)
+    for t in range(5):
+        nl, _ = og.step_quick(ch)
+        assert nl == eg.step(variant=0)
+        assert_state_equal(state_of(og), eg.state(), f"tick {t}")
+
+
 def test_dense_jam_needs_many_passes():
     arrs = random_grid(7, 64, 100, car_p=0.9, weird_p=0.0, offroad_p=0.0)
     og, eg, ch = oracle_grid(arrs), EmulGrid(arrs), O.Chooser(O.CHOOSE_RANDOM)
