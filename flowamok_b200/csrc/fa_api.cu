@@ -528,7 +528,7 @@ struct Path {
 int flowamok_find_cycles(flowamok_context *ctx, flowamok_grid *g, int64_t max_paths, int64_t *n_cycles) {
   if (!g) return fail(ctx, "null grid");
   if (max_paths <= 0) max_paths = 1 << 16;
-  if (g->gh != g->gh_global) return fail(ctx, "find_cycles needs the whole grid (not available on a row band)");
+  if (g->halo != 0) return fail(ctx, "find_cycles needs the whole grid (not available on a row band)");
   const int64_t gh = g->gh, gw = g->gw;
   std::vector<int8_t> uy((size_t)gh * gw), ux((size_t)gh * gw);
   if (flowamok_grid_download(ctx, g, uy.data(), ux.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr)) return 1;
@@ -650,7 +650,7 @@ static GridView make_view(flowamok_grid *g) {
 
 static int launch_u_init(flowamok_context *ctx, flowamok_grid *g, const GridView &v) {
   const unsigned int nb = nblk((long long)g->nsx * g->nsy, STRIP_THREADS / 32);
-  if (g->gh != g->gh_global)   // a row band: ghost rows, boundary rows always on the frontier
+  if (g->halo != 0)   // a row band: ghost rows, boundary rows always on the frontier
     k_u_local<true><<<nb, STRIP_THREADS, 0, ctx->stream>>>(v, g->nsx, g->nsy, g->rs, g->table, g->qlist[0], g->qlist[1], g->is);
   else
     k_u_local<false><<<nb, STRIP_THREADS, 0, ctx->stream>>>(v, g->nsx, g->nsy, g->rs, g->table, g->qlist[0], g->qlist[1], g->is);
@@ -681,7 +681,7 @@ static int launch_move(flowamok_context *ctx, flowamok_grid *g, const GridView &
 }
 
 static int enqueue_tick(flowamok_context *ctx, flowamok_grid *g, bool perfect, u32 *leak_plane, cudaEvent_t *ev = nullptr) {
-  if (g->gh != g->gh_global) return fail(ctx, "a row band is stepped with the flowamok_band_* calls");
+  if (g->halo != 0) return fail(ctx, "a row band is stepped with the flowamok_band_* calls");
   cudaStream_t st = ctx->stream;
   GridView v = make_view(g);
   if (ev) CU(cudaEventRecord(ev[0], st));
@@ -796,7 +796,7 @@ int flowamok_step_leaks(flowamok_context *ctx, flowamok_grid *g, int perfect, in
 int flowamok_render(flowamok_context *ctx, const flowamok_grid *g, int64_t scale, uint32_t *pixels) {
   if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
   if (!g || scale < 1) return fail(ctx, "bad render arguments");
-  if (g->gh != g->gh_global) return fail(ctx, "render needs the whole grid (not available on a row band)");
+  if (g->halo != 0) return fail(ctx, "render needs the whole grid (not available on a row band)");
   CU(cudaSetDevice(ctx->device));
   long long n = (long long)g->gh * scale * g->gw * scale;
   u32 *d = nullptr;

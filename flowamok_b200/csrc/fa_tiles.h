@@ -23,7 +23,8 @@ struct GridView {
   int gh, gw;        // rows held in this device's planes (a band plus its halo rows) / cells per row
   int pitch;         // words per plane row (multiple of 4 -> 16-byte aligned rows)
   int wvalid;        // ceil(gw / 32): words that hold cells
-  int gh_global;     // rows of the whole grid (== gh on a single GPU)
+  int gh_global;     // rows of the whole grid (a band is recognised by its halo rows, never by gh != gh_global:
+                     // a band's rows plus its halo rows can add up to exactly the grid's height)
   int row0;          // global row of local row 0 (0 on a single GPU; -halo for the first band)
   int own0, own1;    // local rows [own0, own1) are owned (stepped and written) by this device
   const U4 *road;    // {UYN, UYS, UXN, UXS} per word                       [gh][pitch]
@@ -170,6 +171,9 @@ FA_HD u32 u_try_queue(const GridView &g, int y, int w) {
 FA_HD bool band_word_reads_ghost(const GridView &g, const UEntry *table, int side, int own_row, int wg, int dx, u32 chg) {
   const int w = wg + dx;
   if (w < 0 || w >= g.pitch) return false;
+#ifdef FA_BAND_WAKE_ALL
+  return true;
+#endif
   const size_t o = (size_t)own_row * g.pitch + w;
 #if defined(__CUDA_ARCH__)
   const u32 sv = *(volatile const u32 *)&g.ustate[o];

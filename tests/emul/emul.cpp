@@ -77,7 +77,7 @@ struct UArgs { HostGrid *h; const GridView *g; int sx, ya, yb; unsigned int qn; 
 template <int SW, int K>
 void u_lane(void *p, int lane) {
   UArgs<SW, K> *a = (UArgs<SW, K> *)p;
-  if (a->g->gh != a->g->gh_global) UStrip<SW, K, true>::run(*a->g, a->sx, a->ya, a->yb, lane, a->h->table.data(), a->qs->data(), a->ql->data(), &a->qn);
+  if (a->h->halo != 0) UStrip<SW, K, true>::run(*a->g, a->sx, a->ya, a->yb, lane, a->h->table.data(), a->qs->data(), a->ql->data(), &a->qn);
   else UStrip<SW, K, false>::run(*a->g, a->sx, a->ya, a->yb, lane, a->h->table.data(), a->qs->data(), a->ql->data(), &a->qn);
 }
 template <int SW, int K>
@@ -336,6 +336,18 @@ int64_t emul_band_merge_u(void *p, int side, const void *buf, int wake) {  // k_
     }
   }
   return (int64_t)h->frontier.size();
+}
+// debugging aid: calc / my / mx of the cell (global y, x) as this band sees it (owned, ghost or halo row)
+int emul_debug_cell(void *p, int y, int x) {
+  HostGrid *h = (HostGrid *)p;
+  const int yl = y - h->row0;
+  if (yl < 0 || yl >= h->gh) return -1;
+  const size_t o = (size_t)yl * h->pitch + (x >> 5);
+  const u32 bit = 1u << (x & 31);
+  return ((h->calc[o] & bit) ? 1 : 0) | (((u32)h->mymx[o] & bit) ? 2 : 0) | (((u32)(h->mymx[o] >> 32) & bit) ? 4 : 0) |
+         ((h->pref[h->cur][o] & bit) ? 8 : 0) | ((h->ustate[o] != U_NONE) ? 16 : 0) |
+         ((h->head[h->cur][o].x & bit) ? 32 : 0) | ((h->head[h->cur][o].z & bit) ? 64 : 0) | ((h->road[o].x & bit) ? 128 : 0) |
+         ((h->road[o].z & bit) ? 256 : 0);
 }
 void emul_band_u_resume(void *p) {
   HostGrid *h = (HostGrid *)p;

@@ -177,3 +177,25 @@ def test_bands_equal_single_grid(world, case):
             assert np.array_equal(st[k], want[k][lo:hi]), f"rank {r} rows {lo}:{hi} field {k}"
     assert total_leaks == leaks
     assert rounds >= ticks            # at least one convergence round per tick
+
+
+def test_band_whose_rows_plus_halo_rows_equal_the_grid_height():
+    """regression (found by tests/fuzz_bands.py): a band of gh - 4 rows holds gh - 4 + 2 * 2 = gh rows with its halo --
+    it must still be treated as a band (ghost rows, boundary rows on the frontier), not as the whole grid.  In-process
+    driver (LocalBands), bands on the CPU emulation, against the oracle."""
+    from flowamok_b200.bands import LocalBands
+    gh, gw = 54, 82
+    arrs = random_grid(238, gh, gw, n_lines=44, car_p=0.8, weird_p=0.05, offroad_p=0.02)
+    for variant in (0, 2):
+        bands = [EmulBand(arrs, 0, gh - 4, variant), EmulBand(arrs, gh - 4, gh, variant)]
+        run = LocalBands(bands)
+        og, ch = oracle_grid(arrs), O.Chooser(O.CHOOSE_RANDOM)
+        for t in range(6):
+            og.step_quick(ch)
+            run.tick(False)
+            want = state_of(og)
+            got = {k: np.zeros((gh, gw), want[k].dtype) for k in STATE_FIELDS}
+            for b in bands:
+                b.owned_state(got)
+            for k in STATE_FIELDS:
+                assert np.array_equal(want[k], got[k]), f"variant {variant} tick {t} field {k}"

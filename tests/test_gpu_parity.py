@@ -379,6 +379,32 @@ def _oracle_synth(gh, gw, seed=1):
     return og, rings
 
 
+def test_band_whose_rows_plus_halo_rows_equal_the_grid_height(ctx):
+    """regression (found by tests/fuzz_bands.py on the CPU emulation): a band of gh - 4 rows holds exactly gh rows with
+    its halo and must still run as a band"""
+    from flowamok_b200.bands import DeviceBand, LocalBands
+    gh, gw = 54, 82
+    arrs = random_grid(238, gh, gw, n_lines=44, car_p=0.8, weird_p=0.05, offroad_p=0.02)
+    bands = []
+    for lo, hi in ((0, gh - 4), (gh - 4, gh)):
+        b = DeviceBand(ctx, gh, gw, lo, hi)
+        b.grid.upload(**arrs)
+        bands.append(b)
+    run = LocalBands(bands)
+    og, ch = oracle_grid(arrs), O.Chooser(O.CHOOSE_RANDOM)
+    for t in range(6):
+        og.step_quick(ch)
+        run.tick(False)
+    want = state_of(og)
+    got = {k: np.zeros((gh, gw), want[k].dtype) for k in STATE_FIELDS}
+    for b in bands:
+        d = b.grid.download(fields=STATE_FIELDS)
+        lo, hi = b.rows
+        for k in STATE_FIELDS:
+            got[k][lo:hi] = d[k][lo:hi]
+    assert_state_equal(want, got, "bands after 6 ticks")
+
+
 def test_config3_4096_vs_oracle_first_ticks(ctx):
     """BASELINE config 3 (4096^2, seed 1, 10 % density): quick and perfect vs the oracle at ticks 1, 2, 3, 10."""
     for perfect in (False, True):
