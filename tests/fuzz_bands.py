@@ -12,8 +12,37 @@ from test_bands_cpu import EmulBand  # noqa: E402
 from flowamok_b200.bands import LocalBands  # noqa: E402
 
 
+def one_synth(seed, r):
+    """perfect mode on the synthetic network: cuts on multiples of 16 (rings never straddle a cut)"""
+    import synth_ref
+    nb16 = int(r.integers(3, 8))
+    gh, gw = 16 * nb16 + int(r.integers(0, 16)), int(r.integers(40, 400))
+    n_bands = int(r.integers(2, min(4, nb16) + 1))
+    cuts = sorted((16 * r.choice(np.arange(1, nb16), n_bands - 1, replace=False)).tolist())
+    rows = list(zip([0] + cuts, cuts + [gh]))
+    arrs, rings = synth_ref.generate(gh, gw, seed=seed)
+    variant = int(r.integers(0, 3))
+    bands = [EmulBand(arrs, lo, hi, variant, rings=rings) for lo, hi in rows]
+    run = LocalBands(bands)
+    og, ch = oracle_grid(arrs), O.Chooser(O.CHOOSE_RANDOM)
+    for t in range(int(r.integers(3, 9))):
+        og.step_perfect_sparse(ch, rings)
+        run.tick(True)
+        want = state_of(og)
+        got = {k: np.zeros((gh, gw), want[k].dtype) for k in STATE_FIELDS}
+        for b in bands:
+            b.owned_state(got)
+        for k in STATE_FIELDS:
+            if not np.array_equal(want[k], got[k]):
+                bad = np.argwhere(want[k] != got[k])
+                raise AssertionError(f"synth seed {seed} {gh}x{gw} rows {rows} variant {variant} tick {t}: {k} differs at {bad[:5].tolist()}")
+    return True
+
+
 def one(seed):
     r = np.random.default_rng(seed)
+    if r.random() < 0.3:
+        return one_synth(seed, r)
     gh, gw = int(r.integers(6, 80)), int(r.integers(1, 200))
     if r.random() < 0.15:
         gw = int(r.integers(900, 1400))

@@ -21,7 +21,9 @@ def one(seed):
     variant = int(r.integers(0, 3))
     # find_cycles returns dense [n][gh][gw] masks and enumerates every cycle of the road graph: small networks only
     perfect = r.random() < 0.4 and gh * gw <= 6000 and n_lines <= 10
-    og, eg, ch = oracle_grid(arrs), EmulGrid(arrs), O.Chooser(O.CHOOSE_RANDOM)
+    mode = int(r.choice([O.CHOOSE_RANDOM, O.CHOOSE_RANDOM, O.CHOOSE_Y, O.CHOOSE_X, O.CHOOSE_TAPE]))
+    tape = r.integers(0, 2, int(r.integers(1, 9))).astype(np.uint8)
+    og, eg, ch = oracle_grid(arrs), EmulGrid(arrs), O.Chooser(mode, tape if mode == O.CHOOSE_TAPE else None)
     rings = None
     if perfect:
         cyc = og.find_cycles()
@@ -31,10 +33,10 @@ def one(seed):
     for t in range(int(r.integers(3, 14))):
         if perfect:
             nl, _ = og.step_perfect(ch, cyc)
-            ne = eg.step(variant=variant, rings=rings)
+            ne = eg.step(variant=variant, rings=rings, chooser=mode, tape_bit=int(tape[t % len(tape)]))
         else:
             nl, _ = og.step_quick(ch)
-            ne = eg.step(variant=variant)
+            ne = eg.step(variant=variant, chooser=mode, tape_bit=int(tape[t % len(tape)]))
         assert nl == ne, (seed, t, "leaks", nl, ne)
         assert_state_equal(state_of(og), eg.state(), f"seed {seed} {gh}x{gw} variant {variant} perfect {perfect} tick {t}")
 
