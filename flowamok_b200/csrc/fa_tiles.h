@@ -171,9 +171,6 @@ FA_HD u32 u_try_queue(const GridView &g, int y, int w) {
 FA_HD bool band_word_reads_ghost(const GridView &g, const UEntry *table, int side, int own_row, int wg, int dx, u32 chg) {
   const int w = wg + dx;
   if (w < 0 || w >= g.pitch) return false;
-#ifdef FA_BAND_WAKE_ALL
-  return true;
-#endif
   const size_t o = (size_t)own_row * g.pitch + w;
 #if defined(__CUDA_ARCH__)
   const u32 sv = *(volatile const u32 *)&g.ustate[o];
