@@ -267,16 +267,21 @@ def test_full_size_properties_4096(ctx):
 
 
 def test_band_of_16384_vs_oracle(ctx):
-    """BASELINE config 4 generator on a 512 x 16384 band: 30 ticks vs the oracle."""
+    """BASELINE config 4 generator on a 512 x 16384 band: 1000 ticks vs the oracle,
+    whole state at ticks 30, 100 and 1000, leak counts on the way."""
     gh, gw = 512, 16384
     arrs, rings = synth_ref.generate(gh, gw, seed=1)
     g = ctx.grid(gh, gw)
     g.generate_synthetic(seed=1)
     og, ch = oracle_grid(arrs), O.Chooser(O.CHOOSE_RANDOM)
-    for t in range(30):
-        nl, _ = og.step_quick(ch)
-        assert g.step(False, 1) == nl
-    assert_state_equal(state_of(og), dev_state(g), "band tick 30")
+    done = 0
+    for stop in (30, 100, 1000):
+        leaks = 0
+        for _ in range(stop - done):
+            leaks += og.step_quick(ch)[0]
+        assert g.step(False, stop - done) == leaks, f"leaks up to tick {stop}"
+        done = stop
+        assert_state_equal(state_of(og), dev_state(g), f"band tick {stop}")
 
 
 def test_futhark_entry_points_readme_program(ctx):
@@ -405,31 +410,36 @@ def test_band_whose_rows_plus_halo_rows_equal_the_grid_height(ctx):
     assert_state_equal(want, got, "bands after 6 ticks")
 
 
-def test_config3_4096_vs_oracle_first_ticks(ctx):
-    """BASELINE config 3 (4096^2, seed 1, 10 % density): quick and perfect vs the oracle at ticks 1, 2, 3, 10."""
-    for perfect in (False, True):
-        og, rings = _oracle_synth(4096, 4096)
-        g = ctx.grid(4096, 4096)
-        g.generate_synthetic(seed=1)
-        ch = O.Chooser(O.CHOOSE_RANDOM)
-        for t in range(1, 11):
-            nl, _ = og.step_perfect_sparse(ch, rings) if perfect else og.step_quick(ch)
-            assert g.step(perfect, 1) == nl
-            if t in (1, 2, 3, 10):
-                assert_state_equal(state_of(og), dev_state(g), f"4096^2 perfect={perfect} tick {t}")
-        g.free()
+@pytest.mark.parametrize("perfect", [False, True])
+def test_config3_4096_vs_oracle_1000_ticks(ctx, perfect):
+    """BASELINE config 3 (4096^2, seed 1, 10 % density, 1000 ticks): quick and perfect vs the oracle, whole state at
+    ticks 1, 2, 3, 10, 100 and 1000, leak counts in between."""
+    og, rings = _oracle_synth(4096, 4096)
+    g = ctx.grid(4096, 4096)
+    g.generate_synthetic(seed=1)
+    ch = O.Chooser(O.CHOOSE_RANDOM)
+    done = 0
+    for stop in (1, 2, 3, 10, 100, 1000):
+        leaks = 0
+        for _ in range(stop - done):
+            leaks += (og.step_perfect_sparse(ch, rings) if perfect else og.step_quick(ch))[0]
+        assert g.step(perfect, stop - done) == leaks, f"leaks up to tick {stop}"
+        done = stop
+        assert_state_equal(state_of(og), dev_state(g), f"4096^2 perfect={perfect} tick {stop}")
+    g.free()
 
 
 def test_config4_16384_vs_oracle_first_ticks(ctx):
-    """BASELINE config 4 (the roofline headline, 16384^2 quick): the first 3 ticks of the full grid vs the oracle."""
+    """BASELINE config 4 (the roofline headline, 16384^2 quick): the first 10 ticks of the full grid vs the oracle
+    (BASELINE.md section 3 row 4), whole state at ticks 1, 3 and 10."""
     og, _rings = _oracle_synth(16384, 16384)
     g = ctx.grid(16384, 16384)
     g.generate_synthetic(seed=1)
     ch = O.Chooser(O.CHOOSE_RANDOM)
-    for t in range(3):
+    for t in range(1, 11):
         nl, _ = og.step_quick(ch)
         assert g.step(False, 1) == nl
-    want = state_of(og)
+        if t in (1, 3, 10):
+            assert_state_equal(state_of(og), dev_state(g), f"16384^2 tick {t}")
     del og
-    assert_state_equal(want, dev_state(g), "16384^2 tick 3")
     g.free()
