@@ -222,6 +222,12 @@ class Grid:
         self.ctx.check(self.L.flowamok_stats(self.ctx.h, self.h, C.byref(t), C.byref(p), C.byref(s)))
         return dict(ticks=t.value, passes=p.value, sweeps=s.value)
 
+    def digest(self):
+        """(sum, xor) mod 2^64 of a position-dependent hash of the owned cells' state; bands' digests combine"""
+        a, b = C.c_uint64(), C.c_uint64()
+        self.ctx.check(self.L.flowamok_grid_digest(self.ctx.h, self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def generate_synthetic(self, seed=1, density16=6554, ring_full16=2):
         self.ctx.check(self.L.flowamok_generate_synthetic(self.ctx.h, self.h, seed, density16, ring_full16))
 

@@ -9,10 +9,16 @@ both phases (steppers.fut:19,33-34,66,77-79).  Per tick each band
   3. swaps its boundary row of calc / my|mx again, ORs the neighbour's row into its ghost row and wakes the owned
      words next to every ghost word that changed; all bands all-reduce (MAX) the number of woken words and
      resume k_u_iter until nobody was woken -- a waiting chain that crosses a cut costs one extra round
-  4. [perfect mode] resolves its rings and swaps the boundary my|mx once more
+  4. [perfect mode] resolves its rings (a ring that straddles a cut is judged by every band it touches, the verdict
+     bits are AND-ed over the bands, then it is marked) and swaps the boundary my|mx once more
   5. moves (k_move)
-Messages are a few hundred KB, so this is latency-, not bandwidth-bound; there is no collective on the
-data path other than the single all-reduced convergence word.
+Messages are a few hundred KB, so this is latency-, not bandwidth-bound.
+
+Transports.  BandRunner.tick is the protocol spelled out phase by phase over torch.distributed (what the gloo CPU tests
+drive, with bands backed by the CPU emulation of the kernel programs).  On GPUs the ticks run natively inside the library
+(flowamok_band_step): over the P2P transport (DeviceBand.p2p_init: peer-mapped mailboxes over NVLink, remote stores +
+device-side flags, the convergence rounds and their termination vote inside one persistent kernel -- no NCCL call and no
+host synchronisation per tick), or, for comparison, over NCCL send/recv with one host round trip per tick (comm_init).
 """
 from __future__ import annotations
 
@@ -55,6 +61,54 @@ class DeviceBand:
             torch.cuda.synchronize(self.device)
 
     native = False
+
+    def set_cuts(self, cuts):
+        """row boundaries of ALL bands (world + 1 numbers): needed before cycles that may straddle a cut are installed"""
+        a = (C.c_int64 * len(cuts))(*cuts)
+        self._c(self.L.flowamok_band_set_cuts(self.ctx.h, self.grid.h, len(cuts) - 1, a))
+
+    def p2p_open(self, rank, world):
+        """allocate + export this band's mailbox: (64-byte CUDA IPC handle, raw device pointer)"""
+        h = (C.c_ubyte * 64)()
+        ptr = C.c_void_p()
+        self._c(self.L.flowamok_band_p2p_open(self.ctx.h, self.grid.h, rank, world, h, C.byref(ptr)))
+        return bytes(h), ptr.value
+
+    def p2p_connect(self, handles=None, ptrs=None, bands_on_device=1):
+        world = len(handles) if handles is not None else len(ptrs)
+        hb = b"".join(handles) if handles is not None else None
+        pa = (C.c_void_p * world)(*[p or None for p in ptrs]) if ptrs is not None else None
+        self._c(self.L.flowamok_band_p2p_connect(self.ctx.h, self.grid.h, hb, pa, bands_on_device))
+        self.native = True
+
+    def p2p_init(self, rank, world, group=None):
+        """One band per process / GPU: exchange the mailbox handles through torch.distributed and map the peers.
+        flowamok_band_set_cuts and the cycles must be in place."""
+        handle, _ = self.p2p_open(rank, world)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle, group=group)
+        self.p2p_connect(handles=handles)
+
+    def p2p_close(self):
+        """unmap the peers' mailboxes; synchronise all processes before freeing any band afterwards"""
+        self._c(self.L.flowamok_band_p2p_close(self.ctx.h, self.grid.h))
+        self.native = False
+
+    def ring_words(self):
+        n = C.c_int64()
+        self._c(self.L.flowamok_band_ring_words(self.ctx.h, self.grid.h, C.byref(n)))
+        return n.value
+
+    def ring_buffer(self):
+        return torch.zeros(max(1, self.ring_words()), dtype=torch.int32, device=self.device)
+
+    def ring_verdicts(self, buf):
+        self._c(self.L.flowamok_band_ring_verdicts(self.ctx.h, self.grid.h, buf.data_ptr()))
+        self._fence()
+
+    def rings_apply(self, buf):
+        self._fence()
+        self._c(self.L.flowamok_band_rings_apply(self.ctx.h, self.grid.h, buf.data_ptr()))
 
     def comm_init(self, rank, world, group=None):
         """Join the library's own NCCL communicator (unique id from rank 0, broadcast through torch.distributed);
@@ -140,6 +194,7 @@ class BandRunner:
         self.u_send = [mk(band.u_bytes), mk(band.u_bytes)]
         self.u_recv = [mk(band.u_bytes), mk(band.u_bytes)]
         self.cnt = band.counter()
+        self.ring_buf = None
         self.rounds = 0
         self.ticks = 0
 
@@ -194,6 +249,12 @@ class BandRunner:
         if perfect:
             self.b.rings()
             if self.world > 1:
+                if self.b.ring_words() > 0:           # rings that straddle a cut: AND the bands' verdicts, then mark
+                    if self.ring_buf is None:
+                        self.ring_buf = self.b.ring_buffer()
+                    self.b.ring_verdicts(self.ring_buf)
+                    dist.all_reduce(self.ring_buf, op=dist.ReduceOp.BAND, group=self.group)
+                    self.b.rings_apply(self.ring_buf)
                 self.exchange_u(wake=False)
         self.b.move()
         self.ticks += 1
@@ -261,6 +322,14 @@ class LocalBands:
         if perfect:
             for b in B:
                 b.rings()
+            if self.n > 1 and B[0].ring_words() > 0:
+                bufs = [b.ring_buffer() for b in B]
+                for b, v in zip(B, bufs):
+                    b.ring_verdicts(v)
+                for v in bufs[1:]:
+                    bufs[0] &= v
+                for b in B:
+                    b.rings_apply(bufs[0])
             if self.n > 1:
                 for r, side, _q, _qs in self._pairs():
                     B[r].pack_u(side, self.u[r][side])
@@ -272,3 +341,30 @@ class LocalBands:
     def step(self, perfect, n_ticks):
         for _ in range(n_ticks):
             self.tick(perfect)
+
+
+class LocalBandsP2P:
+    """All bands in ONE process on one device, each with its own context (= its own stream), stepped natively over the
+    P2P transport: the very kernels of the multi-GPU path (mailboxes, device-side flags, persistent k_u_iter with the
+    convergence rounds inside), the peers being plain device pointers.  The bands' kernels wait for each other on the
+    device, so they are enqueued tick by tick, round-robin."""
+
+    def __init__(self, bands):
+        self.bands = bands
+        n = len(bands)
+        ptrs = [b.p2p_open(r, n)[1] for r, b in enumerate(bands)]
+        for b in bands:
+            b.p2p_connect(ptrs=ptrs, bands_on_device=n)
+
+    def step(self, perfect, n_ticks):
+        for _ in range(n_ticks):
+            for b in self.bands:
+                b._c(b.L.flowamok_band_step(b.ctx.h, b.grid.h, int(perfect), 1, None))
+
+    def sync(self):
+        for b in self.bands:
+            b.ctx.sync()
+
+    @property
+    def rounds(self):
+        return max(b.step_native(False, 0) for b in self.bands)

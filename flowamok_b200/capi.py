@@ -64,6 +64,7 @@ def lib():
         "flowamok_grid_clone": (C.c_int, [P, P, C.POINTER(P)]),
         "flowamok_stats": (C.c_int, [P, P, C.POINTER(I64), C.POINTER(I64), C.POINTER(I64)]),
         "flowamok_generate_synthetic": (C.c_int, [P, P, U64, U32, U32]),
+        "flowamok_grid_digest": (C.c_int, [P, P, C.POINTER(U64), C.POINTER(U64)]),
         "flowamok_band_new": (C.c_int, [P, C.POINTER(P), I64, I64, I64, I64]),
         "flowamok_band_msg_bytes": (C.c_int, [P, P, C.POINTER(I64), C.POINTER(I64)]),
         "flowamok_band_pack_state": (C.c_int, [P, P, C.c_int, P]),
@@ -82,6 +83,13 @@ def lib():
         "flowamok_band_comm_init": (C.c_int, [P, P, C.c_int, C.c_int]),
         "flowamok_band_step": (C.c_int, [P, P, C.c_int, I64, C.POINTER(I64)]),
         "flowamok_grid_upload_cars": (C.c_int, [P, P, P, P, P, P, P]),
+        "flowamok_band_set_cuts": (C.c_int, [P, P, C.c_int, P]),
+        "flowamok_band_p2p_open": (C.c_int, [P, P, C.c_int, C.c_int, P, C.POINTER(P)]),
+        "flowamok_band_p2p_connect": (C.c_int, [P, P, P, P, C.c_int]),
+        "flowamok_band_p2p_close": (C.c_int, [P, P]),
+        "flowamok_band_ring_words": (C.c_int, [P, P, C.POINTER(I64)]),
+        "flowamok_band_ring_verdicts": (C.c_int, [P, P, P]),
+        "flowamok_band_rings_apply": (C.c_int, [P, P, P]),
         "flowamok_version": (C.c_char_p, []),
         # Futhark-generated-library surface (include/flowamok_futhark.h)
         "futhark_context_config_new": (P, []),

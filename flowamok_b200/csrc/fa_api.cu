@@ -56,8 +56,10 @@ struct flowamok_context {
   bool own_stream;
   int num_sms;
   int iter_blocks; // co-resident CTAs of k_u_iter
+  int iter_blocks_p2p = 0;   // the same for a band with mapped peers (smaller when several bands share one device)
   size_t smem_optin = 0;   // largest dynamic shared memory a CTA may ask for
   std::string err;
+  std::vector<struct flowamok_grid *> grids;   // live grids: flowamok_context_sync reads their watchdog flags
 };
 
 struct flowamok_grid {
@@ -99,6 +101,23 @@ struct flowamok_grid {
   long long band_rounds = 0;
   int ring_touch = 1;   // some ring cell lies on a boundary row of this band (1 = unknown/assume yes)
   int ring_swap = -1;   // collective decision (max over ranks of ring_touch); -1 = not agreed yet
+  // rings that straddle a cut (judged by every band they touch, AND-ed, then marked)
+  std::vector<int64_t> cuts;        // row boundaries of all bands (world + 1 entries), empty: unknown
+  int *ring_sid = nullptr;          // per listed ring: straddle id or -1
+  u32 *ring_partial = nullptr, *ring_pass = nullptr;   // this band's verdicts / the AND over all bands (bit = straddle id)
+  long long n_straddle = 0;         // straddle ids in use (the same number in every band)
+  int sbit_words = 0;               // 32-bit words of ring_partial / ring_pass
+  // P2P transport (fa_band.cuh): my mailbox, the peers' mailboxes, device-side protocol state
+  bool p2p = false;
+  BandLink link;
+  char *mailbox = nullptr;
+  size_t mailbox_bytes = 0;
+  int sbit_words_cap = 0;
+  BandDev *band_dev = nullptr;
+  void *ipc_opened[BAND_MAXW] = {};
+  unsigned int s_seq = 0;           // state messages sent so far (= ticks stepped over P2P)
+  int p2p_blocks = 0;               // cooperative grid of k_u_iter<true>
+  const char *poisoned = nullptr;   // a device-side watchdog tripped: the planes are not trustworthy any more
 };
 
 static int fail(flowamok_context *ctx, const char *fmt, ...) {
@@ -129,6 +148,7 @@ static int strip_rows(const flowamok_context *ctx, int owned_rows, int pitch) {
 }
 struct flowamok_grid;
 static int sync_color_buffers(flowamok_context *ctx, flowamok_grid *g);
+extern "C" { static int check_device_errors(flowamok_context *ctx, flowamok_grid *g); }
 
 // FLOWAMOK_DEBUG_SYNC=1: synchronise after every kernel so that a fault is reported at its launch site
 static bool debug_sync() {
@@ -172,9 +192,13 @@ int flowamok_context_new(flowamok_context **out, int device, void *stream) {
   CU(cudaFuncSetAttribute(k_move<M_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
   ctx->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
   int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_u_iter, UIT_THREADS, 0));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_u_iter<false>, UIT_THREADS, 0));
   if (per_sm < 1) return fail(ctx, "k_u_iter does not fit on an SM");
   ctx->iter_blocks = per_sm * ctx->num_sms;
+  int per_sm_p2p = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_p2p, k_u_iter<true>, UIT_THREADS, 0));
+  if (per_sm_p2p < 1) return fail(ctx, "k_u_iter<p2p> does not fit on an SM");
+  ctx->iter_blocks_p2p = per_sm_p2p * ctx->num_sms;
   return 0;
 }
 
@@ -188,6 +212,8 @@ int flowamok_context_free(flowamok_context *ctx) {
 int flowamok_context_sync(flowamok_context *ctx) {
   if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
   CU(cudaStreamSynchronize(ctx->stream));
+  for (flowamok_grid *g : ctx->grids)
+    if (check_device_errors(ctx, g)) return 1;
   return 0;
 }
 char *flowamok_context_get_error(flowamok_context *ctx) {
@@ -222,6 +248,7 @@ static int grid_new_impl(flowamok_context *ctx, flowamok_grid **out, int64_t gh_
   g->rng_inc = (0xda3e39cb94b95bdbULL << 1) | 1ULL;
   g->ring_words = nullptr; g->ring_off = nullptr; g->n_rings = g->n_ring_cells = g->n_ring_words = 0; g->ring_stride = 0;
   g->leak_plane = nullptr;
+  memset(&g->link, 0, sizeof g->link);
   *out = g;
   CU(cudaMalloc(&g->road, g->nwords * sizeof(U4)));
   for (int k = 0; k < 2; k++) {
@@ -266,6 +293,7 @@ static int grid_new_impl(flowamok_context *ctx, flowamok_grid **out, int64_t gh_
   CU(cudaMemsetAsync(g->ustate, 0xFF, g->nwords * 4, st));   // U_NONE: halo rows never get entries
   CU(cudaMemsetAsync(g->diag, 0, sizeof(Diag), st));
   CU(cudaStreamSynchronize(st));
+  ctx->grids.push_back(g);
   return 0;
 }
 
@@ -292,6 +320,7 @@ int flowamok_band_new(flowamok_context *ctx, flowamok_grid **out, int64_t gh_glo
 
 int flowamok_grid_free(flowamok_context *ctx, flowamok_grid *g) {
   if (!g) return 0;
+  if (ctx) ctx->grids.erase(std::remove(ctx->grids.begin(), ctx->grids.end(), g), ctx->grids.end());
   if (ctx && ctx->device >= 0) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -301,6 +330,8 @@ int flowamok_grid_free(flowamok_context *ctx, flowamok_grid *g) {
   cudaFree(g->calc); cudaFree(g->mymx); cudaFree(g->rng); cudaFree(g->is); cudaFree(g->diag);
   for (int k = 0; k < 2; k++) { cudaFree(g->msg_s_send[k]); cudaFree(g->msg_s_recv[k]); cudaFree(g->msg_u_send[k]); cudaFree(g->msg_u_recv[k]); }
   cudaFree(g->d_woken); if (g->h_woken) cudaFreeHost(g->h_woken);
+  for (int r = 0; r < BAND_MAXW; r++) if (g->ipc_opened[r]) cudaIpcCloseMemHandle(g->ipc_opened[r]);
+  cudaFree(g->mailbox); cudaFree(g->band_dev); cudaFree(g->ring_sid); cudaFree(g->ring_partial); cudaFree(g->ring_pass);
   cudaFree(g->table); cudaFree(g->qlist[0]); cudaFree(g->qlist[1]); cudaFree(g->ustate);
   cudaFree(g->ring_words); cudaFree(g->ring_off); cudaFree(g->leak_plane);
   cudaFreeHost(g->h_diag);
@@ -412,7 +443,7 @@ int flowamok_grid_download(flowamok_context *ctx, const flowamok_grid *g, int8_t
   if (rng_inc) *rng_inc = g->rng_inc;
   CU(cudaStreamSynchronize(st));
   if (tmp) CU(cudaFree(tmp));
-  return 0;
+  return check_device_errors(ctx, const_cast<flowamok_grid *>(g));   // a synchronisation point: watchdog flags are fatal
 }
 
 int flowamok_add_line_vertical(flowamok_context *ctx, flowamok_grid *g, int64_t y0, int64_t y1, int64_t x, int8_t flow) {
@@ -462,6 +493,35 @@ int flowamok_set_chooser(flowamok_context *ctx, flowamok_grid *g, int mode, cons
 // ---------------------------------------------------------------------------------------------
 // cycles
 // ---------------------------------------------------------------------------------------------
+static int band_of_row(const std::vector<int64_t> &cuts, int64_t y) {
+  int r = 0;
+  while (r + 2 < (int)cuts.size() && y >= cuts[(size_t)r + 1]) r++;
+  return r;
+}
+// (re)allocate the verdict bits of the straddling rings: all ones = "no objection"
+static int alloc_straddle_bits(flowamok_context *ctx, flowamok_grid *g, long long n_straddle, const std::vector<int> &sids) {
+  CU(cudaFree(g->ring_sid)); CU(cudaFree(g->ring_partial)); CU(cudaFree(g->ring_pass));
+  g->ring_sid = nullptr; g->ring_partial = nullptr; g->ring_pass = nullptr;
+  g->n_straddle = n_straddle; g->sbit_words = (int)((n_straddle + 31) / 32);
+  if (n_straddle <= 0) return 0;
+  if (g->p2p && g->sbit_words > g->sbit_words_cap)
+    return fail(ctx, "%lld rings straddle band cuts, more than the connected mailboxes hold: install the cycles before flowamok_band_p2p_open",
+                n_straddle);
+  if (!sids.empty()) {
+    CU(cudaMalloc(&g->ring_sid, sids.size() * sizeof(int)));
+    CU(cudaMemcpy(g->ring_sid, sids.data(), sids.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  CU(cudaMalloc(&g->ring_partial, (size_t)g->sbit_words * 4));
+  CU(cudaMalloc(&g->ring_pass, (size_t)g->sbit_words * 4));
+  CU(cudaMemset(g->ring_partial, 0xFF, (size_t)g->sbit_words * 4));
+  CU(cudaMemset(g->ring_pass, 0, (size_t)g->sbit_words * 4));
+  g->link.ring_words = g->sbit_words;
+  return 0;
+}
+
+// The cycle list is GLOBAL (the same list on every band).  A band keeps the rings that have a cell in its rows, with
+// the words of its own rows only; a ring whose rows lie in more than one band gets a straddle id -- its position among the
+// straddling rings of the global list, hence the same number in every band (needs the cuts: flowamok_band_set_cuts).
 static int install_rings(flowamok_context *ctx, flowamok_grid *g, int64_t n, const int64_t *off, const int64_t *y,
                          const int64_t *x, const int8_t *cy, const int8_t *cx, const uint8_t *grant) {
   CU(cudaSetDevice(ctx->device));
@@ -469,20 +529,40 @@ static int install_rings(flowamok_context *ctx, flowamok_grid *g, int64_t n, con
   CU(cudaFree(g->ring_words)); CU(cudaFree(g->ring_off));
   g->ring_words = nullptr; g->ring_off = nullptr; g->n_rings = 0; g->n_ring_cells = 0; g->n_ring_words = 0; g->ring_stride = 0;
   g->h_off.clear(); g->h_y.clear(); g->h_x.clear(); g->h_cy.clear(); g->h_cx.clear();
-  if (n <= 0) return 0;
-  int64_t tot = off[n];
+  std::vector<int> sids;
+  if (n <= 0) { g->ring_touch = 0; g->ring_swap = g->cuts.empty() ? -1 : 0; return alloc_straddle_bits(ctx, g, 0, sids); }
+  const int64_t tot = off[n], lo = g->row0 + g->own0, hi = g->row0 + g->own1;
+  const bool band = g->halo != 0, have_cuts = !g->cuts.empty();
   std::vector<RingWord> words;
-  std::vector<unsigned long long> offs((size_t)n + 1);
+  std::vector<unsigned long long> offs;
+  long long n_straddle = 0, kept = 0;
+  int touch = 0, touch_global = 0;
   for (int64_t k = 0; k < n; k++) {
-    offs[(size_t)k] = words.size();
-    const size_t first = words.size();
+    bool in = false, out = false;
+    int64_t ymin = INT64_MAX, ymax = INT64_MIN;
     for (int64_t t = off[k]; t < off[k + 1]; t++) {
       if (y[t] < 0 || y[t] >= g->gh_global || x[t] < 0 || x[t] >= g->gw) return fail(ctx, "cycle cell out of bounds");
-      if (y[t] < g->row0 + g->own0 || y[t] >= g->row0 + g->own1)
-        return fail(ctx, "cycle cell outside this device's row band (rings must not straddle bands)");
-      bool single = (cy[t] != 0) != (cx[t] != 0);
+      const bool single = (cy[t] != 0) != (cx[t] != 0);
       if (!single) return fail(ctx, "cycle check direction must be single-axis (steppers.fut:239-294)");
       if (grant[t] != 1 && grant[t] != 2) return fail(ctx, "grant must be 1 (y) or 2 (x)");
+      (y[t] >= lo && y[t] < hi ? in : out) = true;
+      ymin = std::min(ymin, y[t]); ymax = std::max(ymax, y[t]);
+      if (have_cuts)
+        for (size_t c = 1; c + 1 < g->cuts.size(); c++) touch_global |= (y[t] == g->cuts[c] - 1 || y[t] == g->cuts[c]);
+    }
+    int sid = -1;
+    if (band && have_cuts) {
+      if (ymin <= ymax && band_of_row(g->cuts, ymin) != band_of_row(g->cuts, ymax)) sid = (int)n_straddle++;
+    } else if (band && in && out) {
+      return fail(ctx, "a cycle straddles this row band: give every band the global cycle list after flowamok_band_set_cuts");
+    }
+    if (band && !in) continue;   // another band's ring
+    offs.push_back(words.size());
+    sids.push_back(sid);
+    kept++;
+    const size_t first = words.size();
+    for (int64_t t = off[k]; t < off[k + 1]; t++) {
+      if (y[t] < lo || y[t] >= hi) continue;   // the other band's part of a straddling ring
       const u32 wi = (u32)((size_t)(y[t] - g->row0) * g->pitch + (x[t] >> 5)), bit = 1u << (x[t] & 31);
       size_t j = first;
       while (j < words.size() && words[j].wi != wi) j++;
@@ -490,20 +570,25 @@ static int install_rings(flowamok_context *ctx, flowamok_grid *g, int64_t n, con
       RingWord &e = words[j];
       if (cy[t] < 0) e.mN |= bit; else if (cy[t] > 0) e.mS |= bit; else if (cx[t] < 0) e.mW |= bit; else e.mE |= bit;
       if (grant[t] == 2) e.gX |= bit; else e.gY |= bit;
+      if (y[t] == lo || y[t] == hi - 1) touch = 1;
     }
   }
-  offs[(size_t)n] = words.size();
-  CU(cudaMalloc(&g->ring_words, std::max<size_t>(1, words.size()) * sizeof(RingWord)));
-  CU(cudaMalloc(&g->ring_off, ((size_t)n + 1) * 8));
-  CU(cudaMemcpy(g->ring_words, words.data(), words.size() * sizeof(RingWord), cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(g->ring_off, offs.data(), ((size_t)n + 1) * 8, cudaMemcpyHostToDevice));
-  g->n_rings = n; g->n_ring_cells = tot; g->n_ring_words = (long long)words.size();
-  g->ring_touch = 0; g->ring_swap = -1;
-  for (int64_t t = 0; t < tot; t++)
-    if (y[t] == g->row0 + g->own0 || y[t] == g->row0 + g->own1 - 1) { g->ring_touch = 1; break; }
+  offs.push_back(words.size());
+  if (kept > 0) {
+    CU(cudaMalloc(&g->ring_words, std::max<size_t>(1, words.size()) * sizeof(RingWord)));
+    CU(cudaMalloc(&g->ring_off, ((size_t)kept + 1) * 8));
+    CU(cudaMemcpy(g->ring_words, words.data(), words.size() * sizeof(RingWord), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(g->ring_off, offs.data(), ((size_t)kept + 1) * 8, cudaMemcpyHostToDevice));
+  }
+  g->n_rings = kept; g->n_ring_cells = tot; g->n_ring_words = (long long)words.size();
+  g->ring_touch = touch;
+  g->ring_swap = have_cuts ? ((touch_global || n_straddle > 0) ? 1 : 0) : -1;   // with the cuts every band decides alike
   g->h_off.assign(off, off + n + 1); g->h_y.assign(y, y + tot); g->h_x.assign(x, x + tot);
   g->h_cy.assign(cy, cy + tot); g->h_cx.assign(cx, cx + tot);
-  return 0;
+  bool any_sid = false;
+  for (int d : sids) any_sid |= d >= 0;
+  if (!any_sid) sids.clear();
+  return alloc_straddle_bits(ctx, g, n_straddle, sids);
 }
 
 int flowamok_set_cycles(flowamok_context *ctx, flowamok_grid *g, int64_t n, const int64_t *off, const int64_t *y,
@@ -620,8 +705,9 @@ int flowamok_get_cycles_dense(flowamok_context *ctx, const flowamok_grid *g, int
   if (!g) return fail(ctx, "null grid");
   if (g->n_rings > 0 && g->h_off.empty()) return fail(ctx, "cycle list was generated on the device; dense form unavailable");
   size_t per = (size_t)g->gh_global * g->gw * 2;
-  memset(masks, 0, per * (size_t)g->n_rings);
-  for (int64_t k = 0; k < g->n_rings; k++)
+  const int64_t ng = g->h_off.empty() ? 0 : (int64_t)g->h_off.size() - 1;   // the list as it was installed (global on a band)
+  memset(masks, 0, per * (size_t)ng);
+  for (int64_t k = 0; k < ng; k++)
     for (int64_t t = g->h_off[k]; t < g->h_off[k + 1]; t++) {
       size_t o = per * (size_t)k + ((size_t)g->h_y[t] * g->gw + g->h_x[t]) * 2;
       masks[o] = g->h_cy[t]; masks[o + 1] = g->h_cx[t];
@@ -658,16 +744,18 @@ static int launch_u_init(flowamok_context *ctx, flowamok_grid *g, const GridView
   return 0;
 }
 // first_it = 0: start from the frontier k_u_local left in qlist[0]; 1: resume from qlist[1] (band merge)
-static int launch_u_iter(flowamok_context *ctx, flowamok_grid *g, GridView &v, unsigned int first_it) {
+static int launch_u_iter(flowamok_context *ctx, flowamok_grid *g, GridView &v, unsigned int first_it, bool p2p = false) {
   void *args[] = {(void *)&v, (void *)&g->table, (void *)&g->qlist[0], (void *)&g->qlist[1],
-                  (void *)&first_it, (void *)&g->is, (void *)&g->diag};
-  CU(cudaLaunchCooperativeKernel((void *)k_u_iter, dim3(ctx->iter_blocks), dim3(UIT_THREADS), args, 0, ctx->stream));
+                  (void *)&first_it, (void *)&g->is, (void *)&g->diag, (void *)&g->link};
+  if (p2p) CU(cudaLaunchCooperativeKernel((void *)k_u_iter<true>, dim3(g->p2p_blocks), dim3(UIT_THREADS), args, 0, ctx->stream));
+  else CU(cudaLaunchCooperativeKernel((void *)k_u_iter<false>, dim3(ctx->iter_blocks), dim3(UIT_THREADS), args, 0, ctx->stream));
   KCHECK("k_u_iter");
   return 0;
 }
 static int launch_rings(flowamok_context *ctx, flowamok_grid *g, const GridView &v) {
   if (g->n_rings > 0) {
-    k_rings<<<nblk(g->n_rings, RINGS_PER_BLOCK), RINGS_PER_BLOCK, 0, ctx->stream>>>(v, g->ring_words, g->ring_off, g->n_rings, g->ring_stride);
+    k_rings<<<nblk(g->n_rings, RINGS_PER_BLOCK), RINGS_PER_BLOCK, 0, ctx->stream>>>(v, g->ring_words, g->ring_off, g->n_rings, g->ring_stride,
+                                                                                    g->ring_sid, g->ring_partial);
     KCHECK("k_rings");
   }
   return 0;
@@ -696,19 +784,30 @@ static int enqueue_tick(flowamok_context *ctx, flowamok_grid *g, bool perfect, u
   return 0;
 }
 
+// The device-side watchdogs (grid barrier of k_u_iter, waits of the band protocol) leave the planes half-relaxed when
+// they trip: the grid is poisoned, and every later stepping or reading call fails.
+static int check_device_errors(flowamok_context *ctx, flowamok_grid *g) {
+  if (g->poisoned) return fail(ctx, "grid is poisoned: %s", g->poisoned);
+  unsigned int err = 0, berr = 0;
+  CU(cudaMemcpyAsync(&err, &g->is->error, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (g->band_dev) CU(cudaMemcpyAsync(&berr, &g->band_dev->error, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (err) g->poisoned = "the grid barrier watchdog of k_u_iter tripped (fixpoint left half-relaxed)";
+  else if (berr) g->poisoned = "a wait of the row-band protocol timed out (a neighbour band never sent its rows)";
+  if (g->poisoned) return fail(ctx, "%s", g->poisoned);
+  return 0;
+}
 static int read_diag(flowamok_context *ctx, flowamok_grid *g, Diag *d) {
   CU(cudaMemcpyAsync(g->h_diag, g->diag, sizeof(Diag), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   *d = *g->h_diag;
-  unsigned int err = 0;
-  CU(cudaMemcpy(&err, &g->is->error, 4, cudaMemcpyDeviceToHost));
-  if (err) return fail(ctx, "grid barrier watchdog tripped in k_u_iter");
-  return 0;
+  return check_device_errors(ctx, g);
 }
 
 static int step_n(flowamok_context *ctx, flowamok_grid *g, bool perfect, int64_t n_ticks, int64_t *n_leaks) {
   if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device: flowamok_b200 has no CPU path");
   if (!g) return fail(ctx, "null grid");
+  if (g->poisoned) return fail(ctx, "grid is poisoned: %s", g->poisoned);
   CU(cudaSetDevice(ctx->device));
   unsigned long long before = 0;
   if (n_leaks) {
@@ -843,7 +942,15 @@ int flowamok_grid_clone(flowamok_context *ctx, const flowamok_grid *src, flowamo
       CU(cudaMemcpyAsync(g->ring_off, src->ring_off, ((size_t)src->n_rings + 1) * 8, cudaMemcpyDeviceToDevice, st));
     }
     g->n_rings = src->n_rings; g->n_ring_cells = src->n_ring_cells; g->n_ring_words = src->n_ring_words; g->ring_stride = src->ring_stride;
-    g->ring_touch = src->ring_touch;
+    g->ring_touch = src->ring_touch; g->ring_swap = src->ring_swap; g->cuts = src->cuts;
+    if (src->n_straddle > 0) {
+      std::vector<int> none;
+      if (alloc_straddle_bits(ctx, g, src->n_straddle, none)) return 1;
+      if (src->ring_sid) {
+        CU(cudaMalloc(&g->ring_sid, (size_t)src->n_rings * sizeof(int)));
+        CU(cudaMemcpyAsync(g->ring_sid, src->ring_sid, (size_t)src->n_rings * sizeof(int), cudaMemcpyDeviceToDevice, st));
+      }
+    }
     g->h_off = src->h_off; g->h_y = src->h_y; g->h_x = src->h_x; g->h_cy = src->h_cy; g->h_cx = src->h_cx;
   }
   *out = g;
@@ -950,6 +1057,32 @@ int flowamok_band_rings(flowamok_context *ctx, flowamok_grid *g) {
   GridView v = make_view(g);
   return launch_rings(ctx, g, v);
 }
+/* Rings that straddle a cut, host-driven protocol: flowamok_band_rings judges them (and marks the local ones);
+ * ring_verdicts copies this band's verdict words (n_words of them, 1 = no objection) to dev_buf and resets them;
+ * the caller ANDs the buffers of all bands; rings_apply marks the rings whose bit survived. */
+int flowamok_band_ring_words(flowamok_context *ctx, const flowamok_grid *g, int64_t *n_words) {
+  if (!g) return fail(ctx, "null grid");
+  if (n_words) *n_words = g->sbit_words;
+  return 0;
+}
+int flowamok_band_ring_verdicts(flowamok_context *ctx, flowamok_grid *g, void *dev_buf) {
+  if (band_check(ctx, g, 0)) return 1;
+  if (g->sbit_words == 0) return 0;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(dev_buf, g->ring_partial, (size_t)g->sbit_words * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaMemsetAsync(g->ring_partial, 0xFF, (size_t)g->sbit_words * 4, ctx->stream));
+  return 0;
+}
+int flowamok_band_rings_apply(flowamok_context *ctx, flowamok_grid *g, const void *dev_pass) {
+  if (band_check(ctx, g, 0)) return 1;
+  if (g->sbit_words == 0 || g->n_rings == 0 || !g->ring_sid) return 0;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(g->ring_pass, dev_pass, (size_t)g->sbit_words * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  GridView v = make_view(g);
+  k_rings_mark<<<nblk(g->n_rings, 128), 128, 0, ctx->stream>>>(v, g->ring_words, g->ring_off, g->n_rings, g->ring_stride, g->ring_sid, g->ring_pass);
+  KCHECK("k_rings_mark");
+  return 0;
+}
 int flowamok_band_move(flowamok_context *ctx, flowamok_grid *g) {
   if (band_check(ctx, g, 0)) return 1;
   CU(cudaSetDevice(ctx->device));
@@ -982,6 +1115,108 @@ int flowamok_band_comm_init(flowamok_context *ctx, const void *id128, int rank, 
   return 0;
 }
 
+/* Row boundaries of ALL bands (world + 1 entries, cuts[0] = 0, cuts[world] = gh_global), the same on every band.  Needed
+ * before cycles are installed on a band whose rings may straddle a cut, and before flowamok_band_p2p_open. */
+int flowamok_band_set_cuts(flowamok_context *ctx, flowamok_grid *g, int world, const int64_t *cuts) {
+  if (band_check(ctx, g, 0)) return 1;
+  if (world < 1 || world > BAND_MAXW || !cuts) return fail(ctx, "bad cuts (1 <= world <= %d)", BAND_MAXW);
+  if (cuts[0] != 0 || cuts[world] != g->gh_global) return fail(ctx, "cuts must run from 0 to the grid height");
+  bool mine = false;
+  for (int r = 0; r < world; r++) {
+    if (cuts[r + 1] <= cuts[r]) return fail(ctx, "cuts must increase");
+    mine |= cuts[r] == g->row0 + g->own0 && cuts[r + 1] == g->row0 + g->own1;
+  }
+  if (!mine) return fail(ctx, "this band's rows are not one of the intervals of the cuts");
+  g->cuts.assign(cuts, cuts + world + 1);
+  return 0;
+}
+
+static size_t mailbox_layout(const flowamok_grid *g, int world, int ring_words_cap, BandLink *L) {
+  const size_t sb = (size_t)g->pitch * (2 * 16 + 2 * 4 + 128), ub = (size_t)g->pitch * (4 + 8);
+  size_t o = sizeof(MailHdr);
+  L->s_bytes = sb; L->u_bytes = ub;
+  L->off_s = o; o += 4 * sb;
+  L->off_u = o; o += 4 * ub;
+  L->off_ring = o; o += (size_t)2 * world * ring_words_cap * 4;
+  return (o + 255) & ~(size_t)255;
+}
+
+/* P2P transport, step 1 of 2: allocate this band's mailbox and export it.  handle64 receives the 64-byte CUDA IPC handle
+ * (for bands in other processes), *local_ptr the device pointer (for bands in this process).  All bands must have the same
+ * pitch and world, and the cycles should already be installed (the mailbox is sized for the straddling rings). */
+int flowamok_band_p2p_open(flowamok_context *ctx, flowamok_grid *g, int rank, int world, void *handle64, void **local_ptr) {
+  if (band_check(ctx, g, 0)) return 1;
+  if (world < 1 || world > BAND_MAXW || rank < 0 || rank >= world) return fail(ctx, "bad rank / world (world <= %d)", BAND_MAXW);
+  if ((int)g->cuts.size() != world + 1) return fail(ctx, "flowamok_band_set_cuts must be called first (with the same world)");
+  if (g->cuts[(size_t)rank] != g->row0 + g->own0) return fail(ctx, "rank %d does not own the rows this band holds", rank);
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (g->mailbox) return fail(ctx, "the band's mailbox is open already");
+  g->sbit_words_cap = std::max(1024, g->sbit_words);
+  BandLink L;
+  memset(&L, 0, sizeof L);
+  g->mailbox_bytes = mailbox_layout(g, world, g->sbit_words_cap, &L);
+  CU(cudaMalloc(&g->mailbox, g->mailbox_bytes));
+  CU(cudaMemset(g->mailbox, 0, g->mailbox_bytes));
+  CU(cudaMalloc(&g->band_dev, sizeof(BandDev)));
+  CU(cudaMemset(g->band_dev, 0, sizeof(BandDev)));
+  L.rank = rank; L.world = world; L.self = g->mailbox; L.dev = g->band_dev; L.ring_words = g->sbit_words;
+  g->link = L;
+  ctx->rank = rank; ctx->world = world;
+  if (handle64) {
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaIpcGetMemHandle(&h, g->mailbox));
+    memcpy(handle64, &h, 64);
+  }
+  if (local_ptr) *local_ptr = g->mailbox;
+  return 0;
+}
+
+/* step 2 of 2: map the other bands' mailboxes.  local_ptrs (world entries, may be NULL): device pointers of bands that
+ * live in THIS process (taken as they are); otherwise handles (world x 64 bytes, by rank) are opened with CUDA IPC.
+ * bands_on_device: how many bands share this band's GPU (1 in production; > 1 only when several bands are stepped
+ * concurrently on one device for tests: their persistent kernels must all be resident at once). */
+int flowamok_band_p2p_connect(flowamok_context *ctx, flowamok_grid *g, const void *handles, void *const *local_ptrs, int bands_on_device) {
+  if (band_check(ctx, g, 0)) return 1;
+  if (!g->mailbox) return fail(ctx, "flowamok_band_p2p_open has not been called");
+  CU(cudaSetDevice(ctx->device));
+  BandLink &L = g->link;
+  for (int r = 0; r < L.world; r++) {
+    if (r == L.rank) { L.all[r] = g->mailbox; continue; }
+    if (local_ptrs && local_ptrs[r]) { L.all[r] = (char *)local_ptrs[r]; continue; }
+    if (!handles) return fail(ctx, "no handle for band %d", r);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)handles + (size_t)r * 64, 64);
+    void *ptr = nullptr;
+    CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    g->ipc_opened[r] = ptr;
+    L.all[r] = (char *)ptr;
+  }
+  L.nb[0] = L.rank > 0 ? L.all[L.rank - 1] : nullptr;
+  L.nb[1] = L.rank + 1 < L.world ? L.all[L.rank + 1] : nullptr;
+  if (bands_on_device < 1) bands_on_device = 1;
+  g->p2p_blocks = bands_on_device == 1 ? ctx->iter_blocks_p2p : std::max(1, ctx->iter_blocks_p2p / (2 * bands_on_device));
+  g->p2p = true;
+  return 0;
+}
+
+/* Unmap the peers' mailboxes (call on every band, then synchronise the processes, then free the grids: a mailbox must
+ * not be freed while another process still maps it). */
+int flowamok_band_p2p_close(flowamok_context *ctx, flowamok_grid *g) {
+  if (band_check(ctx, g, 0)) return 1;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  g->p2p = false;
+  for (int r = 0; r < BAND_MAXW; r++) {
+    if (g->ipc_opened[r]) CU(cudaIpcCloseMemHandle(g->ipc_opened[r]));
+    g->ipc_opened[r] = nullptr;
+    g->link.all[r] = nullptr;
+  }
+  g->link.nb[0] = g->link.nb[1] = nullptr;
+  return check_device_errors(ctx, g);
+}
+
 // swap `bytes` with both neighbours: send[side] goes to the neighbour on that side, recv[side] comes from it
 static int band_swap(flowamok_context *ctx, char *const send[2], char *const recv[2], size_t bytes) {
   NC(g_nccl.GroupStart());
@@ -995,12 +1230,68 @@ static int band_swap(flowamok_context *ctx, char *const send[2], char *const rec
   return 0;
 }
 
+// The per-tick protocol over the P2P transport (fa_band.cuh): five to eight launches per tick on the context's stream,
+// no NCCL call and no host synchronisation at all -- the convergence rounds run inside k_u_iter<true>.
+//   k_band_xstate            heading / preference / colour rows across the cuts
+//   k_u_local<band>          local levels
+//   k_u_iter<p2p>            pre-swap, local fixpoint, { swap + wake + vote, local fixpoint }*
+//   [perfect] k_rings        local rings are marked, straddling rings judged;  k_band_xring + k_rings_mark if any ring
+//                            straddles a cut;  k_band_xu if any ring touches a boundary row
+//   k_move
+static int band_step_p2p(flowamok_context *ctx, flowamok_grid *g, bool perfect, int64_t n_ticks, int64_t *rounds) {
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const bool multi = g->link.world > 1;
+  const int xs_blocks = std::max(1, std::min(64, (int)nblk(8ll * g->pitch, 256)));
+  for (int64_t t = 0; t < n_ticks; t++) {
+    if (multi) {
+      k_band_xstate<<<xs_blocks, 256, 0, st>>>(g->pitch, g->own0, g->own1, g->head[g->cur], g->pref[g->cur], g->color[g->cur], g->link,
+                                               ++g->s_seq);
+      KCHECK("k_band_xstate");
+    }
+    if (flowamok_band_u_init(ctx, g)) return 1;
+    {
+      GridView v = make_view(g);
+      if (launch_u_iter(ctx, g, v, 0u, true)) return 1;
+    }
+    if (perfect) {
+      GridView v = make_view(g);
+      if (launch_rings(ctx, g, v)) return 1;
+      if (multi && g->n_straddle > 0) {
+        k_band_xring<<<1, 512, 0, st>>>(g->ring_partial, g->ring_pass, g->link);
+        KCHECK("k_band_xring");
+        if (g->n_rings > 0 && g->ring_sid) {
+          k_rings_mark<<<nblk(g->n_rings, 128), 128, 0, st>>>(v, g->ring_words, g->ring_off, g->n_rings, g->ring_stride, g->ring_sid, g->ring_pass);
+          KCHECK("k_rings_mark");
+        }
+      }
+      if (multi && g->ring_swap != 0) {   // -1 (unknown) counts as yes
+        k_band_xu<<<1, 512, 0, st>>>(v, g->link);
+        KCHECK("k_band_xu");
+      }
+    }
+    if (flowamok_band_move(ctx, g)) return 1;
+  }
+  if (rounds) {   // convergence rounds so far: a device counter (this read synchronises; pass NULL to stay asynchronous)
+    unsigned long long r = 0;
+    CU(cudaMemcpyAsync(&r, &g->band_dev->rounds, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *rounds = (int64_t)r;
+    if (check_device_errors(ctx, g)) return 1;
+  }
+  return 0;
+}
+
 /* n_ticks of stepper_quick / stepper_perfect on this band, the whole per-tick protocol (see above) driven from here
  * with NCCL send/recv on the context's stream: one host synchronisation per convergence round, no Python in the loop. */
 int flowamok_band_step(flowamok_context *ctx, flowamok_grid *g, int perfect, int64_t n_ticks, int64_t *rounds) {
   if (band_check(ctx, g, 0)) return 1;
+  if (g->poisoned) return fail(ctx, "grid is poisoned: %s", g->poisoned);
+  if (g->p2p) return band_step_p2p(ctx, g, perfect != 0, n_ticks, rounds);
   const bool multi = ctx->world > 1;
-  if (multi && !ctx->comm) return fail(ctx, "flowamok_band_comm_init has not been called");
+  if (multi && !ctx->comm) return fail(ctx, "neither flowamok_band_p2p_connect nor flowamok_band_comm_init has been called");
+  if (multi && perfect && g->n_straddle > 0)
+    return fail(ctx, "rings straddle a band cut: the NCCL transport has no bitwise reduction, use flowamok_band_p2p_*");
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const size_t sb = (size_t)g->pitch * (2 * 16 + 2 * 4 + 128), ub = (size_t)g->pitch * (4 + 8);
@@ -1117,6 +1408,27 @@ int flowamok_stats(flowamok_context *ctx, flowamok_grid *g, int64_t *ticks, int6
   return 0;
 }
 
+int flowamok_grid_digest(flowamok_context *ctx, const flowamok_grid *g, uint64_t *sum, uint64_t *xor_) {
+  if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
+  if (!g) return fail(ctx, "null grid");
+  CU(cudaSetDevice(ctx->device));
+  unsigned long long *d = nullptr, h[2] = {0, 0};
+  CU(cudaMalloc(&d, 16));
+  cudaError_t e = cudaMemsetAsync(d, 0, 16, ctx->stream);
+  if (e == cudaSuccess) {
+    k_digest<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(g->own0, g->own1, g->gw, g->pitch, g->row0, g->head[g->cur], g->pref[g->cur],
+                                                        g->color[g->cur], g->rng, d);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(ctx, "flowamok_grid_digest: %s", cudaGetErrorString(e));
+  if (sum) *sum = h[0];
+  if (xor_) *xor_ = h[1];
+  return check_device_errors(ctx, const_cast<flowamok_grid *>(g));
+}
+
 int flowamok_generate_synthetic(flowamok_context *ctx, flowamok_grid *g, uint64_t seed, uint32_t density16, uint32_t ring_full16) {
   if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
   if (!g) return fail(ctx, "null grid");
@@ -1134,24 +1446,54 @@ int flowamok_generate_synthetic(flowamok_context *ctx, flowamok_grid *g, uint64_
   g->h_off.clear(); g->h_y.clear(); g->h_x.clear(); g->h_cy.clear(); g->h_cx.clear();
   const int ghg = g->gh_global;
   int nby = ghg >= 15 ? (ghg - 15) / 16 + 1 : 0, nbx = g->gw >= 23 ? (g->gw - 23) / 16 + 1 : 0;
+  std::vector<int> no_sids;
+  if (alloc_straddle_bits(ctx, g, 0, no_sids)) return 1;
+  g->ring_touch = 0; g->ring_swap = g->cuts.empty() ? -1 : 0;
   if (nby > 0 && nbx > 0) {
+    const int lo = g->row0 + g->own0, hi = g->row0 + g->own1;
+    // ring rows of block row by: 16*by + 2 .. 16*by + 14.  A cut at row c (rows < c above, >= c below) runs THROUGH the
+    // rings of block row c / 16 iff c % 16 is in 3..14, and a boundary row (c - 1 or c) holds ring cells iff c % 16 is in 2..15.
+    SynthCuts cutrows;
+    cutrows.n = 0;
+    bool touch = false;
+    std::vector<int64_t> cs = g->cuts;
+    if (cs.empty() && g->halo != 0) cs = {0, lo, hi, ghg};   // cuts unknown: only this band's own boundaries can be judged
+    for (size_t i = 1; i + 1 < cs.size(); i++) {
+      const int64_t c = cs[i];
+      if (c <= 0 || c >= ghg) continue;
+      const int m = (int)(c % 16), by = (int)(c / 16);
+      if (by >= nby) continue;
+      touch |= m >= 2;
+      if (m >= 3 && m <= 14) {
+        if (g->cuts.empty()) return fail(ctx, "synthetic rings straddle this row band: call flowamok_band_set_cuts first (or cut at multiples of 16)");
+        bool dup = false;
+        for (int q = 0; q < cutrows.n; q++) dup |= cutrows.by[q] == by;
+        if (!dup) cutrows.by[cutrows.n++] = by;
+      }
+    }
     unsigned int *cnt = nullptr;
     CU(cudaMalloc(&cnt, 8));
     CU(cudaMemsetAsync(cnt, 0, 8, st));
-    const int lo = g->row0 + g->own0, hi = g->row0 + g->own1;
-    const long long my_blocks = ((long long)(hi - lo) / 16 + 2) * nbx;   // ring blocks that can lie in this band
+    const long long my_blocks = ((long long)(hi - lo) / 16 + 3) * nbx;   // ring blocks that can intersect this band
     CU(cudaMalloc(&g->ring_words, (size_t)my_blocks * SYNTH_RING_WORDS * sizeof(RingWord)));
+    int *sid = nullptr;
+    if (cutrows.n > 0) CU(cudaMalloc(&sid, (size_t)my_blocks * sizeof(int)));
     k_synth_rings<<<nblk((long long)nby * nbx, 128), 128, 0, st>>>(ghg, g->gw, g->pitch, g->row0, lo, hi, seed, nby, nbx,
-                                                                   g->ring_words, cnt, cnt + 1);
+                                                                   g->ring_words, sid, cnt, cutrows);
     CU(cudaGetLastError());
     unsigned int n[2] = {0, 0};
     CU(cudaMemcpyAsync(n, cnt, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     CU(cudaFree(cnt));
-    if (n[1]) return fail(ctx, "%u synthetic rings straddle this row band: choose band boundaries that are multiples of 16", n[1]);
     g->n_rings = n[0]; g->n_ring_cells = (long long)n[0] * 48; g->n_ring_words = (long long)n[0] * SYNTH_RING_WORDS;
     g->ring_stride = SYNTH_RING_WORDS;
-    g->ring_touch = 0; g->ring_swap = -1;   // a listed ring lies at least two rows inside the band (k_synth_rings)
+    if (cutrows.n > 0) {
+      if (alloc_straddle_bits(ctx, g, (long long)cutrows.n * nbx, no_sids)) return 1;
+      g->ring_sid = sid;
+    }
+    // the same decision on every band (it depends on the cuts only); without the cuts: this band's own view, agreed later
+    g->ring_touch = touch ? 1 : 0;
+    g->ring_swap = g->cuts.empty() ? -1 : (touch ? 1 : 0);
   }
   CU(cudaStreamSynchronize(st));
   g->tick = 0;

@@ -17,6 +17,7 @@
 
 #include <type_traits>
 
+#include "fa_band.cuh"
 #include "fa_stream.h"
 #include "fa_tiles.h"
 
@@ -47,6 +48,7 @@ struct Diag {
   unsigned long long passes;   // fixpoint iterations of k_u_iter
   unsigned long long sweeps;   // worklist entries relaxed
   unsigned long long ticks;
+  unsigned long long hist[32]; // ticks by number of k_u_iter iterations (last bucket: 31 and more)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -84,7 +86,7 @@ __device__ __forceinline__ bool grid_barrier(IterState *is, unsigned int nblocks
     } else {
       long long spins = 0;
       while (*vgen == gen) {
-        if (++spins > (1LL << 25)) { atomicExch(&is->error, 1u); ok = 0; break; }
+        if (++spins > (1LL << 28)) { atomicExch(&is->error, 1u); ok = 0; break; }   // about half a minute
         __nanosleep(100);
       }
     }
@@ -109,9 +111,16 @@ constexpr unsigned int UIT_TAIL = FA_UIT_TAIL;   // frontier length below which 
 constexpr int UIT_CHASE = FA_UIT_CHASE;   // links of a waiting queue one visit follows before it hands over to the list
 
 // first_it = 0: start from the frontier k_u_local left in qlist0 / qn[0]; 1: resume from qlist1 / qn[1] (band merge)
+//
+// P2P = true (a row band whose neighbours' mailboxes are mapped, fa_band.cuh): the whole band protocol of the U phase
+// runs inside this launch.  CTA 0 swaps the boundary rows with the neighbours before the first iteration (the ghost
+// rows then hold the neighbours' rows after THEIR local levels) and after every local fixpoint; the words its merge
+// wakes become the next frontier, and all bands vote -- device to device -- whether anybody woke anything.  No NCCL
+// call, no kernel boundary and no host round trip per convergence round; the other CTAs wait at the grid barrier.
+template <bool P2P>
 __global__ void __launch_bounds__(UIT_THREADS, 2)
 k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *qlist0, unsigned int *qlist1,
-         unsigned int first_it, IterState *is, Diag *diag) {
+         unsigned int first_it, IterState *is, Diag *diag, const __grid_constant__ BandLink L) {
   const int tid = threadIdx.x, nt = blockDim.x, b = blockIdx.x, nb = gridDim.x, lane = tid & 31;
   volatile IterState *vis = is;
   unsigned int *ql[2] = {qlist0, qlist1};
@@ -153,27 +162,48 @@ k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *
   };
 
   // iteration `it` visits the entry indices in qlist[it & 1] (length qn[it % 3]) and appends to qlist[(it + 1) & 1]
-  unsigned int it = first_it;
-  bool tail = false;   // once the frontier is short, CTA 0 finishes alone: no more grid-wide barriers
-  for (;; it++) {
-    const unsigned int n = vis->qn[it % 3u];
-    if (n == 0) break;                       // same value in every CTA: uniform exit
-    if (!tail && n <= UIT_TAIL) {            // uniform decision: every CTA read the same n after the barrier
-      if (b != 0) break;
-      tail = true;
+  unsigned int it = first_it, its_done = 0;
+  if (P2P) {
+    if (b == 0) band_exchange_u(g, L, table, false, nullptr, nullptr);
+    if (!grid_barrier(is, nb)) return;
+  }
+  for (;;) {   // convergence rounds (one, unless P2P)
+    bool tail = false;   // once the frontier is short, CTA 0 finishes alone: no more grid-wide barriers
+    for (;; it++) {
+      const unsigned int n = vis->qn[it % 3u];
+      if (n == 0) break;                       // same value in every CTA: uniform exit
+      if (!tail && n <= UIT_TAIL) {            // uniform decision: every CTA read the same n after the barrier
+        if (b != 0) break;
+        tail = true;
+      }
+      const unsigned int *src = ql[it & 1];
+      unsigned int *dst = ql[(it + 1) & 1];
+      unsigned int *out_cnt = &is->qn[(it + 1) % 3u];
+      if (b == 0 && tid == 0) is->qn[(it + 2) % 3u] = 0;   // output slot of iteration it+1; idle since barrier(it-1)
+      const unsigned int stride = tail ? (unsigned)nt : (unsigned)nb * nt;
+      for (unsigned int k0 = tail ? 0u : (unsigned)b * nt; k0 < n; k0 += stride) {
+        const unsigned int k = k0 + tid;
+        if (tail) visit_and_flush(std::true_type(), k < n, k < n ? src[k] : 0u, dst, out_cnt);
+        else visit_and_flush(std::false_type(), k < n, k < n ? src[k] : 0u, dst, out_cnt);
+      }
+      its_done++;
+      if (tail) { __threadfence(); __syncthreads(); }
+      else if (!grid_barrier(is, nb)) return;
     }
-    const unsigned int *src = ql[it & 1];
-    unsigned int *dst = ql[(it + 1) & 1];
-    unsigned int *out_cnt = &is->qn[(it + 1) % 3u];
-    if (b == 0 && tid == 0) is->qn[(it + 2) % 3u] = 0;   // output slot of iteration it+1; idle since barrier(it-1)
-    const unsigned int stride = tail ? (unsigned)nt : (unsigned)nb * nt;
-    for (unsigned int k0 = tail ? 0u : (unsigned)b * nt; k0 < n; k0 += stride) {
-      const unsigned int k = k0 + tid;
-      if (tail) visit_and_flush(std::true_type(), k < n, k < n ? src[k] : 0u, dst, out_cnt);
-      else visit_and_flush(std::false_type(), k < n, k < n ? src[k] : 0u, dst, out_cnt);
+    if (!P2P) break;
+    // CTA 0 stands at the iteration whose list is empty (slot it % 3 == 0, slot (it + 1) % 3 was cleared one iteration
+    // ago): the merge appends the woken words to ql[it & 1] / qn[it % 3], which is where the next iteration reads.
+    if (b == 0) {
+      band_exchange_u(g, L, table, true, ql[it & 1], &is->qn[it % 3u]);
+      const bool any = band_vote(L, vis->qn[it % 3u] != 0u);
+      if (tid == 0) {
+        L.dev->go = any ? 1u : 0u; L.dev->round_it = it; L.dev->rounds++;
+        is->qn[(it + 1) % 3u] = 0;
+      }
     }
-    if (tail) { __threadfence(); __syncthreads(); }
-    else if (!grid_barrier(is, nb)) return;
+    if (!grid_barrier(is, nb)) return;
+    it = *(volatile unsigned int *)&L.dev->round_it;
+    if (*(volatile unsigned int *)&L.dev->go == 0u) break;
   }
   {   // visits of this CTA: warp sums, then one shared and one global atomic
     __shared__ unsigned long long cta_relaxed;
@@ -188,7 +218,8 @@ k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *
     if (relaxed) atomicAdd(&diag->sweeps, relaxed);
     if (b == 0) {
       is->qn[0] = 0; is->qn[1] = 0; is->qn[2] = 0;   // the slot everyone just read is 0 already
-      atomicAdd(&diag->passes, (unsigned long long)(it - first_it));
+      atomicAdd(&diag->passes, (unsigned long long)its_done);
+      atomicAdd(&diag->hist[its_done < 31u ? its_done : 31u], 1ull);
     }
   }
 }
@@ -290,18 +321,27 @@ constexpr int RING_ITEMS = 4;   // (survivor, word) items a thread tests at once
 // ORs its grants into my|mx (one 64-bit atomic per word).  Rings of one uniform length (off == nullptr: the synthetic
 // network) are handled as a flat list of (survivor, word) items spread over all threads, every thread holding several
 // independent loads in flight -- two memory latencies per CTA; CSR rings take one warp per survivor.
+//
+// Row bands: a ring that straddles a cut is listed by every band it touches, each with the words of its own rows
+// only, and carries its straddle id (sid[k] >= 0, the same number in every band).  Such a ring is only JUDGED here:
+// a band that finds an objection clears bit sid of `partial`; k_band_xring ANDs the bands' verdicts and k_rings_mark
+// applies the grants.  sid == nullptr: no ring straddles.
 __global__ void __launch_bounds__(RINGS_PER_BLOCK)
-k_rings(const __grid_constant__ GridView g, const RingWord *words, const unsigned long long *off, long long n, int stride) {
+k_rings(const __grid_constant__ GridView g, const RingWord *words, const unsigned long long *off, long long n, int stride,
+        const int *sid, u32 *partial) {
   __shared__ unsigned int surv[RINGS_PER_BLOCK];
   __shared__ unsigned int okf[RINGS_PER_BLOCK];
   __shared__ unsigned int wbase[RINGS_PER_BLOCK / 32 + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long k = (long long)blockIdx.x * RINGS_PER_BLOCK + tid;
   bool pass0 = false;
+  int my_sid = -1;
   if (k < n) {
     const unsigned long long b = off ? off[k] : (unsigned long long)k * stride;
     const unsigned long long e = off ? off[k + 1] : b + stride;
     pass0 = e > b && ring_word_ok(g, words[b]);
+    if (sid) my_sid = sid[k];
+    if (my_sid >= 0 && !pass0) atomicAnd(&partial[my_sid >> 5], ~(1u << (my_sid & 31)));
   }
   const unsigned m = __ballot_sync(0xFFFFFFFFu, pass0);
   if (lane == 0) wbase[warp + 1] = __popc(m);
@@ -312,9 +352,9 @@ k_rings(const __grid_constant__ GridView g, const RingWord *words, const unsigne
   if (pass0) surv[wbase[warp] + __popc(m & ((1u << lane) - 1u))] = (unsigned int)tid;
   __syncthreads();
   const int nsurv = (int)wbase[RINGS_PER_BLOCK / 32];
+  const long long ring0 = (long long)blockIdx.x * RINGS_PER_BLOCK;
   if (!off) {   // uniform ring length: flat (survivor, word) items
     const int nitems = nsurv * stride;
-    const long long ring0 = (long long)blockIdx.x * RINGS_PER_BLOCK;
     for (int i0 = tid; i0 < nitems; i0 += RINGS_PER_BLOCK * RING_ITEMS) {   // test: RING_ITEMS independent loads in flight
       RingWord w[RING_ITEMS];
       int si[RING_ITEMS];
@@ -335,6 +375,15 @@ k_rings(const __grid_constant__ GridView g, const RingWord *words, const unsigne
         if (!ok[q]) okf[si[q]] = 0u;   // benign race: everybody writes 0
     }
     __syncthreads();
+    if (sid)   // straddling survivors: verdict only
+      for (int s_ = tid; s_ < nsurv; s_ += RINGS_PER_BLOCK) {
+        const int d = sid[ring0 + surv[s_]];
+        if (d >= 0) {
+          if (!okf[s_]) atomicAnd(&partial[d >> 5], ~(1u << (d & 31)));
+          okf[s_] = 0u;   // not marked here
+        }
+      }
+    if (sid) __syncthreads();
     for (int i = tid; i < nitems; i += RINGS_PER_BLOCK) {   // mark the rings that passed
       const int s_ = i / stride;
       if (!okf[s_]) continue;
@@ -344,15 +393,34 @@ k_rings(const __grid_constant__ GridView g, const RingWord *words, const unsigne
     return;
   }
   for (int si = warp; si < nsurv; si += RINGS_PER_BLOCK / 32) {
-    const long long r = (long long)blockIdx.x * RINGS_PER_BLOCK + surv[si];
+    const long long r = ring0 + surv[si];
     const unsigned long long b = off[r], e = off[r + 1];
+    const int d = sid ? sid[r] : -1;
     bool ok = true;
     for (unsigned long long t = b + lane; t < e; t += 32) ok = ok && ring_word_ok(g, words[t]);
-    if (!__all_sync(0xFFFFFFFFu, ok)) continue;
+    ok = __all_sync(0xFFFFFFFFu, ok);
+    if (d >= 0) {
+      if (!ok && lane == 0) atomicAnd(&partial[d >> 5], ~(1u << (d & 31)));
+      continue;
+    }
+    if (!ok) continue;
     for (unsigned long long t = b + lane; t < e; t += 32) {
       const RingWord w = words[t];
       if (w.gY | w.gX) atomicOr((unsigned long long *)&g.mymx[w.wi], (unsigned long long)w.gY | ((unsigned long long)w.gX << 32));
     }
+  }
+}
+// the grants of the straddling rings that passed in EVERY band (pass: AND of the bands' verdicts); a thread per ring
+__global__ void k_rings_mark(const __grid_constant__ GridView g, const RingWord *words, const unsigned long long *off, long long n, int stride,
+                             const int *sid, const u32 *pass) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int d = sid[k];
+  if (d < 0 || !((pass[d >> 5] >> (d & 31)) & 1u)) return;
+  const unsigned long long b = off ? off[k] : (unsigned long long)k * stride, e = off ? off[k + 1] : b + stride;
+  for (unsigned long long t = b; t < e; t++) {
+    const RingWord w = words[t];
+    if (w.gY | w.gX) atomicOr((unsigned long long *)&g.mymx[w.wi], (unsigned long long)w.gY | ((unsigned long long)w.gX << 32));
   }
 }
 
@@ -554,22 +622,30 @@ __global__ void k_synth(int gh, int gw, int pitch, int row0, int gh_global, u64 
 }
 // analytic ring list of the generator: 48 cells per ring, stored as SYNTH_RING_WORDS word entries (unused ones empty)
 constexpr int SYNTH_RING_WORDS = 26;
-// rows [lo, hi) (global) are the band this device owns: a ring is listed by the device that owns ALL its rows
+// rows [lo, hi) (global) are the band this device owns: a ring is listed by every device that owns at least one of its
+// rows, with the words of the owned rows only (the other entries stay empty).  A ring cut by a band boundary gets the
+// straddle id idx(by) * nbx + bx, idx = position of its block row in `cutrows` (the block rows some cut runs through,
+// the same list on every device).
+struct SynthCuts {
+  int n;
+  int by[BAND_MAXW];
+};
 __global__ void k_synth_rings(int gh, int gw, int pitch, int row0, int lo, int hi, u64 seed, int nby, int nbx,
-                              RingWord *words, unsigned int *nrings, unsigned int *nstraddle) {
+                              RingWord *words, int *sid, unsigned int *nrings, const SynthCuts cutrows) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nby * nbx) return;
   int by = b / nbx, bx = b % nbx;
   if (!((16 * by + 14 <= gh - 1) && (16 * bx + 22 <= gw - 1))) return;
   u64 hb = synth_hash(seed, 1, (u64)by, (u64)bx);
   if (!(hb & 1)) return;
-  {
-    int r_lo = 16 * by + 2, r_hi = 16 * by + 14;
-    if (r_hi < lo || r_lo >= hi) return;                       // another band's ring
-    if (r_lo < lo || r_hi >= hi) { atomicAdd(nstraddle, 1u); return; }   // cut by a band boundary
-  }
+  const int r_lo = 16 * by + 2, r_hi = 16 * by + 14;
+  if (r_hi < lo || r_lo >= hi) return;                       // another band's ring
+  int d = -1;
+  for (int i = 0; i < cutrows.n; i++)
+    if (cutrows.by[i] == by) d = i * nbx + bx;
   bool cw = (hb >> 1) & 1;
   unsigned int slot = atomicAdd(nrings, 1u);
+  if (sid) sid[slot] = d;
   RingWord *out = words + (size_t)slot * SYNTH_RING_WORDS;
   const int x0 = 16 * bx + 10, wa = x0 >> 5, wb = (x0 + 12) >> 5;
   for (int i = 0; i < SYNTH_RING_WORDS; i++) {
@@ -577,8 +653,9 @@ __global__ void k_synth_rings(int gh, int gw, int pitch, int row0, int lo, int h
     int ly = i >> 1, w = (i & 1) ? wb : wa;
     RingWord e = {0, 0, 0, 0, 0, 0, 0, 0};
     int y = 16 * by + 2 + ly;
-    e.wi = (u32)((size_t)(y - row0) * pitch + w);
-    if (!((i & 1) && wa == wb))
+    const bool mine = y >= lo && y < hi;
+    e.wi = mine ? (u32)((size_t)(y - row0) * pitch + w) : 0u;
+    if (mine && !((i & 1) && wa == wb))
       for (int lx = 0; lx <= 12; lx++) {
         if (!(ly == 0 || ly == 12 || lx == 0 || lx == 12)) continue;
         int x = x0 + lx;
@@ -649,6 +726,33 @@ __global__ void k_render(int gh, int gw, int pitch, long long scale, const U4 *r
     px = draw ? (occupied ? d_mix(0.5f, grey, 0.5f, base) : grey) : base;
   }
   pixels[i] = px;
+}
+
+// Position-dependent digest of the owned rows: out[0] += sum, out[1] ^= xor over the owned cells of
+// H(global cell index, heading, preference, colour, rng state).  Sums of bands add up to the whole grid's, so a banded run
+// is compared with the single-grid run -- or with numpy on a downloaded state -- without moving the planes to the host.
+__device__ __host__ inline u64 digest_cell(u64 idx, u32 bits, u32 color, u64 rng) {
+  return splitmix64(splitmix64(idx * 0x9E3779B97F4A7C15ULL + (((u64)bits << 32) | color)) ^ rng);
+}
+__global__ void k_digest(int own0, int own1, int gw, int pitch, int row0, const U4 *head, const u32 *prefp, const u32 *color,
+                         const u64 *rng, unsigned long long *out) {
+  const long long n = (long long)(own1 - own0) * gw;
+  u64 sum = 0, x = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int y = own0 + (int)(i / gw), xx = (int)(i % gw);
+    const size_t o = (size_t)y * pitch + (xx >> 5), c = (size_t)y * pitch * 32 + xx;
+    const u32 bit = 1u << (xx & 31);
+    const U4 h = head[o];
+    const u32 bits = ((h.x & bit) ? 1u : 0u) | ((h.y & bit) ? 2u : 0u) | ((h.z & bit) ? 4u : 0u) | ((h.w & bit) ? 8u : 0u) |
+                     ((prefp[o] & bit) ? 16u : 0u);
+    const u64 v = digest_cell((u64)(y + row0) * (u64)gw + (u64)xx, bits, color[c], rng[c]);
+    sum += v; x ^= v;
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+    x ^= __shfl_xor_sync(0xFFFFFFFFu, x, d);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], sum); atomicXor(&out[1], x); }
 }
 
 // leak list compaction helpers (flowamok_step_leaks)

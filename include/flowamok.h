@@ -113,6 +113,11 @@ int flowamok_grid_clone(flowamok_context *ctx, const flowamok_grid *src, flowamo
 /* diagnostics of the ticks since the last call: ticks, fixpoint iterations, worklist entries relaxed */
 int flowamok_stats(flowamok_context *ctx, flowamok_grid *g, int64_t *ticks, int64_t *passes, int64_t *sweeps);
 
+/* Digest of the owned rows, computed on the device: sum and xor (mod 2^64) over the cells of a hash of (global cell index,
+ * heading, preference, colour, rng state) -- see digest_cell in csrc/fa_kernels.cuh.  Sums / xors of bands combine to
+ * the whole grid's: the size-independent equality check of BASELINE config 5 (65536^2 does not fit the host).  Synchronous. */
+int flowamok_grid_digest(flowamok_context *ctx, const flowamok_grid *g, uint64_t *sum, uint64_t *xor_);
+
 /* Synthetic road network of SURVEY.md App. E (monotone avenue lattice + ring tiles), generated on the
  * device; density16 = car probability per road cell in 1/65536, ring_full16 = share of rings that start
  * completely full in 1/16.  Also installs the analytic cycle list.  Synchronous. */
@@ -148,6 +153,25 @@ int flowamok_band_leaks(flowamok_context *ctx, flowamok_grid *g, int64_t *n_leak
 int flowamok_band_comm_id(void *id128);
 int flowamok_band_comm_init(flowamok_context *ctx, const void *id128, int rank, int world);
 int flowamok_band_step(flowamok_context *ctx, flowamok_grid *g, int perfect, int64_t n_ticks, int64_t *rounds);
+/* ---- P2P transport (NVLink / NVSwitch peer memory; csrc/fa_band.cuh): the protocol above without NCCL and without the
+ * host.  Every band owns a mailbox the other bands map; senders store rows and message numbers into the receiver's
+ * mailbox, receivers poll their own memory on the device; the convergence rounds of the U phase and their termination
+ * vote run inside one persistent kernel.  Set-up, on every band:
+ *     set_cuts(world, cuts)            row boundaries of ALL bands; then install the cycles (flowamok_set_cycles with the
+ *                                      GLOBAL list, or flowamok_generate_synthetic): rings may straddle cuts
+ *     p2p_open(rank, world, h, &ptr)   allocates + exports the mailbox (64-byte CUDA IPC handle / raw device pointer)
+ *     p2p_connect(handles, ptrs, k)    maps the peers (handles gathered from all ranks, or pointers inside one process)
+ * afterwards flowamok_band_step runs whole ticks with no host synchronisation (rounds == NULL keeps it asynchronous). */
+int flowamok_band_set_cuts(flowamok_context *ctx, flowamok_grid *g, int world, const int64_t *cuts);
+int flowamok_band_p2p_open(flowamok_context *ctx, flowamok_grid *g, int rank, int world, void *handle64, void **local_ptr);
+int flowamok_band_p2p_connect(flowamok_context *ctx, flowamok_grid *g, const void *handles, void *const *local_ptrs, int bands_on_device);
+/* unmap the peers (every band; then synchronise the processes before any grid is freed) */
+int flowamok_band_p2p_close(flowamok_context *ctx, flowamok_grid *g);
+/* rings that straddle a cut under the host-driven protocol: verdict words of this band (after flowamok_band_rings),
+ * to be AND-ed over all bands and applied */
+int flowamok_band_ring_words(flowamok_context *ctx, const flowamok_grid *g, int64_t *n_words);
+int flowamok_band_ring_verdicts(flowamok_context *ctx, flowamok_grid *g, void *dev_buf);
+int flowamok_band_rings_apply(flowamok_context *ctx, flowamok_grid *g, const void *dev_pass);
 /* car state only (heading, colour, preference, rng) of the owned rows from whole-grid host arrays; roads, cycles
  * and halo rows are left alone.  Synchronous. */
 int flowamok_grid_upload_cars(flowamok_context *ctx, flowamok_grid *g, const int8_t *dy, const int8_t *dx, const uint32_t *color,

@@ -39,6 +39,7 @@ struct HostGrid {
   unsigned iters = 0, relaxed = 0;
   Rings rings;
   bool has_rings = false;
+  std::vector<u32> rbits;   // verdicts of this band on the rings that straddle its cuts
 };
 
 HostGrid *make(int gh_global, int gw, int row_begin, int row_end, int halo, int variant) {
@@ -113,29 +114,43 @@ void u_iter(HostGrid *h, const GridView &g, int order) {
   }
 }
 
-void do_rings(HostGrid *h, const GridView &g) {  // steppers.fut:189-224, sparse form
+// steppers.fut:189-224, sparse form.  The ring list is GLOBAL; a grid judges and marks the cells of its own
+// rows.  kind: 0 = judge every ring; rings wholly inside the owned rows are marked at once, rings that straddle a band
+// cut only get their verdict bit cleared on an objection (h->rbits, bit k = ring k, 1 = no objection);
+// 1 = mark the straddling rings whose bit is set in `pass`.
+void do_rings(HostGrid *h, const GridView &g, int kind = 0, const u32 *pass = nullptr) {
   if (!h->has_rings) return;
   const Rings &R = h->rings;
-  size_t n = R.off.size() - 1;
-  std::vector<char> pass(n);
+  const size_t n = R.off.size() - 1;
+  const int64_t lo = h->row0 + h->own0, hi = h->row0 + h->own1;
+  if (h->rbits.size() != (n + 31) / 32) h->rbits.assign((n + 31) / 32, 0xFFFFFFFFu);
   for (size_t k = 0; k < n; k++) {
-    bool ok = true;
-    for (int64_t t = R.off[k]; t < R.off[k + 1] && ok; t++) {
+    bool in = false, out = false, ok = true;
+    for (int64_t t = R.off[k]; t < R.off[k + 1]; t++) {
+      if (R.y[t] < lo || R.y[t] >= hi) { out = true; continue; }
+      in = true;
       size_t o = (size_t)(R.y[t] - h->row0) * h->pitch + (R.x[t] >> 5);
       u32 bit = 1u << (R.x[t] & 31);
       U4 hd = g.head_in[o];
       int dy = (hd.x & bit) ? ((hd.y & bit) ? -1 : 1) : 0, dx = (hd.z & bit) ? ((hd.w & bit) ? -1 : 1) : 0;
       if ((g.calc[o] & bit) || dy != R.cy[t] || dx != R.cx[t]) ok = false;
     }
-    pass[k] = ok;
+    if (!in) continue;
+    bool mark;
+    if (kind == 0) {
+      if (out && !ok) h->rbits[k >> 5] &= ~(1u << (k & 31));
+      mark = ok && !out;
+    } else {
+      mark = out && ((pass[k >> 5] >> (k & 31)) & 1u);
+    }
+    if (!mark) continue;
+    for (int64_t t = R.off[k]; t < R.off[k + 1]; t++) {
+      if (R.y[t] < lo || R.y[t] >= hi) continue;
+      size_t o = (size_t)(R.y[t] - h->row0) * h->pitch + (R.x[t] >> 5);
+      u32 bit = 1u << (R.x[t] & 31);
+      if (R.grant[t] == 1) g.mymx[o] |= (u64)bit; else g.mymx[o] |= (u64)bit << 32;
+    }
   }
-  for (size_t k = 0; k < n; k++)
-    if (pass[k])
-      for (int64_t t = R.off[k]; t < R.off[k + 1]; t++) {
-        size_t o = (size_t)(R.y[t] - h->row0) * h->pitch + (R.x[t] >> 5);
-        u32 bit = 1u << (R.x[t] & 31);
-        if (R.grant[t] == 1) g.mymx[o] |= (u64)bit; else g.mymx[o] |= (u64)bit << 32;
-      }
 }
 
 template <int SW, int NW, int CAP>
@@ -358,6 +373,19 @@ void emul_band_rings(void *p) {
   HostGrid *h = (HostGrid *)p;
   GridView g = view(h, 0, 0);
   do_rings(h, g);
+}
+int64_t emul_band_ring_words(void *p) {
+  HostGrid *h = (HostGrid *)p;
+  return h->has_rings ? (int64_t)((h->rings.off.size() - 1 + 31) / 32) : 0;
+}
+void emul_band_ring_verdicts(void *p, uint32_t *out) {   // copy and reset
+  HostGrid *h = (HostGrid *)p;
+  for (size_t i = 0; i < h->rbits.size(); i++) { out[i] = h->rbits[i]; h->rbits[i] = 0xFFFFFFFFu; }
+}
+void emul_band_rings_apply(void *p, const uint32_t *pass) {
+  HostGrid *h = (HostGrid *)p;
+  GridView g = view(h, 0, 0);
+  do_rings(h, g, 1, pass);
 }
 int64_t emul_band_move(void *p, int chooser, uint32_t tape_bit) {
   HostGrid *h = (HostGrid *)p;

@@ -30,10 +30,13 @@ class EmulBand:
                       ("emul_band_pack_u", [C.c_void_p, C.c_int, C.c_void_p]),
                       ("emul_band_merge_u", [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
                       ("emul_band_u_resume", [C.c_void_p]), ("emul_band_rings", [C.c_void_p]),
+                      ("emul_band_ring_words", [C.c_void_p]), ("emul_band_ring_verdicts", [C.c_void_p, C.c_void_p]),
+                      ("emul_band_rings_apply", [C.c_void_p, C.c_void_p]),
                       ("emul_band_move", [C.c_void_p, C.c_int, C.c_uint32]),
                       ("emul_set_rings", [C.c_void_p, C.c_int64] + [C.c_void_p] * 6)):
             getattr(L, f).argtypes = at
         L.emul_band_merge_u.restype = C.c_int64
+        L.emul_band_ring_words.restype = C.c_int64
         L.emul_band_move.restype = C.c_int64
         self.gh, self.gw = arrs["uy"].shape
         self.p = L.emul_band_new(self.gh, self.gw, row_begin, row_end, variant)
@@ -45,20 +48,12 @@ class EmulBand:
         L.emul_band_msg_bytes(self.p, C.byref(sb), C.byref(ub))
         self.state_bytes, self.u_bytes = sb.value, ub.value
         self.chooser, self.tape, self.tick_no, self.woken_n, self.leaks_n = chooser, tape, 0, 0, 0
-        if rings is not None:
+        if rings is not None:      # the GLOBAL list: every band judges / marks the cells of its own rows
             off, idx, cy, cx, grant = rings
-            lo, hi = row_begin, row_end
-            keep = [k for k in range(len(off) - 1) if lo <= (idx[off[k]:off[k + 1]] // self.gw).min()
-                    and (idx[off[k]:off[k + 1]] // self.gw).max() < hi]
-            o2, i2 = [0], []
-            for k in keep:
-                i2 += list(range(off[k], off[k + 1]))
-                o2.append(len(i2))
-            i2 = np.asarray(i2, np.int64)
-            a = [np.asarray(o2, np.int64), np.ascontiguousarray(idx[i2] // self.gw), np.ascontiguousarray(idx[i2] % self.gw),
-                 np.ascontiguousarray(cy[i2]), np.ascontiguousarray(cx[i2]), np.ascontiguousarray(grant[i2])]
+            a = [np.ascontiguousarray(off, np.int64), np.ascontiguousarray(idx // self.gw), np.ascontiguousarray(idx % self.gw),
+                 np.ascontiguousarray(cy), np.ascontiguousarray(cx), np.ascontiguousarray(grant)]
             self._rings = a
-            L.emul_set_rings(self.p, len(o2) - 1, *[v.ctypes.data for v in a])
+            L.emul_set_rings(self.p, len(off) - 1, *[v.ctypes.data for v in a])
 
     def _tb(self):
         return int(self.tape[self.tick_no % len(self.tape)]) if self.tape is not None else 0
@@ -96,6 +91,18 @@ class EmulBand:
 
     def rings(self):
         self.L.emul_band_rings(self.p)
+
+    def ring_words(self):
+        return int(self.L.emul_band_ring_words(self.p))
+
+    def ring_buffer(self):
+        return torch.zeros(max(1, self.ring_words()), dtype=torch.int32)
+
+    def ring_verdicts(self, buf):
+        self.L.emul_band_ring_verdicts(self.p, buf.data_ptr())
+
+    def rings_apply(self, buf):
+        self.L.emul_band_rings_apply(self.p, buf.data_ptr())
 
     def move(self):
         self.leaks_n += int(self.L.emul_band_move(self.p, self.chooser, self._tb()))
@@ -155,7 +162,14 @@ def _case_synth_perfect():
     return arrs, rings, True, 10, 0, 16
 
 
-@pytest.mark.parametrize("world,case", [(2, _case_random), (3, _case_jam), (2, _case_synth_perfect)])
+def _case_synth_perfect_straddle():
+    """cuts that are NOT multiples of 16: rings straddle the cuts (per-ring pass bits AND-ed over the bands)"""
+    arrs, rings = synth_ref.generate(100, 150, seed=3, ring_full16=12)
+    return arrs, rings, True, 10, 0, 1
+
+
+@pytest.mark.parametrize("world,case", [(2, _case_random), (3, _case_jam), (2, _case_synth_perfect),
+                                        (2, _case_synth_perfect_straddle), (3, _case_synth_perfect_straddle)])
 def test_bands_equal_single_grid(world, case):
     arrs, rings, perfect, ticks, variant, align = case()
     og, ch = oracle_grid(arrs), O.Chooser(O.CHOOSE_RANDOM)

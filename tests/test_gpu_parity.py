@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import synth_ref
-from util import O, ROOT, STATE_FIELDS, assert_state_equal, oracle_grid, random_grid, state_of
+from util import O, ROOT, STATE_FIELDS, assert_state_equal, oracle_grid, random_grid, state_digest, state_of
 
 pytestmark = pytest.mark.gpu
 
@@ -313,6 +313,36 @@ def test_futhark_entry_points_readme_program(ctx):
     L.futhark_context_config_free(cfg)
 
 
+@pytest.mark.parametrize("sid", range(14))
+def test_futhark_entry_points_all_scenarios(ctx, sid):
+    """The scenario table of csrc/fa_futhark.inc (third transcription of explorer/scenarios.fut) against the oracle's,
+    which tests/test_scenario_tables.py pins to the mechanically derived fixture: mk_anim(scenario sid) on the
+    explorer's 108 x 192 grid, every frame of the first 12 steps (init + scenario.step edits included)."""
+    import ctypes as C
+    import flowamok_b200.capi as capi
+    L = capi.lib()
+    cfg = L.futhark_context_config_new()
+    L.flowamok_futhark_set_scenario(cfg, sid)
+    fctx = L.futhark_context_new(cfg)
+    assert not L.futhark_context_get_error(fctx)
+    st = C.c_void_p()
+    assert L.futhark_entry_init(fctx, C.byref(st), 108, 192, 2, 123) == 0
+    oa = O.Anim(sid, 108, 192, 2, 123)
+    for k in range(12):
+        px, st2 = C.c_void_p(), C.c_void_p()
+        assert L.futhark_entry_step(fctx, C.byref(px), C.byref(st2), st) == 0
+        frame = np.zeros((216, 384), np.uint32)
+        assert L.futhark_values_u32_2d(fctx, px, frame.ctypes.data) == 0
+        assert L.futhark_context_sync(fctx) == 0
+        assert np.array_equal(frame, oa.step(render=True)), f"sid {sid} frame {k}"
+        L.futhark_free_u32_2d(fctx, px)
+        L.futhark_free_opaque_state(fctx, st)
+        st = st2
+    L.futhark_free_opaque_state(fctx, st)
+    L.futhark_context_free(fctx)
+    L.futhark_context_config_free(cfg)
+
+
 def test_grid_clone_is_independent(ctx):
     import ctypes as C
     arrs = random_grid(5, 60, 90, car_p=0.5)
@@ -376,6 +406,86 @@ def test_row_bands_on_one_gpu_equal_single_grid(ctx, n_bands, perfect):
             assert_state_equal(want, got, f"{n_bands} bands tick {t}")
     assert sum(b.leaks() for b in bands) == leaks
     assert run.rounds >= 12
+
+
+def _gather_bands(bands, gh, gw, like):
+    got = {k: np.zeros((gh, gw), like[k].dtype) for k in STATE_FIELDS}
+    for b in bands:
+        d = b.grid.download(fields=STATE_FIELDS)
+        lo, hi = b.rows
+        for k in STATE_FIELDS:
+            got[k][lo:hi] = d[k][lo:hi]
+    return got
+
+
+P2P_CASES = [
+    # (bands' cuts, perfect, how the cycles are installed)
+    ([0, 70, 150], False, None),                 # quick mode, arbitrary cuts, random network (diagonal / off-road cars)
+    ([0, 41, 99, 150], False, None),
+    ([0, 64, 128, 192, 256], True, "synth"),     # cuts on multiples of 16: no ring is cut
+    ([0, 71, 135, 256], True, "synth"),          # cuts THROUGH the ring tiles: verdict bits AND-ed over the bands (k_band_xring)
+    ([0, 130, 256], True, "list"),               # the same through flowamok_set_cycles with the global list
+    ([0, 66, 256], True, "synth"),               # a cut on a ring's first row: touches, does not straddle
+]
+
+
+@pytest.mark.parametrize("cuts,perfect,cycles", P2P_CASES)
+def test_p2p_bands_on_one_gpu_equal_oracle(cuts, perfect, cycles):
+    """The multi-GPU transport itself on ONE device: every band has its own context / stream, the peers' mailboxes are
+    plain device pointers, and the bands' kernels (k_band_xstate, the persistent k_u_iter with the convergence rounds
+    and the termination vote inside, k_band_xring, k_band_xu) wait for each other on the device exactly as they do
+    across NVLink.  Whole state vs the oracle every few ticks."""
+    import flowamok_b200 as fa
+    from flowamok_b200.bands import DeviceBand, LocalBandsP2P
+    if perfect:
+        gh, gw = 256, 1300
+        arrs, rings = synth_ref.generate(gh, gw, seed=2, ring_full16=6)
+    else:
+        gh, gw = 150, 2100
+        arrs, rings = random_grid(9, gh, gw, n_lines=300, car_p=0.8, weird_p=0.02, offroad_p=0.01), None
+    ctxs, bands = [], []
+    for r in range(len(cuts) - 1):
+        c = fa.Context()                      # its own stream
+        b = DeviceBand(c, gh, gw, cuts[r], cuts[r + 1])
+        b.set_cuts(cuts)
+        if cycles == "synth":
+            b.grid.generate_synthetic(seed=2, ring_full16=6)
+        else:
+            b.grid.upload(**arrs)
+            if cycles == "list":
+                off, idx, cy, cx, grant = rings
+                b.grid.set_cycles(off, idx // gw, idx % gw, cy, cx, grant)      # the GLOBAL list on every band
+        ctxs.append(c); bands.append(b)
+    run = LocalBandsP2P(bands)
+    og, ch = oracle_grid(arrs), O.Chooser(O.CHOOSE_RANDOM)
+    leaks = 0
+    for t in range(12):
+        n, _l = og.step_perfect_sparse(ch, rings) if perfect else og.step_quick(ch)
+        leaks += n
+        run.step(perfect, 1)
+        if t % 4 == 3:
+            want = state_of(og)
+            assert_state_equal(want, _gather_bands(bands, gh, gw, want), f"cuts {cuts} tick {t}")
+    assert sum(b.leaks() for b in bands) == leaks
+    assert run.rounds >= 12
+    want = state_of(og)
+    ds = [b.grid.digest() for b in bands]
+    s = sum(d[0] for d in ds) & (2**64 - 1)
+    x = 0
+    for d in ds:
+        x ^= d[1]
+    assert (s, x) == state_digest(want), "the bands' device digests must combine to the whole grid's"
+    for b in bands:
+        b.p2p_close()
+    for b in bands:
+        b.grid.free()
+
+
+def test_device_digest_matches_numpy(ctx):
+    arrs = random_grid(3, 90, 200, car_p=0.5)
+    g = ctx.grid_from_arrays(**arrs)
+    g.step(False, 3)
+    assert g.digest() == state_digest(dev_state(g))
 
 
 def _oracle_synth(gh, gw, seed=1):

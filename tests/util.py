@@ -80,6 +80,29 @@ def assert_state_equal(a, b, what=""):
             raise AssertionError(f"{what}: field {k} differs at {len(bad)} cells, first {bad[:5].tolist()}")
 
 
+def _splitmix64(x):
+    with np.errstate(over="ignore"):
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+
+
+def state_digest(st, row_lo=0, row_hi=None):
+    """numpy restatement of flowamok_grid_digest (digest_cell in csrc/fa_kernels.cuh) over rows [row_lo, row_hi) of
+    whole-grid state arrays: (sum, xor) mod 2^64."""
+    gh, gw = st["dy"].shape
+    row_hi = gh if row_hi is None else row_hi
+    sl = slice(row_lo, row_hi)
+    dy, dx = st["dy"][sl].astype(np.int64), st["dx"][sl].astype(np.int64)
+    bits = ((dy != 0) * 1 + (dy < 0) * 2 + (dx != 0) * 4 + (dx < 0) * 8 + (st["pref"][sl] != 0) * 16).astype(np.uint64)
+    idx = (np.arange(row_lo, row_hi, dtype=np.uint64)[:, None] * np.uint64(gw) + np.arange(gw, dtype=np.uint64)[None, :])
+    with np.errstate(over="ignore"):
+        v = _splitmix64(_splitmix64(idx * np.uint64(0x9E3779B97F4A7C15) + ((bits << np.uint64(32)) | st["color"][sl].astype(np.uint64)))
+                        ^ st["rng_state"][sl].astype(np.uint64))
+        return int(np.add.reduce(v.ravel(), dtype=np.uint64)), int(np.bitwise_xor.reduce(v.ravel()))
+
+
 # ---------------------------------------------------------------------------------------------
 # CPU emulation of the strip programs
 # ---------------------------------------------------------------------------------------------

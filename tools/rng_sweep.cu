@@ -76,7 +76,7 @@ __global__ void k_sweep2(int nhx, int ninc, u64 x_begin, u64 x_count, Hit *hits,
     const u64 inc = c_inc[ii] | 1ULL;
     for (int v = 0; v < 48; v++) {   // st0 (2) x pre (2) x mix (3) x post (2) x ext (2)
       const int st0 = v & 1, pre = (v >> 1) & 1, post = (v >> 2) & 1, ext = (v >> 3) & 1, mix = v >> 4;
-      if (ext && (int32_t)x32 >= 0) continue;
+      if ((ext && (int32_t)x32 >= 0) || st0) continue;   // st0: pcg's default initstate -- dropped to bound the run time
       const u64 x = ext ? (u64)(int64_t)(int32_t)x32 : (u64)x32;
       u64 m = st0 ? 0x853c49e6748fea9bULL : 0ULL;
       if (pre) m = m * MULT + inc;
@@ -191,7 +191,7 @@ int main(int argc, char **argv) {
   if (mode2) {
     cudaMemset(d_n, 0, 4);
     std::vector<u64> hx;
-    const int64_t idxs[] = {434, 433, 435, 14, 465, 900 - 434, 899 - 434, 0, 1};
+    const int64_t idxs[] = {434, 433, 435};
     for (int64_t ix : idxs) {
       const u32 hu = hash32((u32)ix);
       const int32_t hs = hash32s((int32_t)ix);
@@ -209,7 +209,7 @@ int main(int argc, char **argv) {
     float ms2 = 0; cudaEventElapsedTime(&ms2, e0, e1);
     unsigned int nh2 = 0; cudaMemcpy(&nh2, d_n, 4, cudaMemcpyDeviceToHost);
     printf("seedspace: swept %.3g (x, master variant, index hash, op) combinations x 24 variants in %.1f s: %u hits\n",
-           4294967296.0 * 3 * 40 * hx.size() * 4, ms2 * 1e-3, nh2);
+           4294967296.0 * 3 * 15 * hx.size() * 4, ms2 * 1e-3, nh2);
     std::vector<Hit> h2(nh2 < (unsigned)cap ? nh2 : cap);
     cudaMemcpy(h2.data(), d_hits, h2.size() * sizeof(Hit), cudaMemcpyDeviceToHost);
     for (auto &q : h2)
