@@ -26,10 +26,34 @@ if str(ROOT) not in sys.path:
 
 B_ALG = 12.0  # algorithmic bytes per cell-update (SURVEY 8d / BASELINE.md): r+w of a u16 control word and a u32 colour
 
-# DRAM bytes per launch at BASELINE config 4 (16384^2, quick), dram__bytes_read.sum + dram__bytes_write.sum of one
-# `ncu --set full` capture per kernel (profiles/r01_k_*.txt).  Below the algorithmic 3.22 GB per tick: the colour payload
-# goes through a lazy double buffer, only the 32-byte sectors that hold a car are rewritten.
-NCU_TRAFFIC_16384_QUICK = {"k_u_local": 0.543e9, "k_u_iter": 0.008e9, "k_move": 1.342e9}
+RNG_PARITY = ("unverified: the fork stream of the reference's README GIF is not reproduced (diku-dk/cpprandom 1.3.1 is not "
+              "vendored; DESIGN.md section 4); CUDA == oracle bit for bit, movement semantics pinned by the GIF")
+
+
+def csrc_hash():
+    """sha256 over the kernel sources: the key under which profiles/*_traffic.json records ncu's DRAM bytes"""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted((ROOT / "flowamok_b200" / "csrc").iterdir()):
+        if f.suffix in (".h", ".cuh", ".cu", ".inc"):
+            h.update(f.name.encode())
+            h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(workload):
+    """DRAM bytes per launch and kernel (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture),
+    written by profiles/summarize.py --traffic.  None unless it was captured on THESE kernel sources for THIS workload:
+    a number from other code is not reported."""
+    best = None
+    for f in sorted((ROOT / "profiles").glob("*_traffic.json")):
+        try:
+            d = json.loads(f.read_text())
+        except Exception:
+            continue
+        if d.get("csrc_sha256") == csrc_hash() and d.get("workload") == workload:
+            best = d
+    return best
 
 
 def measured_peak():
@@ -92,8 +116,8 @@ def cpu_oracle_run(size_w, rows, ticks, warm, threads=None, perfect=False):
     """The oracle port (reference layout: record of arrays, one full-grid Jacobi pass per fixpoint iteration,
     count-based termination exactly as steppers.fut:160-163) on a band of the same synthetic network."""
     from oracle import oracle as O
-    if threads:
-        O.set_threads(threads)
+    # all host cores, explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers
+    O.set_threads(threads or len(os.sched_getaffinity(0)) or os.cpu_count() or 1)
     g = O.Grid(rows, size_w)
     rings = g.generate_synthetic(seed=1)
     ch = O.Chooser(O.CHOOSE_RANDOM)
@@ -130,7 +154,9 @@ def run_reference(args, rank):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"synthetic-{size}x{size}-{args.mode} (SURVEY App. E, seed 1, 10% of road cells occupied)",
                        "grid": [size, size], "mode": args.mode, "sample": sample},
-            "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": thr, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": thr, "kind": "port", "sample": sample,
+                             "nproc": os.cpu_count()},
+            "rng_parity": RNG_PARITY,
             "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference is pure Futhark; no Futhark compiler in the image, so this is the C/OpenMP oracle port "
                     "in the reference's layout and schedule (BASELINE.md plan B)"}
@@ -146,6 +172,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=0, help="grid edge; default 16384 on 1 GPU, 65536 on several")
     ap.add_argument("--mode", default="", choices=["", "quick", "perfect"])
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
+                    help="row bands: peer-mapped mailboxes + device-side flags (default) or NCCL send/recv + host round trip")
+    ap.add_argument("--cuts", default="aligned", choices=["aligned", "straddle"],
+                    help="row bands: boundaries on multiples of 16, or shifted by 7 rows (rings straddle the cuts)")
+    ap.add_argument("--density16", type=int, default=6554, help="car probability per road cell in 1/65536 (default: 10 %%)")
+    ap.add_argument("--no-one-gpu", action="store_true", help="several GPUs: skip timing the same grid on rank 0 alone")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -179,19 +211,46 @@ def main():
     perfect = args.mode == "perfect"
     S = args.size
     cells = S * S
+    one_gpu = None
     with torch.cuda.stream(stream):
         ctx = fa.Context(local_rank, stream.cuda_stream)
+        if world > 1 and rank == 0 and not args.no_one_gpu:
+            # the SAME grid on one GPU (efficiency = T(1 GPU) / (N * T(N GPUs)) on 65536^2; 82 GB fit)
+            g1 = ctx.grid(S, S)
+            g1.generate_synthetic(seed=1, density16=args.density16, ring_full16=2)
+            k1 = max(5, min(args.steps, 50))
+            g1.step(perfect, args.warmup, leaks=False)
+            ctx.sync()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            g1.step(perfect, k1, leaks=False)
+            a1.record(stream)
+            ctx.sync()
+            ms1 = a0.elapsed_time(a1) / k1
+            one_gpu = {"value": cells / (ms1 * 1e-3) / 1e9, "unit": "GCUPS", "ms_per_step": ms1, "steps": k1,
+                       "what": f"the same {S}x{S} {args.mode} grid stepped on rank 0's GPU alone, before the banded run"}
+            g1.free()
+            del g1
         if world == 1:
             g = ctx.grid(S, S)
             rows = (0, S)
             runner = None
+            cuts = [0, S]
         else:
-            rows = split_rows(S, world, 16)[rank]
+            cuts = [r[0] for r in split_rows(S, world, 16)] + [S]
+            if args.cuts == "straddle":
+                cuts = [0] + [c + 7 for c in cuts[1:-1]] + [S]
+            rows = (cuts[rank], cuts[rank + 1])
             band = DeviceBand(ctx, S, S, rows[0], rows[1])
             g = band.grid
-            band.comm_init(rank, world)               # the library's own NCCL communicator: ticks run natively
+            band.set_cuts(cuts)
+        g.generate_synthetic(seed=1, density16=args.density16, ring_full16=2)
+        if world > 1:
+            if args.transport == "p2p":
+                band.p2p_init(rank, world)                # peer-mapped mailboxes: ticks run natively, no NCCL, no host sync
+            else:
+                band.comm_init(rank, world)               # the library's own NCCL communicator
             runner = BandRunner(band, rank, world)
-        g.generate_synthetic(seed=1, density16=6554, ring_full16=2)
         n_rings, _ = g.cycle_count()
 
         def run_ticks(n, leaks=False):
@@ -216,6 +275,8 @@ def main():
         ctx.sync()
         g.stats()
         rounds0 = runner.rounds if runner else 0
+        use_p2p = runner is not None and args.transport == "p2p"
+        p2p0 = band.p2p_stats() if use_p2p else None
 
         # ---- device-resident throughput: K ticks, inputs already in HBM, CUDA events on the launching stream
         sampler = ClockSampler(local_rank)
@@ -230,6 +291,7 @@ def main():
         clocks = sampler.stop()
         st = g.stats()
         rounds = (runner.rounds - rounds0) if runner else 0
+        p2p1 = band.p2p_stats() if use_p2p else None
         value = cells * args.steps / (ms * 1e-3) / 1e9
 
         # ---- per-kernel device time (events between the launches, same stream); single-grid path only
@@ -286,57 +348,84 @@ def main():
     per_gpu_gcups = value / world
     achieved = per_gpu_gcups * B_ALG  # GB/s of algorithmic traffic per GPU
     kernels = "k_u_local + k_u_iter" + (" + k_rings" if perfect else "") + " + k_move"
-    known_traffic = world == 1 and S == 16384 and not perfect
+    wl = f"synthetic-{S}x{S}-{args.mode}" + ("" if args.density16 == 6554 else f"-density16={args.density16}")
+    tr = ncu_traffic(wl) if world == 1 else None            # ncu's DRAM bytes per launch, only if captured on these sources
+    ms_tick = ms / args.steps
+    traffic = sum(tr["dram_bytes"].values()) if tr else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": sum(NCU_TRAFFIC_16384_QUICK.values()) if known_traffic else None, "peak_source": peak_src,
-                "algorithmic_bytes": cells / world * B_ALG,
-                "what": f"whole tick ({kernels}), 12 algorithmic B per cell-update (SURVEY 8d), per GPU; traffic = DRAM "
-                        "bytes per tick summed over the kernels' ncu captures (profiles/)"}
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": cells / world * B_ALG,
+                "what": f"whole tick ({kernels}): ALGORITHMIC bytes (12 B per cell-update, SURVEY 8d) / tick time, per GPU.  "
+                        "The tick moves fewer DRAM bytes than that (lazy colour buffer, bit planes): `physical` is what "
+                        "the DRAM actually did",
+                "physical": ({"dram_bytes": traffic, "gbs": traffic / (ms_tick * 1e-3) / 1e9,
+                              "frac": traffic / (ms_tick * 1e-3) / 1e9 / peak,
+                              "source": tr["source"], "csrc_sha256": tr["csrc_sha256"]} if tr else None)}
     if prof:
         tot = sum(prof.values())
         dom = max(prof, key=prof.get)
         dom_ms = prof[dom] / prof_ticks
+        dom_bytes = tr["dram_bytes"].get(dom) if tr else None
         roofline.update({"kernel_ms_per_tick": {k: v / prof_ticks for k, v in prof.items()},
                          "dominant_kernel": dom,
                          "dominant_share": max(prof.values()) / tot if tot else None,
-                         # the dominant kernel alone: it moves the whole persistent state, i.e. all 12 algorithmic B
-                         "dominant": {"kernel": dom, "ms": dom_ms, "achieved": cells / world * B_ALG / (dom_ms * 1e-3) / 1e9,
-                                      "frac": cells / world * B_ALG / (dom_ms * 1e-3) / 1e9 / peak,
-                                      "traffic": NCU_TRAFFIC_16384_QUICK.get(dom) if known_traffic else None,
-                                      "dram_gbs": (NCU_TRAFFIC_16384_QUICK[dom] / (dom_ms * 1e-3) / 1e9)
-                                      if known_traffic and dom in NCU_TRAFFIC_16384_QUICK else None}})
+                         # the dominant kernel against the DRAM bytes ncu measured for it (never above 1)
+                         "dominant": {"kernel": dom, "ms": dom_ms, "traffic": dom_bytes,
+                                      "dram_gbs": dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_bytes else None,
+                                      "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak if dom_bytes else None}})
+    # launches of OUR kernels inside the timed region
     launches_per_tick = 3 + (1 if perfect and n_rings else 0)
+    if runner is not None and args.transport == "p2p":
+        launches_per_tick += 1 + ((2 if args.cuts == "straddle" else 0) + (1 if args.cuts == "straddle" else 0) if perfect else 0)
     gpu_launches = launches_per_tick * args.steps
-    if runner is not None:   # + per convergence round: 2 pack copies are memcpys; k_band_merge x sides, k_u_iter resumes
+    if runner is not None and args.transport == "nccl":   # + per convergence round: pack, merge, k_u_iter resume
         sides = (1 if rank > 0 else 0) + (1 if rank < world - 1 else 0)
-        gpu_launches += rounds * sides + max(0, rounds - args.steps)
+        gpu_launches += rounds * (2 + 1) + args.steps * 4
+    hist = g.stats_hist()
+    if runner is None:
+        par = "1 grid"
+    elif args.transport == "p2p":
+        par = (f"{world} row bands (cuts {args.cuts}: {cuts[1:-1]}), per-tick halo rows by direct stores into the neighbours' "
+               "peer-mapped mailboxes over NVLink + device-side flags; convergence rounds and termination vote inside k_u_iter; "
+               "no NCCL call, no host synchronisation per tick")
+    else:
+        par = f"{world} row bands, per-tick halo rows over NCCL send/recv + 1 all-reduced convergence word (host round trip)"
     line = {"metric": "cell-updates/sec", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak" if world == 1 else "strong",
             "vs_baseline": None, "dtype": "u32 bit-planes (32 cells per word) + u32 colour payload",
             "data": "synthetic",
-            "config": {"workload": f"synthetic-{S}x{S}-{args.mode} (SURVEY App. E, seed 1, 10% of road cells occupied)",
+            "config": {"workload": f"{wl} (SURVEY App. E, seed 1, {args.density16 / 655.36:.0f}% of road cells occupied)",
                        "grid": [S, S], "mode": args.mode, "rings_on_rank0": int(n_rings),
-                       "parallelism": "1 grid" if world == 1 else
-                       f"{world} row bands of {S // world} rows, per-tick halo rows over NCCL send/recv + 1 all-reduced convergence word",
+                       "parallelism": par,
                        "l2": f"planes read+written per tick {cells / world * 7.7 / 1e9:.2f} GB per GPU >> 126 MB L2: inputs larger than L2, no flush"},
             "fixpoint": {"iterations_per_tick": st["passes"] / max(1, st["ticks"]),
                          "worklist_entries_relaxed_per_tick": st["sweeps"] / max(1, st["ticks"]),
-                         "band_convergence_rounds_per_tick": rounds / args.steps if runner else None},
-            "roofline": roofline, "clocks": clocks, "gpu_launches": int(gpu_launches), "e2e": e2e}
+                         "iterations_histogram": {"what": "ticks by number of frontier iterations of k_u_iter on rank 0 "
+                                                          "(all ticks since the grid was made; bucket 31 = 31 and more)",
+                                                  "ticks": {str(k): v for k, v in enumerate(hist) if v}},
+                         "band_convergence_rounds_per_tick": rounds / args.steps if runner else None,
+                         "band_wait_ms_per_tick_rank0": ((p2p1["wait_ns"] - p2p0["wait_ns"]) / 1e6 / args.steps) if p2p1 else None},
+            "roofline": roofline, "clocks": clocks, "gpu_launches": int(gpu_launches), "e2e": e2e,
+            "rng_parity": RNG_PARITY, "nproc": os.cpu_count()}
+    if one_gpu:
+        line["one_gpu_same_workload"] = one_gpu
+        line["efficiency_same_workload"] = value / (world * one_gpu["value"])
     if rank == 0 and not args.no_cpu:
         try:
             g1, dt1, thr = cpu_oracle_run(S, 64, 2, 1, perfect=perfect)
             rows_c = int(15.0 / (dt1 / (64 * S * 2) * S * 6))
             rows_c = max(32, min(S, (rows_c // 16) * 16))
             gc, dt, thr = cpu_oracle_run(S, rows_c, 5, 1, perfect=perfect)
-            line["cpu_baseline"] = {"value": gc, "unit": "GCUPS", "cores": thr, "kind": "port",
+            line["cpu_baseline"] = {"value": gc, "unit": "GCUPS", "cores": thr, "kind": "port", "nproc": os.cpu_count(),
                                     "sample": f"{rows_c}x{S} band of the same network, 5 ticks, {args.mode} mode, {dt:.1f} s"}
         except Exception as e:  # the oracle is only a reported baseline
             line["cpu_baseline"] = {"value": None, "unit": "GCUPS", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:
+        if use_p2p:
+            band.p2p_close()      # unmap the peers' mailboxes, then make sure everybody has before anything is freed
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

@@ -222,6 +222,12 @@ class Grid:
         self.ctx.check(self.L.flowamok_stats(self.ctx.h, self.h, C.byref(t), C.byref(p), C.byref(s)))
         return dict(ticks=t.value, passes=p.value, sweeps=s.value)
 
+    def stats_hist(self):
+        """ticks by number of fixpoint iterations (index 31: 31 and more), since the grid was created"""
+        h = (C.c_int64 * 32)()
+        self.ctx.check(self.L.flowamok_stats_hist(self.ctx.h, self.h, h))
+        return list(h)
+
     def digest(self):
         """(sum, xor) mod 2^64 of a position-dependent hash of the owned cells' state; bands' digests combine"""
         a, b = C.c_uint64(), C.c_uint64()

@@ -89,6 +89,11 @@ class DeviceBand:
         dist.all_gather_object(handles, handle, group=group)
         self.p2p_connect(handles=handles)
 
+    def p2p_stats(self):
+        r, w = C.c_int64(), C.c_int64()
+        self._c(self.L.flowamok_band_p2p_stats(self.ctx.h, self.grid.h, C.byref(r), C.byref(w)))
+        return dict(rounds=r.value, wait_ns=w.value)
+
     def p2p_close(self):
         """unmap the peers' mailboxes; synchronise all processes before freeing any band afterwards"""
         self._c(self.L.flowamok_band_p2p_close(self.ctx.h, self.grid.h))

@@ -65,6 +65,8 @@ def lib():
         "flowamok_stats": (C.c_int, [P, P, C.POINTER(I64), C.POINTER(I64), C.POINTER(I64)]),
         "flowamok_generate_synthetic": (C.c_int, [P, P, U64, U32, U32]),
         "flowamok_grid_digest": (C.c_int, [P, P, C.POINTER(U64), C.POINTER(U64)]),
+        "flowamok_stats_hist": (C.c_int, [P, P, P]),
+        "flowamok_band_p2p_stats": (C.c_int, [P, P, C.POINTER(I64), C.POINTER(I64)]),
         "flowamok_band_new": (C.c_int, [P, C.POINTER(P), I64, I64, I64, I64]),
         "flowamok_band_msg_bytes": (C.c_int, [P, P, C.POINTER(I64), C.POINTER(I64)]),
         "flowamok_band_pack_state": (C.c_int, [P, P, C.c_int, P]),

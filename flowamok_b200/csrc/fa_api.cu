@@ -118,6 +118,7 @@ struct flowamok_grid {
   unsigned int s_seq = 0;           // state messages sent so far (= ticks stepped over P2P)
   int p2p_blocks = 0;               // cooperative grid of k_u_iter<true>
   const char *poisoned = nullptr;   // a device-side watchdog tripped: the planes are not trustworthy any more
+  char poison_text[160];
 };
 
 static int fail(flowamok_context *ctx, const char *fmt, ...) {
@@ -195,6 +196,19 @@ int flowamok_context_new(flowamok_context **out, int device, void *stream) {
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_u_iter<false>, UIT_THREADS, 0));
   if (per_sm < 1) return fail(ctx, "k_u_iter does not fit on an SM");
   ctx->iter_blocks = per_sm * ctx->num_sms;
+  {   // Load every kernel of the stepping path NOW.  With CUDA's lazy module loading the first launch of a kernel may have to
+      // wait for running kernels to finish -- and the band kernels wait for each other on the device, so a load in the middle
+      // of a tick could wait forever for a kernel whose neighbour has not been enqueued yet.
+    const void *fns[] = {(const void *)k_u_local<false>, (const void *)k_u_local<true>, (const void *)k_u_iter<false>,
+                         (const void *)k_u_iter<true>, (const void *)k_rings, (const void *)k_rings_mark, (const void *)k_move<M_WARPS>,
+                         (const void *)k_band_xstate, (const void *)k_band_xu, (const void *)k_band_xring, (const void *)k_band_state,
+                         (const void *)k_band_pack_u, (const void *)k_band_merge, (const void *)k_digest, (const void *)k_pack,
+                         (const void *)k_unpack};
+    for (const void *f : fns) {
+      cudaFuncAttributes at;
+      CU(cudaFuncGetAttributes(&at, f));
+    }
+  }
   int per_sm_p2p = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_p2p, k_u_iter<true>, UIT_THREADS, 0));
   if (per_sm_p2p < 1) return fail(ctx, "k_u_iter<p2p> does not fit on an SM");
@@ -788,12 +802,19 @@ static int enqueue_tick(flowamok_context *ctx, flowamok_grid *g, bool perfect, u
 // they trip: the grid is poisoned, and every later stepping or reading call fails.
 static int check_device_errors(flowamok_context *ctx, flowamok_grid *g) {
   if (g->poisoned) return fail(ctx, "grid is poisoned: %s", g->poisoned);
-  unsigned int err = 0, berr = 0;
+  unsigned int err = 0;
+  BandDev bd;
+  memset(&bd, 0, sizeof bd);
   CU(cudaMemcpyAsync(&err, &g->is->error, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  if (g->band_dev) CU(cudaMemcpyAsync(&berr, &g->band_dev->error, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (g->band_dev) CU(cudaMemcpyAsync(&bd, g->band_dev, sizeof bd, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   if (err) g->poisoned = "the grid barrier watchdog of k_u_iter tripped (fixpoint left half-relaxed)";
-  else if (berr) g->poisoned = "a wait of the row-band protocol timed out (a neighbour band never sent its rows)";
+  else if (bd.error) {
+    static const char *what[] = {"?", "state rows", "u rows", "termination vote", "ring verdicts"};
+    snprintf(g->poison_text, sizeof g->poison_text, "band %d: a wait of the row-band protocol timed out (%s: message %u never came, last seen %u)",
+             g->link.rank, what[(bd.error >> 8) < 5 ? (bd.error >> 8) : 0], bd.err_want, bd.err_got);
+    g->poisoned = g->poison_text;
+  }
   if (g->poisoned) return fail(ctx, "%s", g->poisoned);
   return 0;
 }
@@ -1406,6 +1427,27 @@ int flowamok_stats(flowamok_context *ctx, flowamok_grid *g, int64_t *ticks, int6
   if (sweeps) *sweeps = (int64_t)(d.sweeps - g->base.sweeps);
   g->base = d;
   return 0;
+}
+
+/* ticks by number of k_u_iter iterations since the grid was created: hist[k] for k = 0..30, hist[31] = 31 and more */
+int flowamok_stats_hist(flowamok_context *ctx, flowamok_grid *g, int64_t *hist32) {
+  if (!g || !hist32) return fail(ctx, "null argument");
+  CU(cudaSetDevice(ctx->device));
+  Diag d;
+  if (read_diag(ctx, g, &d)) return 1;
+  for (int k = 0; k < 32; k++) hist32[k] = (int64_t)d.hist[k];
+  return 0;
+}
+/* row bands over the P2P transport: convergence rounds so far and the time CTA 0 spent waiting for neighbours (ns) */
+int flowamok_band_p2p_stats(flowamok_context *ctx, flowamok_grid *g, int64_t *rounds, int64_t *wait_ns) {
+  if (!g || !g->band_dev) return fail(ctx, "not a band with an open mailbox");
+  CU(cudaSetDevice(ctx->device));
+  BandDev bd;
+  CU(cudaMemcpyAsync(&bd, g->band_dev, sizeof bd, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (rounds) *rounds = (int64_t)bd.rounds;
+  if (wait_ns) *wait_ns = (int64_t)bd.waits_ns;
+  return check_device_errors(ctx, g);
 }
 
 int flowamok_grid_digest(flowamok_context *ctx, const flowamok_grid *g, uint64_t *sum, uint64_t *xor_) {

@@ -43,7 +43,8 @@ static_assert(sizeof(MailHdr) == 256, "mailbox header layout");
 struct BandDev {
   unsigned int u_seq, epoch, ring_seq, pad0;    // numbers of the last messages SENT (state messages: the host counts)
   unsigned int xstate_arrived;                  // CTA arrival counter of k_band_xstate (monotone)
-  unsigned int error;                           // 2: a wait timed out
+  unsigned int error;                           // 2 | tag << 8: a wait timed out (tag: 1 state, 2 u rows, 3 vote, 4 ring verdicts)
+  unsigned int err_want, err_got;               // the message number that never came / the last one seen
   unsigned int go, round_it;                    // CTA 0 -> grid hand-over inside k_u_iter
   unsigned long long rounds;                    // convergence rounds so far
   unsigned long long waits_ns;                  // time CTA 0 spent waiting for neighbours (diagnostic)
@@ -76,7 +77,7 @@ __device__ __forceinline__ unsigned long long band_now() {
 // spin until the message number at *p has reached `want` (numbers wrap; compare as a signed difference); shift: the
 // vote words carry the epoch above bit 0.  Returns the word read.  On a timeout the band's error flag is set and every
 // later wait returns at once, so the queued ticks drain quickly and the host reports the failure.
-__device__ __forceinline__ unsigned int band_wait(const unsigned int *p, unsigned int want, int shift, BandDev *dev) {
+__device__ __forceinline__ unsigned int band_wait(const unsigned int *p, unsigned int want, int shift, BandDev *dev, unsigned int tag) {
   unsigned long long t0 = 0;
   for (unsigned int spins = 0;; spins++) {
     const unsigned int v = ld_acquire_sys(p);
@@ -88,7 +89,10 @@ __device__ __forceinline__ unsigned int band_wait(const unsigned int *p, unsigne
     if (spins == 32) t0 = band_now();
     if (spins > 32) {
       __nanosleep(100);
-      if ((spins & 1023u) == 0 && band_now() - t0 > FA_BAND_TIMEOUT_NS) { atomicExch(&dev->error, 2u); return v; }
+      if ((spins & 1023u) == 0 && band_now() - t0 > FA_BAND_TIMEOUT_NS) {
+        if (atomicCAS(&dev->error, 0u, 2u | (tag << 8)) == 0u) { dev->err_want = want; dev->err_got = v >> shift; }
+        return v;
+      }
     }
   }
 }
@@ -134,7 +138,7 @@ __device__ __forceinline__ void band_exchange_u(const GridView &g, const BandLin
   __syncthreads();
   if (tid < 2 && L.nb[tid]) {
     st_release_sys(&reinterpret_cast<MailHdr *>(L.nb[tid])->u_seq[1 - tid], seq);
-    band_wait(&reinterpret_cast<MailHdr *>(L.self)->u_seq[tid], seq, 0, L.dev);
+    band_wait(&reinterpret_cast<MailHdr *>(L.self)->u_seq[tid], seq, 0, L.dev, 2u);
   }
   __syncthreads();
   for (int side = 0; side < 2; side++) {
@@ -173,7 +177,7 @@ __device__ __forceinline__ bool band_vote(const BandLink &L, bool any) {
   const unsigned int ep = ep_sh;
   if (tid < L.world) {
     st_release_sys(&reinterpret_cast<MailHdr *>(L.all[tid])->vote[ep & 1u][L.rank], (ep << 1) | (any ? 1u : 0u));
-    const unsigned int v = band_wait(&reinterpret_cast<MailHdr *>(L.self)->vote[ep & 1u][tid], ep, 1, L.dev);
+    const unsigned int v = band_wait(&reinterpret_cast<MailHdr *>(L.self)->vote[ep & 1u][tid], ep, 1, L.dev, 3u);
     if (v & 1u) atomicOr(&any_sh, 1u);
   }
   __syncthreads();
@@ -216,7 +220,7 @@ k_band_xstate(int pitch, int own0, int own1, U4 *head, u32 *pref, u32 *color, co
         if (L.nb[side]) st_release_sys(&reinterpret_cast<MailHdr *>(L.nb[side])->s_seq[1 - side], seq);
     }
     for (int side = 0; side < 2; side++)
-      if (L.nb[side]) band_wait(&reinterpret_cast<MailHdr *>(L.self)->s_seq[side], seq, 0, L.dev);
+      if (L.nb[side]) band_wait(&reinterpret_cast<MailHdr *>(L.self)->s_seq[side], seq, 0, L.dev, 1u);
   }
   __syncthreads();
   for (int side = 0; side < 2; side++) {
@@ -260,7 +264,7 @@ k_band_xring(u32 *partial, u32 *pass, const __grid_constant__ BandLink L) {
   __syncthreads();
   if (tid < L.world) {
     st_release_sys(&reinterpret_cast<MailHdr *>(L.all[tid])->ring_seq[L.rank], seq);
-    band_wait(&reinterpret_cast<MailHdr *>(L.self)->ring_seq[tid], seq, 0, L.dev);
+    band_wait(&reinterpret_cast<MailHdr *>(L.self)->ring_seq[tid], seq, 0, L.dev, 4u);
   }
   __syncthreads();
   const u32 *rows = reinterpret_cast<const u32 *>(L.self + L.off_ring) + (size_t)(seq & 1u) * L.world * nw;

@@ -113,6 +113,12 @@ int flowamok_grid_clone(flowamok_context *ctx, const flowamok_grid *src, flowamo
 /* diagnostics of the ticks since the last call: ticks, fixpoint iterations, worklist entries relaxed */
 int flowamok_stats(flowamok_context *ctx, flowamok_grid *g, int64_t *ticks, int64_t *passes, int64_t *sweeps);
 
+/* ticks by number of frontier iterations of the U fixpoint ("iterations-per-tick histogram so the jam depth behind
+ * a number is visible"): hist32[k], k = 0..30, hist32[31] = 31 and more; counted since the grid was created */
+int flowamok_stats_hist(flowamok_context *ctx, flowamok_grid *g, int64_t *hist32);
+/* P2P transport diagnostics: convergence rounds so far, nanoseconds the band spent waiting for its neighbours' rows */
+int flowamok_band_p2p_stats(flowamok_context *ctx, flowamok_grid *g, int64_t *rounds, int64_t *wait_ns);
+
 /* Digest of the owned rows, computed on the device: sum and xor (mod 2^64) over the cells of a hash of (global cell index,
  * heading, preference, colour, rng state) -- see digest_cell in csrc/fa_kernels.cuh.  Sums / xors of bands combine to
  * the whole grid's: the size-independent equality check of BASELINE config 5 (65536^2 does not fit the host).  Synchronous. */
