@@ -298,6 +298,8 @@ def main():
         prof, prof_ticks = None, min(50, args.steps)
         if runner is None:
             prof = g.step_profile(perfect, prof_ticks)
+        elif use_p2p:
+            prof = band.step_profile(perfect, prof_ticks)      # this rank's band; every band steps the same ticks
 
         # ---- end to end through the C ABI with HOST buffers: upload + K ticks + leak count + download
         e2e = None

@@ -206,6 +206,11 @@ class Grid:
         self.ctx.check(self.L.flowamok_step_profile(self.ctx.h, self.h, int(perfect), n_ticks, ms))
         return dict(k_u_local=ms[0], k_u_iter=ms[1], k_rings=ms[2], k_move=ms[3])
 
+    def step_timeline(self, perfect: bool, n_ticks=10):
+        ms = (C.c_double * 5)()
+        self.ctx.check(self.L.flowamok_step_timeline(self.ctx.h, self.h, int(perfect), n_ticks, ms))
+        return dict(local=ms[0], fork_to_fixpoint_end=ms[1], fork_to_move_end=ms[2], fixup=ms[3], tick=ms[4])
+
     def step_leaks(self, perfect: bool, cap=1 << 20):
         buf = np.zeros((cap, 8), np.int64)
         n = C.c_int64()

@@ -89,6 +89,11 @@ class DeviceBand:
         dist.all_gather_object(handles, handle, group=group)
         self.p2p_connect(handles=handles)
 
+    def step_profile(self, perfect, n_ticks=20):
+        ms = (C.c_double * 5)()
+        self._c(self.L.flowamok_band_step_profile(self.ctx.h, self.grid.h, int(perfect), n_ticks, ms))
+        return dict(k_band_xstate=ms[0], k_u_local=ms[1], k_rings=ms[2], k_u_iter=ms[3], k_move=ms[4])
+
     def p2p_stats(self):
         r, w = C.c_int64(), C.c_int64()
         self._c(self.L.flowamok_band_p2p_stats(self.ctx.h, self.grid.h, C.byref(r), C.byref(w)))

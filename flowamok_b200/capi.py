@@ -58,6 +58,7 @@ def lib():
         "flowamok_step_quick": (C.c_int, [P, P, I64, C.POINTER(I64)]),
         "flowamok_step_perfect": (C.c_int, [P, P, I64, C.POINTER(I64)]),
         "flowamok_step_profile": (C.c_int, [P, P, C.c_int, I64, C.POINTER(C.c_double)]),
+        "flowamok_step_timeline": (C.c_int, [P, P, C.c_int, I64, C.POINTER(C.c_double)]),
         "flowamok_step_leaks": (C.c_int, [P, P, C.c_int, I64, P, C.POINTER(I64)]),
         "flowamok_render": (C.c_int, [P, P, I64, P]),
         "flowamok_render_device": (C.c_int, [P, P, I64, C.POINTER(P)]),
@@ -89,6 +90,7 @@ def lib():
         "flowamok_band_p2p_open": (C.c_int, [P, P, C.c_int, C.c_int, P, C.POINTER(P)]),
         "flowamok_band_p2p_connect": (C.c_int, [P, P, P, P, C.c_int]),
         "flowamok_band_p2p_close": (C.c_int, [P, P]),
+        "flowamok_band_step_profile": (C.c_int, [P, P, C.c_int, I64, C.POINTER(C.c_double)]),
         "flowamok_band_ring_words": (C.c_int, [P, P, C.POINTER(I64)]),
         "flowamok_band_ring_verdicts": (C.c_int, [P, P, P]),
         "flowamok_band_rings_apply": (C.c_int, [P, P, P]),

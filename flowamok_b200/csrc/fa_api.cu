@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <unordered_set>
 #include <vector>
@@ -54,6 +55,12 @@ struct flowamok_context {
   int device;
   cudaStream_t stream;
   bool own_stream;
+  // The tick forks after k_u_local: the global fixpoint (k_u_iter: latency-bound, one small CTA per SM) runs on `hi` (highest
+  // priority: its cooperative grid is placed as soon as k_move's CTAs make room), k_move runs beside it on the main stream,
+  // and the streams join before the fix-up (fa_stream.h, fix_word).
+  cudaStream_t hi = nullptr;
+  cudaEvent_t ev_local = nullptr, ev_fix = nullptr;
+  bool split = true;
   int num_sms;
   int iter_blocks; // co-resident CTAs of k_u_iter
   int iter_blocks_p2p = 0;   // the same for a band with mapped peers (smaller when several bands share one device)
@@ -93,6 +100,10 @@ struct flowamok_grid {
   u32 *ustate;            // per word: U_NONE or entry index (| U_QUEUED)
   int nsx, nsy, rs;       // strips across / down, rows per strip (k_u_local)
   int mtx, mty, rs_m;     // k_move tiles (M_WARPS strips wide, rs_m rows)
+  // speculative move (fa_stream.h, fix_word): the fixpoint's delta plane, the words that have a delta, fix-up claims
+  u64 *mymx_B = nullptr;
+  u32 *chg_list = nullptr, *fix_claim = nullptr;
+  u32 fix_epoch = 0;                     // tag of the current tick's claims (never reset, unlike `tick`)
   Diag base;  // diag values already reported
   // native band stepping: message buffers [side] and the all-reduced convergence word
   char *msg_s_send[2] = {nullptr, nullptr}, *msg_s_recv[2] = {nullptr, nullptr};
@@ -190,19 +201,28 @@ int flowamok_context_new(flowamok_context **out, int device, void *stream) {
   ctx->num_sms = prop.multiProcessorCount;
   if (stream) ctx->stream = (cudaStream_t)stream;
   else { CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+  {
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo: least priority (numerically largest), hi: greatest
+    CU(cudaStreamCreateWithPriority(&ctx->hi, cudaStreamNonBlocking, hi));
+    CU(cudaEventCreateWithFlags(&ctx->ev_local, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->ev_fix, cudaEventDisableTiming));
+    const char *e = getenv("FLOWAMOK_SPLIT");
+    ctx->split = !(e && e[0] == '0');
+  }
   CU(cudaFuncSetAttribute(k_move<M_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
   ctx->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_u_iter<false>, UIT_THREADS, 0));
   if (per_sm < 1) return fail(ctx, "k_u_iter does not fit on an SM");
-  ctx->iter_blocks = per_sm * ctx->num_sms;
+  ctx->iter_blocks = ctx->num_sms;   // ONE small CTA per SM: the clean k_move tiles run beside the fixpoint
   {   // Load every kernel of the stepping path NOW.  With CUDA's lazy module loading the first launch of a kernel may have to
       // wait for running kernels to finish -- and the band kernels wait for each other on the device, so a load in the middle
       // of a tick could wait forever for a kernel whose neighbour has not been enqueued yet.
     const void *fns[] = {(const void *)k_u_local<false>, (const void *)k_u_local<true>, (const void *)k_u_iter<false>,
                          (const void *)k_u_iter<true>, (const void *)k_rings, (const void *)k_rings_mark, (const void *)k_move<M_WARPS>,
                          (const void *)k_band_xstate, (const void *)k_band_xu, (const void *)k_band_xring, (const void *)k_band_state,
-                         (const void *)k_band_pack_u, (const void *)k_band_merge, (const void *)k_digest, (const void *)k_pack,
+                         (const void *)k_band_pack_u, (const void *)k_band_merge, (const void *)k_digest, (const void *)k_pack, (const void *)k_move_fix,
                          (const void *)k_unpack};
     for (const void *f : fns) {
       cudaFuncAttributes at;
@@ -212,13 +232,19 @@ int flowamok_context_new(flowamok_context **out, int device, void *stream) {
   int per_sm_p2p = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_p2p, k_u_iter<true>, UIT_THREADS, 0));
   if (per_sm_p2p < 1) return fail(ctx, "k_u_iter<p2p> does not fit on an SM");
-  ctx->iter_blocks_p2p = per_sm_p2p * ctx->num_sms;
+  ctx->iter_blocks_p2p = ctx->num_sms;
   return 0;
 }
 
 int flowamok_context_free(flowamok_context *ctx) {
   if (!ctx) return 0;
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+  if (ctx->device >= 0) {
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->hi) { cudaStreamSynchronize(ctx->hi); cudaStreamDestroy(ctx->hi); }
+    if (ctx->ev_local) cudaEventDestroy(ctx->ev_local);
+    if (ctx->ev_fix) cudaEventDestroy(ctx->ev_fix);
+  }
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return 0;
@@ -281,6 +307,11 @@ static int grid_new_impl(flowamok_context *ctx, flowamok_grid **out, int64_t gh_
   if (const char *e = getenv("FLOWAMOK_MOVE_ROWS")) { int v = atoi(e); if (v >= 1 && v <= 128) g->rs_m = v; }
   while (g->rs_m > 1 && MTL::Smem::bytes(g->rs_m) > ctx->smem_optin) g->rs_m--;
   g->mtx = (g->nsx + M_WARPS - 1) / M_WARPS; g->mty = (owned + g->rs_m - 1) / g->rs_m;
+  CU(cudaMalloc(&g->mymx_B, g->nwords * 8));
+  CU(cudaMalloc(&g->chg_list, g->nwords * 4));
+  CU(cudaMalloc(&g->fix_claim, g->nwords * 4));
+  CU(cudaMemsetAsync(g->mymx_B, 0, g->nwords * 8, ctx->stream));
+  CU(cudaMemsetAsync(g->fix_claim, 0, g->nwords * 4, ctx->stream));
   CU(cudaMalloc(&g->table, g->nwords * sizeof(UEntry)));
   {   // frontier lists; qlist[1] doubles as the per-strip staging area of k_u_local (STRIP_W * rs slots per strip)
     const size_t nslots = std::max(g->nwords, (size_t)g->nsx * g->nsy * STRIP_W * g->rs);
@@ -346,7 +377,7 @@ int flowamok_grid_free(flowamok_context *ctx, flowamok_grid *g) {
   cudaFree(g->d_woken); if (g->h_woken) cudaFreeHost(g->h_woken);
   for (int r = 0; r < BAND_MAXW; r++) if (g->ipc_opened[r]) cudaIpcCloseMemHandle(g->ipc_opened[r]);
   cudaFree(g->mailbox); cudaFree(g->band_dev); cudaFree(g->ring_sid); cudaFree(g->ring_partial); cudaFree(g->ring_pass);
-  cudaFree(g->table); cudaFree(g->qlist[0]); cudaFree(g->qlist[1]); cudaFree(g->ustate);
+  cudaFree(g->table); cudaFree(g->qlist[0]); cudaFree(g->qlist[1]); cudaFree(g->ustate); cudaFree(g->mymx_B); cudaFree(g->chg_list); cudaFree(g->fix_claim);
   cudaFree(g->ring_words); cudaFree(g->ring_off); cudaFree(g->leak_plane);
   cudaFreeHost(g->h_diag);
   delete g;
@@ -740,6 +771,7 @@ static GridView make_view(flowamok_grid *g) {
   v.head_in = g->head[g->cur]; v.head_out = g->head[g->cur ^ 1];
   v.pref_in = g->pref[g->cur]; v.pref_out = g->pref[g->cur ^ 1];
   v.calc = g->calc; v.mymx = g->mymx; v.ustate = g->ustate;
+  v.mymx_B = nullptr; v.chg_list = nullptr; v.chg_n = nullptr;
   v.color_in = g->color[g->cur]; v.color_out = g->color[g->cur ^ 1];
   v.dirty_in = g->dirty[g->cur]; v.dirty_out = g->dirty[g->cur ^ 1];
   v.rng = g->rng; v.rng_inc = g->rng_inc;
@@ -758,18 +790,21 @@ static int launch_u_init(flowamok_context *ctx, flowamok_grid *g, const GridView
   return 0;
 }
 // first_it = 0: start from the frontier k_u_local left in qlist[0]; 1: resume from qlist[1] (band merge)
-static int launch_u_iter(flowamok_context *ctx, flowamok_grid *g, GridView &v, unsigned int first_it, bool p2p = false) {
+static int launch_u_iter(flowamok_context *ctx, flowamok_grid *g, GridView &v, unsigned int first_it, bool p2p = false,
+                         cudaStream_t st = nullptr) {
+  if (!st) st = ctx->stream;
   void *args[] = {(void *)&v, (void *)&g->table, (void *)&g->qlist[0], (void *)&g->qlist[1],
                   (void *)&first_it, (void *)&g->is, (void *)&g->diag, (void *)&g->link};
-  if (p2p) CU(cudaLaunchCooperativeKernel((void *)k_u_iter<true>, dim3(g->p2p_blocks), dim3(UIT_THREADS), args, 0, ctx->stream));
-  else CU(cudaLaunchCooperativeKernel((void *)k_u_iter<false>, dim3(ctx->iter_blocks), dim3(UIT_THREADS), args, 0, ctx->stream));
+  if (p2p) CU(cudaLaunchCooperativeKernel((void *)k_u_iter<true>, dim3(g->p2p_blocks), dim3(UIT_THREADS), args, 0, st));
+  else CU(cudaLaunchCooperativeKernel((void *)k_u_iter<false>, dim3(ctx->iter_blocks), dim3(UIT_THREADS), args, 0, st));
   KCHECK("k_u_iter");
   return 0;
 }
-static int launch_rings(flowamok_context *ctx, flowamok_grid *g, const GridView &v) {
+static int launch_rings(flowamok_context *ctx, flowamok_grid *g, const GridView &v, cudaStream_t st = nullptr) {
+  if (!st) st = ctx->stream;
   if (g->n_rings > 0) {
-    k_rings<<<nblk(g->n_rings, RINGS_PER_BLOCK), RINGS_PER_BLOCK, 0, ctx->stream>>>(v, g->ring_words, g->ring_off, g->n_rings, g->ring_stride,
-                                                                                    g->ring_sid, g->ring_partial);
+    k_rings<<<nblk(g->n_rings, RINGS_PER_BLOCK), RINGS_PER_BLOCK, 0, st>>>(v, g->ring_words, g->ring_off, g->n_rings, g->ring_stride,
+                                                                           g->ring_sid, g->ring_partial);
     KCHECK("k_rings");
   }
   return 0;
@@ -782,9 +817,49 @@ static int launch_move(flowamok_context *ctx, flowamok_grid *g, const GridView &
   return 0;
 }
 
-static int enqueue_tick(flowamok_context *ctx, flowamok_grid *g, bool perfect, u32 *leak_plane, cudaEvent_t *ev = nullptr) {
+// The view of the global fixpoint (and of the fix-up) when the tick moves speculatively: grants go into the delta plane
+static GridView spec_view(flowamok_grid *g) {
+  GridView v = make_view(g);
+  v.mymx_B = g->mymx_B; v.chg_list = g->chg_list; v.chg_n = &g->is->chg_n;
+  return v;
+}
+// Fork: k_u_local (ring resolution, a band's first boundary swap) are enqueued on the main stream.  The global fixpoint goes
+// to the high-priority stream and keeps its grants in the delta plane; k_move follows k_u_local at once on the main stream,
+// gathering from the plane as published; join; fix-up of the words around the ones the fixpoint changed.
+static int fork_fix_and_move(flowamok_context *ctx, flowamok_grid *g, bool p2p, cudaEvent_t *tev = nullptr) {
+  cudaStream_t st = ctx->stream;
+  if (tev) CU(cudaEventRecord(tev[1], st));
+  CU(cudaEventRecord(ctx->ev_local, st));
+  CU(cudaStreamWaitEvent(ctx->hi, ctx->ev_local, 0));
+  GridView vf = spec_view(g);
+  if (launch_u_iter(ctx, g, vf, 0u, p2p, ctx->hi)) return 1;
+  if (tev) CU(cudaEventRecord(tev[2], ctx->hi));
+  CU(cudaEventRecord(ctx->ev_fix, ctx->hi));
+  GridView vs = make_view(g);
+  k_move<M_WARPS><<<g->mtx * g->mty, M_WARPS * 32, MTL::Smem::bytes(g->rs_m), st>>>(vs, g->nsx, g->mtx, g->rs_m, g->diag, nullptr);
+  KCHECK("k_move");
+  if (tev) CU(cudaEventRecord(tev[3], st));
+  CU(cudaStreamWaitEvent(st, ctx->ev_fix, 0));
+  k_move_fix<<<ctx->num_sms * 2, 256, 0, st>>>(vf, g->fix_claim, ++g->fix_epoch, g->is, g->diag);
+  KCHECK("k_move_fix");
+  if (tev) CU(cudaEventRecord(tev[4], st));
+  g->cur ^= 1;
+  g->tick++;
+  return 0;
+}
+
+// ev != nullptr (flowamok_step_profile) or a leak plane: the kernels one after the other on the main stream
+static int enqueue_tick(flowamok_context *ctx, flowamok_grid *g, bool perfect, u32 *leak_plane, cudaEvent_t *ev = nullptr,
+                        cudaEvent_t *tev = nullptr) {
   if (g->halo != 0) return fail(ctx, "a row band is stepped with the flowamok_band_* calls");
   cudaStream_t st = ctx->stream;
+  if (ctx->split && !ev && !leak_plane) {
+    if (tev) CU(cudaEventRecord(tev[0], st));
+    GridView v = make_view(g);
+    if (launch_u_init(ctx, g, v)) return 1;
+    if (perfect && launch_rings(ctx, g, v)) return 1;   // ring resolution does not depend on the fixpoint (ring_grant)
+    return fork_fix_and_move(ctx, g, false, tev);
+  }
   GridView v = make_view(g);
   if (ev) CU(cudaEventRecord(ev[0], st));
   if (launch_u_init(ctx, g, v)) return 1;
@@ -871,6 +946,32 @@ int flowamok_step_profile(flowamok_context *ctx, flowamok_grid *g, int perfect, 
     }
   for (auto &e : ev) cudaEventDestroy(e);
   return 0;
+}
+
+/* The production tick (speculative move, three streams) on a time line, summed over n_ticks <= 1024, in ms:
+ * ms[0] k_u_local (+ k_rings) on the main stream; ms[1] fork -> end of k_u_iter (high-priority stream); ms[2] fork -> end of
+ * the speculative k_move (side stream); ms[3] join -> end of k_move_fix; ms[4] the whole tick. */
+int flowamok_step_timeline(flowamok_context *ctx, flowamok_grid *g, int perfect, int64_t n_ticks, double *ms5) {
+  if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
+  if (!g || !ms5 || n_ticks < 1 || n_ticks > 1024 || !ctx->split) return fail(ctx, "bad timeline arguments");
+  CU(cudaSetDevice(ctx->device));
+  std::vector<cudaEvent_t> ev((size_t)n_ticks * 5);
+  for (auto &e : ev) CU(cudaEventCreate(&e));
+  int rc = 0;
+  for (int64_t t = 0; t < n_ticks && !rc; t++) rc = enqueue_tick(ctx, g, perfect != 0, nullptr, nullptr, &ev[(size_t)t * 5]);
+  cudaError_t se = cudaStreamSynchronize(ctx->stream);
+  for (int k = 0; k < 5; k++) ms5[k] = 0.0;
+  if (!rc && se == cudaSuccess)
+    for (int64_t t = 0; t < n_ticks; t++) {
+      cudaEvent_t *e = &ev[(size_t)t * 5];
+      float a = 0, b = 0, c = 0, d1 = 0, d2 = 0, tot = 0;
+      cudaEventElapsedTime(&a, e[0], e[1]); cudaEventElapsedTime(&b, e[1], e[2]); cudaEventElapsedTime(&c, e[1], e[3]);
+      cudaEventElapsedTime(&d1, e[2], e[4]); cudaEventElapsedTime(&d2, e[3], e[4]); cudaEventElapsedTime(&tot, e[0], e[4]);
+      ms5[0] += a; ms5[1] += b; ms5[2] += c; ms5[3] += d1 < d2 ? d1 : d2; ms5[4] += tot;
+    }
+  for (auto &e : ev) cudaEventDestroy(e);
+  if (se != cudaSuccess) return fail(ctx, "timeline: %s", cudaGetErrorString(se));
+  return rc ? 1 : check_device_errors(ctx, g);
 }
 
 int flowamok_step_leaks(flowamok_context *ctx, flowamok_grid *g, int perfect, int64_t cap, int64_t *leaks, int64_t *n_leaks) {
@@ -1259,24 +1360,27 @@ static int band_swap(flowamok_context *ctx, char *const send[2], char *const rec
 //   [perfect] k_rings        local rings are marked, straddling rings judged;  k_band_xring + k_rings_mark if any ring
 //                            straddles a cut;  k_band_xu if any ring touches a boundary row
 //   k_move
-static int band_step_p2p(flowamok_context *ctx, flowamok_grid *g, bool perfect, int64_t n_ticks, int64_t *rounds) {
+static int band_step_p2p(flowamok_context *ctx, flowamok_grid *g, bool perfect, int64_t n_ticks, int64_t *rounds, cudaEvent_t *ev = nullptr) {
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const bool multi = g->link.world > 1;
   const int xs_blocks = std::max(1, std::min(64, (int)nblk(8ll * g->pitch, 256)));
   for (int64_t t = 0; t < n_ticks; t++) {
+    cudaEvent_t *e = ev ? ev + t * 6 : nullptr;   // brackets: xstate | u_local | rings + verdicts + boundary swap | u_iter | move
+    if (e) CU(cudaEventRecord(e[0], st));
     if (multi) {
       k_band_xstate<<<xs_blocks, 256, 0, st>>>(g->pitch, g->own0, g->own1, g->head[g->cur], g->pref[g->cur], g->color[g->cur], g->link,
                                                ++g->s_seq);
       KCHECK("k_band_xstate");
     }
-    if (flowamok_band_u_init(ctx, g)) return 1;
-    {
-      GridView v = make_view(g);
-      if (launch_u_iter(ctx, g, v, 0u, true)) return 1;
-    }
-    if (perfect) {
-      GridView v = make_view(g);
+    if (e) CU(cudaEventRecord(e[1], st));
+    const bool spec = ctx->split && !e && g->p2p_blocks == ctx->iter_blocks_p2p;   // several bands on one device: one after the other
+    CU(cudaMemsetAsync(g->is->qn, 0, sizeof(g->is->qn), st));   // a tick starts with empty frontier counters
+    GridView v = make_view(g);
+    if (launch_u_init(ctx, g, v)) return 1;
+    if (e) CU(cudaEventRecord(e[2], st));
+    if (perfect) {   // ring resolution does not depend on the fixpoint (ring_grant): it runs first, so its marks travel with
+                     // the boundary swap below and belong to the snapshot the speculative k_move reads
       if (launch_rings(ctx, g, v)) return 1;
       if (multi && g->n_straddle > 0) {
         k_band_xring<<<1, 512, 0, st>>>(g->ring_partial, g->ring_pass, g->link);
@@ -1286,12 +1390,20 @@ static int band_step_p2p(flowamok_context *ctx, flowamok_grid *g, bool perfect, 
           KCHECK("k_rings_mark");
         }
       }
-      if (multi && g->ring_swap != 0) {   // -1 (unknown) counts as yes
-        k_band_xu<<<1, 512, 0, st>>>(v, g->link);
-        KCHECK("k_band_xu");
-      }
     }
-    if (flowamok_band_move(ctx, g)) return 1;
+    if (multi) {   // ghost rows := the neighbours' boundary rows after THEIR local levels (and ring marks)
+      k_band_xu<<<1, 512, 0, st>>>(v, g->link);
+      KCHECK("k_band_xu");
+    }
+    if (e) CU(cudaEventRecord(e[3], st));
+    if (spec) {
+      if (fork_fix_and_move(ctx, g, true)) return 1;
+      continue;
+    }
+    if (launch_u_iter(ctx, g, v, 0u, true)) return 1;
+    if (e) CU(cudaEventRecord(e[4], st));
+    if (launch_move(ctx, g, v, nullptr)) return 1;
+    if (e) CU(cudaEventRecord(e[5], st));
   }
   if (rounds) {   // convergence rounds so far: a device counter (this read synchronises; pass NULL to stay asynchronous)
     unsigned long long r = 0;
@@ -1301,6 +1413,30 @@ static int band_step_p2p(flowamok_context *ctx, flowamok_grid *g, bool perfect, 
     if (check_device_errors(ctx, g)) return 1;
   }
   return 0;
+}
+
+/* flowamok_step_profile for a band on the P2P transport: summed device milliseconds of {k_band_xstate, k_u_local, ring
+ * resolution + boundary swap, k_u_iter (with the convergence rounds), k_move}, the kernels one after the other, over
+ * n_ticks <= 1024.  Every band must call it. */
+int flowamok_band_step_profile(flowamok_context *ctx, flowamok_grid *g, int perfect, int64_t n_ticks, double *ms5) {
+  if (band_check(ctx, g, 0)) return 1;
+  if (!g->p2p || !ms5 || n_ticks < 1 || n_ticks > 1024) return fail(ctx, "bad band profile arguments (P2P transport only)");
+  CU(cudaSetDevice(ctx->device));
+  std::vector<cudaEvent_t> ev((size_t)n_ticks * 6);
+  for (auto &e : ev) CU(cudaEventCreate(&e));
+  int rc = band_step_p2p(ctx, g, perfect != 0, n_ticks, nullptr, ev.data());
+  cudaError_t se = cudaStreamSynchronize(ctx->stream);
+  for (int k = 0; k < 5; k++) ms5[k] = 0.0;
+  if (!rc && se == cudaSuccess)
+    for (int64_t t = 0; t < n_ticks; t++)
+      for (int k = 0; k < 5; k++) {
+        float f = 0.f;
+        cudaEventElapsedTime(&f, ev[(size_t)t * 6 + k], ev[(size_t)t * 6 + k + 1]);
+        ms5[k] += f;
+      }
+  for (auto &e : ev) cudaEventDestroy(e);
+  if (se != cudaSuccess) return fail(ctx, "band profile: %s", cudaGetErrorString(se));
+  return rc ? 1 : check_device_errors(ctx, g);
 }
 
 /* n_ticks of stepper_quick / stepper_perfect on this band, the whole per-tick protocol (see above) driven from here

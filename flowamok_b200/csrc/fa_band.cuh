@@ -131,7 +131,7 @@ __device__ __forceinline__ void band_exchange_u(const GridView &g, const BandLin
     const size_t o = (size_t)(side == 0 ? g.own0 : g.own1 - 1) * P;
     for (int w = tid; w < P; w += nt) {
       dc[w] = __ldcg(&g.calc[o + w]);
-      dm[w] = __ldcg(&g.mymx[o + w]);
+      dm[w] = __ldcg(&g.mymx[o + w]) | (g.mymx_B ? __ldcg(&g.mymx_B[o + w]) : 0ull);
     }
   }
   __threadfence_system();
@@ -150,9 +150,9 @@ __device__ __forceinline__ void band_exchange_u(const GridView &g, const BandLin
     for (int w = tid; w < P; w += nt) {
       const size_t o = (size_t)ghost_row * P + w;
       const u32 oc = __ldcg(&g.calc[o]), nc = oc | __ldcg(&rc[w]);
-      const u64 om = __ldcg(&g.mymx[o]), nm = om | __ldcg(&rm[w]);
+      const u64 om = __ldcg(&g.mymx[o]) | (g.mymx_B ? __ldcg(&g.mymx_B[o]) : 0ull), nm = om | __ldcg(&rm[w]);
       if (nc == oc && nm == om) continue;
-      g.mymx[o] = nm;
+      u_grant(g, o, om, nm);   // into the plane, or (speculative move under way) into the delta plane + fix-up list
       g.calc[o] = nc;
       if (!wake) continue;
       const u32 chg = (oc ^ nc) | (u32)(om ^ nm) | (u32)((om ^ nm) >> 32);

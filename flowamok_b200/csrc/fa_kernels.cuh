@@ -34,13 +34,17 @@ constexpr int STRIP_THREADS = 128;         // k_u_local / k_move block: 4 warps 
 #ifndef FA_M_MINB
 #define FA_M_MINB 5                        // the same for k_move
 #endif
-constexpr int UIT_THREADS = 512;           // k_u_iter block
+#ifndef FA_UIT_THREADS
+#define FA_UIT_THREADS 128
+#endif
+constexpr int UIT_THREADS = FA_UIT_THREADS;   // k_u_iter block; ONE per SM: the clean k_move tiles run beside the fixpoint
 
 struct IterState {
   unsigned int qn[3];       // frontier lengths: iteration it >= 1 reads slot it % 3 and writes (it + 1) % 3
   unsigned int bar[2];      // grid barrier: arrivals, generation
   unsigned int error;       // barrier watchdog tripped
-  unsigned int pad[2];
+  unsigned int chg_n;       // words listed for the fix-up of the speculative move (k_u_iter wipes the previous tick's first)
+  unsigned int pad[1];
 };
 
 struct Diag {
@@ -102,7 +106,7 @@ __device__ __forceinline__ bool grid_barrier(IterState *is, unsigned int nblocks
 // global atomic per warp and push slot.  Ends when an iteration produces an empty list.
 // ---------------------------------------------------------------------------------------------
 #ifndef FA_UIT_TAIL
-#define FA_UIT_TAIL 512
+#define FA_UIT_TAIL 128
 #endif
 constexpr unsigned int UIT_TAIL = FA_UIT_TAIL;   // frontier length below which CTA 0 finishes the fixpoint alone
 #ifndef FA_UIT_CHASE
@@ -112,13 +116,13 @@ constexpr int UIT_CHASE = FA_UIT_CHASE;   // links of a waiting queue one visit 
 
 // first_it = 0: start from the frontier k_u_local left in qlist0 / qn[0]; 1: resume from qlist1 / qn[1] (band merge)
 //
-// P2P = true (a row band whose neighbours' mailboxes are mapped, fa_band.cuh): the whole band protocol of the U phase
-// runs inside this launch.  CTA 0 swaps the boundary rows with the neighbours before the first iteration (the ghost
-// rows then hold the neighbours' rows after THEIR local levels) and after every local fixpoint; the words its merge
-// wakes become the next frontier, and all bands vote -- device to device -- whether anybody woke anything.  No NCCL
-// call, no kernel boundary and no host round trip per convergence round; the other CTAs wait at the grid barrier.
+// P2P = true (a row band whose neighbours' mailboxes are mapped, fa_band.cuh): the convergence rounds of the band protocol
+// run inside this launch.  (k_band_xu has swapped the boundary rows once before it: the ghost rows hold the neighbours' rows
+// after THEIR local levels.)  After every local fixpoint CTA 0 swaps the boundary rows again; the words its merge wakes
+// become the next frontier, and all bands vote -- device to device -- whether anybody woke anything.  No NCCL call, no
+// kernel boundary and no host round trip per convergence round; the other CTAs wait at the grid barrier.
 template <bool P2P>
-__global__ void __launch_bounds__(UIT_THREADS, 2)
+__global__ void __launch_bounds__(UIT_THREADS, 8)   // <= 64 registers: 8 K of an SM's 64 K, so that k_move keeps 4 of its 5 CTAs beside it
 k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *qlist0, unsigned int *qlist1,
          unsigned int first_it, IterState *is, Diag *diag, const __grid_constant__ BandLink L) {
   const int tid = threadIdx.x, nt = blockDim.x, b = blockIdx.x, nb = gridDim.x, lane = tid & 31;
@@ -163,11 +167,14 @@ k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *
 
   // iteration `it` visits the entry indices in qlist[it & 1] (length qn[it % 3]) and appends to qlist[(it + 1) & 1]
   unsigned int it = first_it, its_done = 0;
-  if (P2P) {
-    if (b == 0) band_exchange_u(g, L, table, false, nullptr, nullptr);
+  if (g.mymx_B) {   // speculative move: the previous tick's deltas (its fix-up is done) are wiped, the list starts empty
+    const unsigned int n = *(volatile unsigned int *)g.chg_n;
+    for (unsigned int k = (unsigned)b * nt + tid; k < n; k += (unsigned)nb * nt) g.mymx_B[g.chg_list[k]] = 0ull;
+    if (!grid_barrier(is, nb)) return;
+    if (b == 0 && tid == 0) *g.chg_n = 0u;
     if (!grid_barrier(is, nb)) return;
   }
-  for (;;) {   // convergence rounds (one, unless P2P)
+  for (;;) {   // convergence rounds (one, unless P2P; the boundary rows were swapped once before this launch: k_band_xu)
     bool tail = false;   // once the frontier is short, CTA 0 finishes alone: no more grid-wide barriers
     for (;; it++) {
       const unsigned int n = vis->qn[it % 3u];
@@ -305,6 +312,13 @@ struct alignas(32) RingWord {
   u32 gY, gX;             // cells granted direction.y / direction.x when the ring passes
   u32 pad;
 };
+// The grants of a passing ring go into my|mx.  (A ring whose cells all head along it passes whatever the rest of the fixpoint
+// does: every ring cell waits for the next one, so none is ever calculated, steppers.fut:197-200.  Ring resolution can
+// therefore run BEFORE k_u_iter -- the production order: its grants are then part of the plane the speculative k_move reads.
+// The visits never take a ring's grants for the fixpoint's: they only count grants of calculated cells.)
+__device__ __forceinline__ void ring_grant(const GridView &g, const RingWord &w) {
+  if (w.gY | w.gX) atomicOr((unsigned long long *)&g.mymx[w.wi], (unsigned long long)w.gY | ((unsigned long long)w.gX << 32));
+}
 // every ring cell of the word is uncalculated and holds a car heading exactly the check direction (:197-200)
 __device__ __forceinline__ bool ring_word_ok(const GridView &g, const RingWord &e) {
   const u32 m = e.mN | e.mS | e.mW | e.mE;
@@ -388,7 +402,7 @@ k_rings(const __grid_constant__ GridView g, const RingWord *words, const unsigne
       const int s_ = i / stride;
       if (!okf[s_]) continue;
       const RingWord w = words[(unsigned long long)(ring0 + surv[s_]) * stride + (unsigned)(i - s_ * stride)];
-      if (w.gY | w.gX) atomicOr((unsigned long long *)&g.mymx[w.wi], (unsigned long long)w.gY | ((unsigned long long)w.gX << 32));
+      ring_grant(g, w);
     }
     return;
   }
@@ -406,7 +420,7 @@ k_rings(const __grid_constant__ GridView g, const RingWord *words, const unsigne
     if (!ok) continue;
     for (unsigned long long t = b + lane; t < e; t += 32) {
       const RingWord w = words[t];
-      if (w.gY | w.gX) atomicOr((unsigned long long *)&g.mymx[w.wi], (unsigned long long)w.gY | ((unsigned long long)w.gX << 32));
+      ring_grant(g, w);
     }
   }
 }
@@ -420,7 +434,7 @@ __global__ void k_rings_mark(const __grid_constant__ GridView g, const RingWord 
   const unsigned long long b = off ? off[k] : (unsigned long long)k * stride, e = off ? off[k + 1] : b + stride;
   for (unsigned long long t = b; t < e; t++) {
     const RingWord w = words[t];
-    if (w.gY | w.gX) atomicOr((unsigned long long *)&g.mymx[w.wi], (unsigned long long)w.gY | ((unsigned long long)w.gX << 32));
+    ring_grant(g, w);
   }
 }
 
@@ -451,6 +465,17 @@ k_move(const __grid_constant__ GridView g, int nsx, int ntx, int rs, Diag *diag,
   MTL::phaseB1(g, sm, tx * NW, ya, tid, nt);
   __syncthreads();   // the sector copies are ordered before the arrival patches
   MTL::phaseB2(g, sm, tx * NW, ya, yb - ya, tid, nt);
+}
+
+// The fix-up of the speculative move (fa_stream.h, fix_word): the words around every word whose my|mx the fixpoint changed
+// after the snapshot.  The list length lives on the device (is->chg_n): a fixed grid strides over it.
+__global__ void __launch_bounds__(256)
+k_move_fix(const __grid_constant__ GridView g, u32 *claim, u32 tag, IterState *is, Diag *diag) {
+  const unsigned int n = *(volatile unsigned int *)&is->chg_n * 9u;
+  unsigned int leaks = 0;
+  for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) leaks += fix_item(g, claim, tag, t);
+  leaks = __reduce_add_sync(0xFFFFFFFFu, leaks);
+  if ((threadIdx.x & 31) == 0 && leaks) atomicAdd(&diag->leaks, (unsigned long long)leaks);
 }
 
 // ---------------------------------------------------------------------------------------------

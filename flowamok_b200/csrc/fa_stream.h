@@ -545,4 +545,114 @@ struct MTile {
   }
 };
 
+// =============================================================================================
+// Speculative move + fix-up.  k_move is a pure gather of radius one (steppers.fut:58-125), and the only part of its input
+// that the global fixpoint still changes after k_u_local is my|mx -- of a few thousand words.  So the fixpoint keeps its
+// grants in a delta plane (GridView::mymx_B), k_move runs on the plane k_u_local published BESIDE k_u_iter, and afterwards
+// fix_word recomputes every word in the 3 x 3 neighbourhood of a word with a delta from the final my|mx (plane | delta).
+// What makes this exact:
+//   * a cell's (calc, my, mx) is written once, so the final planes only ADD bits: every arrival the
+//     speculative pass saw stays what it was, new ones appear;
+//   * the new heading plane and the dirty-sector byte are simply rewritten; a new arrival's colour is patched in (its sector of
+//     color_out equals color_in unless it was copied already: the lazy buffer's invariant);
+//   * the per-cell RNG must draw once per fork arrival: arrivals the speculative pass saw are recognised by recomputing
+//     the word from the plane without the delta, and their choice is read back from the heading it wrote; only NEW fork
+//     arrivals draw;
+//   * leaks are counted as the difference between the two recomputations.
+// One thread per word; claim[] (tagged with the tick) makes sure a word is fixed once even if several changed words surround it.
+// =============================================================================================
+struct FixNbh {
+  MRow up, c, dn;
+};
+// rows y-1 .. y+1, words w-1 .. w+1: statics and headings once, my|mx without (nL) and with (nF) the fixpoint's delta
+FA_HD void fix_load(const GridView &g, int y, int w, int ylo, int yhi, FixNbh &nL, FixNbh &nF) {
+  MRow *rowsL[3] = {&nL.up, &nL.c, &nL.dn}, *rowsF[3] = {&nF.up, &nF.c, &nF.dn};
+  for (int r = 0; r < 3; r++) {
+    u32 v[12][3];
+    for (int k = 0; k < 3; k++) {
+      const int yy = y + r - 1, ww = w + k - 1;
+      U4 rd = {0u, 0u, 0u, 0u}, hd = {0u, 0u, 0u, 0u};
+      u64 m = 0ull, d = 0ull;
+      if (yy >= ylo && yy < yhi && ww >= 0 && ww < g.pitch) {
+        const size_t o = (size_t)yy * g.pitch + ww;
+        rd = g.road[o]; hd = g.head_in[o]; m = g.mymx[o]; d = g.mymx_B[o];
+      }
+      v[0][k] = rd.x; v[1][k] = rd.y; v[2][k] = rd.z; v[3][k] = rd.w;
+      v[4][k] = hd.x; v[5][k] = hd.y; v[6][k] = hd.z; v[7][k] = hd.w;
+      v[8][k] = (u32)m; v[9][k] = (u32)(m >> 32);
+      v[10][k] = (u32)(m | d); v[11][k] = (u32)((m | d) >> 32);
+    }
+    for (int pass = 0; pass < 2; pass++) {
+      MRow &q = pass ? *rowsF[r] : *rowsL[r];
+      W3 *f[10] = {&q.UYN, &q.UYS, &q.UXN, &q.UXS, &q.DYN, &q.DYS, &q.DXN, &q.DXS, &q.MY, &q.MX};
+      for (int i = 0; i < 10; i++) {
+        const int j = (pass && i >= 8) ? i + 2 : i;
+        f[i]->l = v[j][0]; f[i]->c = v[j][1]; f[i]->r = v[j][2];
+      }
+    }
+  }
+}
+// returns the number of additional leaks
+FA_HD unsigned int fix_word(const GridView &g, int y, int w) {
+  const int ylo = g.row0 < 0 ? -g.row0 : 0;
+  const int yhi = g.gh < g.gh_global - g.row0 ? g.gh : g.gh_global - g.row0;
+  const size_t o = (size_t)y * g.pitch + w;
+  const Edge e = edge_of(g, y, w);
+  FixNbh nL, nF;
+  fix_load(g, y, w, ylo, yhi, nL, nF);
+  const MPre pL = m_pre(nL.up, nL.c, nL.dn, e), pF = m_pre(nF.up, nF.c, nF.dn, e);
+  const u32 fkL = pL.fork & e.valid, fkF = pF.fork & e.valid;
+  // choices: the speculative pass's for the forks it saw (a fork arrival's new heading has DXN set iff the choice was x)
+  u32 CH = g.head_out[o].z & fkL;
+  u32 m = fkF & ~fkL;
+  if (m) {
+    if (g.chooser == CHOOSE_X) CH |= m;
+    else if (g.chooser == CHOOSE_TAPE) CH |= g.tape_bit ? m : 0u;
+    else if (g.chooser == CHOOSE_RANDOM)
+      while (m) {
+        const int b = ffs32(m);
+        m &= m - 1;
+        const size_t ci = o * 32 + b;
+        u64 st = g.rng[ci];
+        if (draw_choice01(st, g.rng_inc)) CH |= 1u << b;
+        g.rng[ci] = st;
+      }
+  }
+  const MOut out = m_post(pF, CH);
+  const U4 hd = {out.DYN, out.DYS, out.DXN, out.DXS};
+  g.head_out[o] = hd;
+  const u32 arrF = out.AY | out.AX, arrL = (pL.AY | pL.AX) & e.valid;
+  u32 arrS = 0u;
+  for (int k = 0; k < 4; k++) arrS |= ((arrF >> (8 * k)) & 0xFFu) ? (1u << k) : 0u;
+  g.dirty_out[o] = (unsigned char)arrS;
+  const size_t cpitch = (size_t)g.pitch * 32;
+  u32 na = arrF & ~arrL;
+  while (na) {   // a new arrival takes its predecessor's colour (steppers.fut:109)
+    const int b = ffs32(na);
+    na &= na - 1;
+    const u32 bit = 1u << b;
+    const size_t dst = o * 32 + b;
+    size_t src;
+    if (out.AY & bit) src = (pF.UYS & bit) ? dst + cpitch : dst - cpitch;
+    else src = (pF.UXS & bit) ? dst + 1 : dst - 1;
+    g.color_out[dst] = g.color_in[src];
+  }
+  return (unsigned int)(popc32(out.leak) - popc32(pL.leak & e.valid));
+}
+// item t of the fix-up: neighbour t % 9 of listed word t / 9; claim: one u32 per plane word, tag = tick number + 1
+FA_HD unsigned int fix_item(const GridView &g, u32 *claim, u32 tag, unsigned int t) {
+  const u32 wi = g.chg_list[t / 9u];
+  const int k = (int)(t % 9u);
+  const int y = (int)(wi / (u32)g.pitch) + k / 3 - 1, w = (int)(wi % (u32)g.pitch) + k % 3 - 1;
+  if (y < g.own0 || y >= g.own1 || w < 0 || w >= g.pitch) return 0u;   // only owned words are moved
+  const size_t o = (size_t)y * g.pitch + w;
+#if defined(__CUDA_ARCH__)
+  if (atomicExch(&claim[o], tag) == tag) return 0u;
+#else
+  if (claim[o] == tag) return 0u;
+  claim[o] = tag;
+#endif
+  return fix_word(g, y, w);
+}
+
 }  // namespace fa

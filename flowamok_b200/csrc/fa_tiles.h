@@ -34,6 +34,13 @@ struct GridView {
   u32 *pref_out;
   u32 *calc;               // per-tick plane `calculated` (steppers.fut:140-145 resets it: here it is scratch)
   u64 *mymx;               // per-tick planes direction.y (low word) / direction.x (high word), one 64-bit access
+  // Speculative move (fa_stream.h, fix_word): with mymx_B set, the global fixpoint leaves `mymx` -- as k_u_local, ring
+  // resolution and a band's first boundary swap wrote it -- alone and ORs its grants into the delta plane mymx_B (zero
+  // between ticks); k_move gathers from `mymx` BESIDE the fixpoint, and every word whose delta becomes non-zero is listed once
+  // in chg_list for the fix-up.  The final planes are mymx | mymx_B.  All three null: the kernels run one after the other.
+  u64 *mymx_B;
+  u32 *chg_list;
+  unsigned int *chg_n;
   u32 *ustate;             // per word: U_NONE, or its worklist entry index (| U_QUEUED while on the next list)
   // colour payload [gh][pitch*32], LAZY double buffer (fa_stream.h, MTile): color_out already equals color_in
   // everywhere except in the 32-byte sectors that received a car during the previous tick (dirty_in: one byte per plane
@@ -111,6 +118,15 @@ FA_HD void fa_fence() {
 }
 FA_HD void fa_fence_device() { fa_fence<false>(); }
 FA_HD u64 pack_mymx(u32 my, u32 mx) { return (u64)my | ((u64)mx << 32); }
+// The fixpoint (a visit, or a band's merge of the neighbour's row) grants `add` in word o whose my|mx currently reads `cur`:
+// into the plane itself, or -- speculative move -- into the delta plane; the first delta of a word lists it for the fix-up.
+FA_HD void u_grant(const GridView &g, size_t o, u64 cur, u64 add) {
+  if (!g.mymx_B) { FA_ATOMIC_OR_U64(&g.mymx[o], add); return; }
+  const u64 d = add & ~cur;
+  if (d == 0ull) return;
+  const u64 old = FA_ATOMIC_OR_U64(&g.mymx_B[o], d);
+  if (old == 0ull) g.chg_list[FA_ATOMIC_ADD_U32(g.chg_n, 1u)] = (u32)o;
+}
 
 constexpr u32 U_NONE = 0xFFFFFFFFu;    // word has no unresolved waiting car
 constexpr u32 U_QUEUED = 0x80000000u;  // word is already on the next iteration's list
@@ -140,8 +156,10 @@ FA_HD void u_ld_mymx(const GridView &g, size_t o, bool ok, UPlanes &p) {
   if (ok) {
 #if defined(__CUDA_ARCH__)
     m = *(volatile const u64 *)&g.mymx[o];
+    if (g.mymx_B) m |= *(volatile const u64 *)&g.mymx_B[o];
 #else
     m = g.mymx[o];
+    if (g.mymx_B) m |= g.mymx_B[o];
 #endif
   }
   p.MY = (u32)m; p.MX = (u32)(m >> 32);
@@ -248,8 +266,10 @@ FA_HD int u_iter_entry(const GridView &g, const UEntry &e, u32 idx, u32 *push) {
   int np = 0;
   if (chg) {
     // next_preference_flow_x follows the grants (k_u_local wrote it for the grants it knew); one visitor per word
-    g.pref_out[e.wi] = u_pref_from_grants(e.GY, e.GX, pref, n.MY, n.MX) & valid;
-    FA_ATOMIC_OR_U64(&g.mymx[e.wi], pack_mymx(n.MY, n.MX));
+    // (grants of the FIXPOINT only, i.e. of calculated cells: ring resolution may already have put its grants into my|mx,
+    // and it never touches the preference, steppers.fut:205-211)
+    g.pref_out[e.wi] = u_pref_from_grants(e.GY, e.GX, pref, n.MY & n.R, n.MX & n.R) & valid;
+    u_grant(g, e.wi, pack_mymx(c.MY, c.MX), pack_mymx(n.MY, n.MX));
     fa_fence<CTA>();
     FA_ATOMIC_OR_U32(&g.calc[e.wi], n.R);
     fa_fence<CTA>();

@@ -95,6 +95,11 @@ int flowamok_step_perfect(flowamok_context *ctx, flowamok_grid *g, int64_t n_tic
  * n_ticks <= 4096.  Measurement aid for bench.py's roofline object, not a reference operator. */
 int flowamok_step_profile(flowamok_context *ctx, flowamok_grid *g, int perfect, int64_t n_ticks, double *ms);
 
+/* The production tick on a time line (it forks after k_u_local: the global fixpoint on one stream, k_move on the snapshot
+ * beside it, then the fix-up), summed over n_ticks <= 1024, in ms: {k_u_local (+ k_rings), fork -> end of k_u_iter,
+ * fork -> end of the speculative k_move, join -> end of k_move_fix, whole tick}.  Measurement aid. */
+int flowamok_step_timeline(flowamok_context *ctx, flowamok_grid *g, int perfect, int64_t n_ticks, double *ms5);
+
 /* Ordered cell_leak list of ONE tick (src/model.fut:26, option.fut:3-12): runs one tick and returns up
  * to cap leaks in row-major order of the source cell as 8 int64 per leak:
  * {y_next, x_next, y_src, x_src, dy, dx, color, pref}.  Synchronous. */
@@ -171,6 +176,9 @@ int flowamok_band_step(flowamok_context *ctx, flowamok_grid *g, int perfect, int
 int flowamok_band_set_cuts(flowamok_context *ctx, flowamok_grid *g, int world, const int64_t *cuts);
 int flowamok_band_p2p_open(flowamok_context *ctx, flowamok_grid *g, int rank, int world, void *handle64, void **local_ptr);
 int flowamok_band_p2p_connect(flowamok_context *ctx, flowamok_grid *g, const void *handles, void *const *local_ptrs, int bands_on_device);
+/* flowamok_step_profile for a band on the P2P transport: summed device ms of {k_band_xstate, k_u_local, k_u_iter with the
+ * convergence rounds, ring resolution with its swaps, k_move} over n_ticks; every band must call it */
+int flowamok_band_step_profile(flowamok_context *ctx, flowamok_grid *g, int perfect, int64_t n_ticks, double *ms5);
 /* unmap the peers (every band; then synchronise the processes before any grid is freed) */
 int flowamok_band_p2p_close(flowamok_context *ctx, flowamok_grid *g);
 /* rings that straddle a cut under the host-driven protocol: verdict words of this band (after flowamok_band_rings),

@@ -40,6 +40,12 @@ struct HostGrid {
   Rings rings;
   bool has_rings = false;
   std::vector<u32> rbits;   // verdicts of this band on the rings that straddle its cuts
+  // speculative move (fa_stream.h fix_word): the fixpoint's delta plane, the words that have a delta, fix-up claims
+  std::vector<u64> mymx_B;
+  std::vector<u32> chg_list, claim;
+  unsigned int chg_n = 0;
+  u32 tick = 0;
+  int64_t leaks_spec = 0;
 };
 
 HostGrid *make(int gh_global, int gw, int row_begin, int row_end, int halo, int variant) {
@@ -53,12 +59,18 @@ HostGrid *make(int gh_global, int gw, int row_begin, int row_end, int halo, int 
   h->road.assign(nw, U4{0, 0, 0, 0});
   for (int k = 0; k < 2; k++) { h->head[k].assign(nw, U4{0, 0, 0, 0}); h->pref[k].assign(nw, 0); h->color[k].assign(nc, 0); h->dirty[k].assign(nw, 0); }
   h->calc.assign(nw, 0); h->mymx.assign(nw, 0); h->ustate.assign(nw, U_NONE);
+  h->mymx_B.assign(nw, 0); h->chg_list.assign(nw, 0); h->claim.assign(nw, 0);
   h->rng.assign(nc, 0);
   return h;
 }
 
-GridView view(HostGrid *h, int chooser, u32 tape_bit) {
+// spec: 0 = what runs before the speculative move reads the plane (or a tick without one), 2 = what runs after: grants go
+// into the delta plane, changed words are listed
+GridView view(HostGrid *h, int chooser, u32 tape_bit, int spec = 0) {
   GridView g;
+  g.mymx_B = spec == 2 ? h->mymx_B.data() : nullptr;
+  g.chg_list = spec == 2 ? h->chg_list.data() : nullptr;
+  g.chg_n = spec == 2 ? &h->chg_n : nullptr;
   g.gh = h->gh; g.gw = h->gw; g.pitch = h->pitch; g.wvalid = h->wvalid;
   g.gh_global = h->gh_global; g.row0 = h->row0; g.own0 = h->own0; g.own1 = h->own1;
   g.road = h->road.data();
@@ -148,9 +160,19 @@ void do_rings(HostGrid *h, const GridView &g, int kind = 0, const u32 *pass = nu
       if (R.y[t] < lo || R.y[t] >= hi) continue;
       size_t o = (size_t)(R.y[t] - h->row0) * h->pitch + (R.x[t] >> 5);
       u32 bit = 1u << (R.x[t] & 31);
-      if (R.grant[t] == 1) g.mymx[o] |= (u64)bit; else g.mymx[o] |= (u64)bit << 32;
+      const u64 add = R.grant[t] == 1 ? (u64)bit : (u64)bit << 32;
+      u_grant(g, o, g.mymx[o] | (g.mymx_B ? g.mymx_B[o] : 0ull), add);   // plane, or delta plane + fix-up list
     }
   }
+}
+
+// fix-up of the speculative move: every item of the list, as k_move_fix does
+int64_t do_fix(HostGrid *h, const GridView &g) {
+  int64_t leaks = 0;
+  for (unsigned int t = 0; t < h->chg_n * 9u; t++) leaks += fix_item(g, h->claim.data(), h->tick + 1, t);
+  for (unsigned int k = 0; k < h->chg_n; k++) h->mymx_B[h->chg_list[k]] = 0ull;   // k_u_iter's prologue of the next tick
+  h->chg_n = 0;
+  return leaks;
 }
 
 template <int SW, int NW, int CAP>
@@ -160,9 +182,10 @@ void m_lane(void *p, int lane) {
   MArgs<SW, NW, CAP> *a = (MArgs<SW, NW, CAP> *)p;
   a->leaks[lane] = MTile<SW, NW, CAP>::phaseA(*a->g, a->has, a->sx, a->wi, a->ya, a->yb, lane, nullptr, a->sm);
 }
-// k_move: one "CTA" per tile: phase A warp by warp (coroutines), phase B with a loop over the thread ids
+// k_move: one "CTA" per tile: phase A warp by warp (coroutines), phase B with a loop over the thread ids.
+// flip = false: the speculative pass (the buffers are flipped after the fix-up)
 template <int SW, int NW, int CAP>
-int64_t do_move(HostGrid *h, const GridView &g, int rs, int nt) {
+int64_t do_move(HostGrid *h, const GridView &g, int rs, int nt, bool flip) {
   typedef MTile<SW, NW, CAP> MTL;
   int64_t leaks = 0;
   const int nsx = (h->pitch + SW - 1) / SW, ntx = (nsx + NW - 1) / NW, nty = (h->own1 - h->own0 + rs - 1) / rs;
@@ -183,7 +206,7 @@ int64_t do_move(HostGrid *h, const GridView &g, int rs, int nt) {
       for (int tid = 0; tid < nt; tid++) MTL::phaseB1(g, sm, tx * NW, ya, tid, nt);
       for (int tid = 0; tid < nt; tid++) MTL::phaseB2(g, sm, tx * NW, ya, yb - ya, tid, nt);
     }
-  h->cur ^= 1;
+  if (flip) h->cur ^= 1;
   return leaks;
 }
 
@@ -197,12 +220,17 @@ void v_u_init(HostGrid *h, const GridView &g) {
   }
 }
 int v_order(const HostGrid *h) { return h->variant == 1 ? 2 : h->variant == 2 ? 1 : 0; }
-int64_t v_move(HostGrid *h, const GridView &g, int) {
+int64_t v_move(HostGrid *h, const GridView &g, bool flip) {
   switch (h->variant) {
-  case 1: return do_move<2, 3, 8>(h, g, 3, 6);      // tiny arrival list: the overflow path runs
-  case 2: return do_move<5, 2, 64>(h, g, 4, 64);
-  default: return do_move<30, 4, 2048>(h, g, 16, 128);
+  case 1: return do_move<2, 3, 8>(h, g, 3, 6, flip);      // tiny arrival list: the overflow path runs
+  case 2: return do_move<5, 2, 64>(h, g, 4, 64, flip);
+  default: return do_move<30, 4, 2048>(h, g, 16, 128, flip);
   }
+}
+// the speculative pass: k_move gathering from the plane as it is now (the fixpoint's later grants go into the delta plane)
+int64_t v_move_spec(HostGrid *h, int chooser, u32 tape_bit) {
+  GridView gs = view(h, chooser, tape_bit, 0);
+  return v_move(h, gs, false);
 }
 
 }  // namespace
@@ -282,12 +310,25 @@ int64_t emul_step(void *p, int variant, int nthreads, int chooser, uint32_t tape
   HostGrid *h = (HostGrid *)p;
   h->variant = variant;
   emul_set_rings(p, n_rings, off, ry, rx, cy, cx, grant);
-  GridView g = view(h, chooser, tape_bit);
   h->iters = h->relaxed = 0;
-  v_u_init(h, g);
-  u_iter(h, g, v_order(h));
-  do_rings(h, g);
-  int64_t leaks = v_move(h, g, nthreads);
+  h->chg_n = 0;
+  int64_t leaks;
+  if (variant == 2 && n_rings < 0) {   // the kernels one after the other (what flowamok_step_profile / _step_leaks run)
+    GridView g = view(h, chooser, tape_bit, 0);
+    v_u_init(h, g);
+    u_iter(h, g, v_order(h));
+    leaks = v_move(h, g, true);
+  } else {   // the production order: snapshot writers, speculative move, fixpoint with listing, fix-up
+    GridView g1 = view(h, chooser, tape_bit, 0), g2 = view(h, chooser, tape_bit, 2);
+    v_u_init(h, g1);
+    do_rings(h, g1);                               // ring resolution does not depend on the fixpoint: before the snapshot is read
+    leaks = v_move_spec(h, chooser, tape_bit);     // on the GPU: beside k_u_iter
+    u_iter(h, g2, v_order(h));
+    leaks += do_fix(h, g2);
+    h->cur ^= 1;
+  }
+  h->tick++;
+  (void)nthreads;
   if (stats) { stats[0] += h->iters; stats[1] += h->relaxed; }
   return leaks;
 }
@@ -316,10 +357,14 @@ void emul_band_unpack_state(void *p, int side, const void *buf) {
   memcpy(h->pref[h->cur].data() + (size_t)r2 * P, b + 2 * P * 16, 2 * P * 4);
   memcpy(h->color[h->cur].data() + (size_t)rc * P * 32, b + 2 * P * 20, P * 128);
 }
-void emul_band_u_init(void *p, int chooser, uint32_t tape_bit) {   // k_u_init only; emul_band_u_resume runs the frontier
+// k_u_local, and at once the speculative k_move on the snapshot it leaves: everything the band protocol does afterwards
+// (merges of the neighbours' rows, frontier iterations, ring resolution) lists the words it changes, and emul_band_move
+// is the fix-up.  Stricter than the GPU path, which reads the snapshot after the first boundary swap.
+void emul_band_u_init(void *p, int chooser, uint32_t tape_bit) {
   HostGrid *h = (HostGrid *)p;
-  GridView g = view(h, chooser, tape_bit);
+  GridView g = view(h, chooser, tape_bit, 0);
   v_u_init(h, g);
+  h->leaks_spec = v_move_spec(h, chooser, tape_bit);
 }
 void emul_band_pack_u(void *p, int side, void *buf) {
   HostGrid *h = (HostGrid *)p;
@@ -327,22 +372,25 @@ void emul_band_pack_u(void *p, int side, void *buf) {
   const int r = side == 0 ? h->own0 : h->own1 - 1;
   char *b = (char *)buf;
   memcpy(b, h->calc.data() + (size_t)r * P, P * 4);
-  memcpy(b + P * 4, h->mymx.data() + (size_t)r * P, P * 8);
+  u64 *dm = (u64 *)(b + P * 4);
+  for (size_t w = 0; w < P; w++) dm[w] = h->mymx[(size_t)r * P + w] | h->mymx_B[(size_t)r * P + w];
 }
-int64_t emul_band_merge_u(void *p, int side, const void *buf, int wake) {  // k_band_merge
+int64_t emul_band_merge_u(void *p, int side, const void *buf, int wake) {  // k_band_merge / band_exchange_u
   HostGrid *h = (HostGrid *)p;
-  GridView g = view(h, 0, 0);
+  GridView g = view(h, 0, 0, 2);
   const size_t P = (size_t)h->pitch;
   const int ghost = side == 0 ? h->own0 - 1 : h->own1, own = side == 0 ? h->own0 : h->own1 - 1;
   const u32 *rc = (const u32 *)buf;
   const u64 *rm = (const u64 *)((const char *)buf + P * 4);
   for (int w = 0; w < h->pitch; w++) {
     size_t o = (size_t)ghost * P + w;
+    const u64 om = h->mymx[o] | h->mymx_B[o];
     u32 nc = h->calc[o] | rc[w];
-    u64 nm = h->mymx[o] | rm[w];
-    if (nc == h->calc[o] && nm == h->mymx[o]) continue;
-    const u32 chg = (h->calc[o] ^ nc) | (u32)(h->mymx[o] ^ nm) | (u32)((h->mymx[o] ^ nm) >> 32);
-    h->mymx[o] = nm; h->calc[o] = nc;
+    u64 nm = om | rm[w];
+    if (nc == h->calc[o] && nm == om) continue;
+    const u32 chg = (h->calc[o] ^ nc) | (u32)(om ^ nm) | (u32)((om ^ nm) >> 32);
+    u_grant(g, o, om, nm);
+    h->calc[o] = nc;
     if (!wake) continue;
     for (int dx = -1; dx <= 1; dx++) {
       if (!band_word_reads_ghost(g, h->table.data(), side, own, w, dx, chg)) continue;
@@ -359,19 +407,19 @@ int emul_debug_cell(void *p, int y, int x) {
   if (yl < 0 || yl >= h->gh) return -1;
   const size_t o = (size_t)yl * h->pitch + (x >> 5);
   const u32 bit = 1u << (x & 31);
-  return ((h->calc[o] & bit) ? 1 : 0) | (((u32)h->mymx[o] & bit) ? 2 : 0) | (((u32)(h->mymx[o] >> 32) & bit) ? 4 : 0) |
+  return ((h->calc[o] & bit) ? 1 : 0) | (((u32)(h->mymx[o] | h->mymx_B[o]) & bit) ? 2 : 0) | (((u32)((h->mymx[o] | h->mymx_B[o]) >> 32) & bit) ? 4 : 0) |
          ((h->pref[h->cur][o] & bit) ? 8 : 0) | ((h->ustate[o] != U_NONE) ? 16 : 0) |
          ((h->head[h->cur][o].x & bit) ? 32 : 0) | ((h->head[h->cur][o].z & bit) ? 64 : 0) | ((h->road[o].x & bit) ? 128 : 0) |
          ((h->road[o].z & bit) ? 256 : 0);
 }
 void emul_band_u_resume(void *p) {
   HostGrid *h = (HostGrid *)p;
-  GridView g = view(h, 0, 0);
+  GridView g = view(h, 0, 0, 2);
   u_iter(h, g, v_order(h));
 }
 void emul_band_rings(void *p) {
   HostGrid *h = (HostGrid *)p;
-  GridView g = view(h, 0, 0);
+  GridView g = view(h, 0, 0, 2);
   do_rings(h, g);
 }
 int64_t emul_band_ring_words(void *p) {
@@ -384,12 +432,15 @@ void emul_band_ring_verdicts(void *p, uint32_t *out) {   // copy and reset
 }
 void emul_band_rings_apply(void *p, const uint32_t *pass) {
   HostGrid *h = (HostGrid *)p;
-  GridView g = view(h, 0, 0);
+  GridView g = view(h, 0, 0, 2);
   do_rings(h, g, 1, pass);
 }
 int64_t emul_band_move(void *p, int chooser, uint32_t tape_bit) {
   HostGrid *h = (HostGrid *)p;
-  GridView g = view(h, chooser, tape_bit);
-  return v_move(h, g, 7);
+  GridView g = view(h, chooser, tape_bit, 2);
+  const int64_t leaks = h->leaks_spec + do_fix(h, g);
+  h->cur ^= 1;
+  h->tick++;
+  return leaks;
 }
 }
