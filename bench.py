@@ -136,7 +136,7 @@ def cpu_oracle_run(size_w, rows, ticks, warm, threads=None, perfect=False):
     return rows * size_w * ticks / dt / 1e9, dt, O.max_threads()
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, emit):
     if rank != 0:
         return 0
     size = args.size
@@ -160,11 +160,19 @@ def run_reference(args, rank):
             "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference is pure Futhark; no Futhark compiler in the image, so this is the C/OpenMP oracle port "
                     "in the reference's layout and schedule (BASELINE.md plan B)"}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
 def main():
+    # ONE JSON line on stdout: everything else that libraries print there (NCCL's version banner, ...) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
@@ -192,7 +200,7 @@ def main():
         args.mode = "quick" if world == 1 else "perfect"
 
     if args.impl == "reference":
-        return run_reference(args, rank)
+        return run_reference(args, rank, emit)
 
     import ctypes as C
     import numpy as np
@@ -423,7 +431,7 @@ def main():
         except Exception as e:  # the oracle is only a reported baseline
             line["cpu_baseline"] = {"value": None, "unit": "GCUPS", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         if use_p2p:
             band.p2p_close()      # unmap the peers' mailboxes, then make sure everybody has before anything is freed
