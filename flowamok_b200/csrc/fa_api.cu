@@ -1392,7 +1392,7 @@ static int band_step_p2p(flowamok_context *ctx, flowamok_grid *g, bool perfect, 
       }
     }
     if (multi) {   // ghost rows := the neighbours' boundary rows after THEIR local levels (and ring marks)
-      k_band_xu<<<1, 512, 0, st>>>(v, g->link);
+      k_band_xu<<<1, 1024, 0, st>>>(v, g->link);
       KCHECK("k_band_xu");
     }
     if (e) CU(cudaEventRecord(e[3], st));

@@ -110,18 +110,16 @@ __device__ __forceinline__ char *band_inbox_s(char *box, const BandLink &L, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// u exchange, by ALL threads of ONE CTA: push this band's boundary rows of calc / my|mx into the neighbours' inboxes,
-// wait for theirs, OR them into the ghost rows.  wake: the owned words that hold a waiting car which reads a changed ghost
-// cell go on `list` (length *cnt) -- the same rule as k_band_merge.  The rows are read with L1-bypassing loads: other
-// CTAs (or the peer) wrote them.
+// u exchange: push this band's boundary rows of calc / my|mx into the neighbours' inboxes, wait for theirs, OR them into the
+// ghost rows.  In three steps, so that a whole grid can share the work (k_u_iter: a slice per thread, grid barriers between
+// the steps) as well as a single CTA (k_band_xu):
+//   band_push_u   thread gtid of gthreads copies its words of both boundary rows (L1-bypassing loads: other CTAs wrote them);
+//                 the caller fences at system scope and synchronises all pushing threads before
+//   band_flags_u  (threads 0 and 1 of ONE CTA) publishes message number `seq` to the neighbours and waits for theirs;
+//   band_merge_u  ORs the received rows into the ghost rows.  wake: the owned words that hold a waiting car which reads a changed
+//                 ghost cell go on `list` (length *cnt) -- the same rule as k_band_merge.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void band_exchange_u(const GridView &g, const BandLink &L, const UEntry *table, bool wake, unsigned int *list,
-                                                unsigned int *cnt) {
-  __shared__ unsigned int seq_sh;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  if (tid == 0) seq_sh = ++L.dev->u_seq;
-  __syncthreads();
-  const unsigned int seq = seq_sh;
+__device__ __forceinline__ void band_push_u(const GridView &g, const BandLink &L, unsigned int seq, int gtid, int gthreads) {
   const int P = g.pitch;
   for (int side = 0; side < 2; side++) {
     if (!L.nb[side]) continue;
@@ -129,25 +127,29 @@ __device__ __forceinline__ void band_exchange_u(const GridView &g, const BandLin
     u32 *dc = reinterpret_cast<u32 *>(slot);
     u64 *dm = reinterpret_cast<u64 *>(slot + (size_t)P * 4);
     const size_t o = (size_t)(side == 0 ? g.own0 : g.own1 - 1) * P;
-    for (int w = tid; w < P; w += nt) {
+    for (int w = gtid; w < P; w += gthreads) {
       dc[w] = __ldcg(&g.calc[o + w]);
       dm[w] = __ldcg(&g.mymx[o + w]) | (g.mymx_B ? __ldcg(&g.mymx_B[o + w]) : 0ull);
     }
   }
-  __threadfence_system();
-  __syncthreads();
+}
+__device__ __forceinline__ void band_flags_u(const BandLink &L, unsigned int seq) {
+  const int tid = threadIdx.x;
   if (tid < 2 && L.nb[tid]) {
     st_release_sys(&reinterpret_cast<MailHdr *>(L.nb[tid])->u_seq[1 - tid], seq);
     band_wait(&reinterpret_cast<MailHdr *>(L.self)->u_seq[tid], seq, 0, L.dev, 2u);
   }
-  __syncthreads();
+}
+__device__ __forceinline__ void band_merge_u(const GridView &g, const BandLink &L, const UEntry *table, unsigned int seq, bool wake,
+                                             unsigned int *list, unsigned int *cnt, int gtid, int gthreads) {
+  const int P = g.pitch;
   for (int side = 0; side < 2; side++) {
     if (!L.nb[side]) continue;
     const char *slot = band_inbox_u(L.self, L, side, seq);
     const u32 *rc = reinterpret_cast<const u32 *>(slot);
     const u64 *rm = reinterpret_cast<const u64 *>(slot + (size_t)P * 4);
     const int ghost_row = side == 0 ? g.own0 - 1 : g.own1, own_row = side == 0 ? g.own0 : g.own1 - 1;
-    for (int w = tid; w < P; w += nt) {
+    for (int w = gtid; w < P; w += gthreads) {
       const size_t o = (size_t)ghost_row * P + w;
       const u32 oc = __ldcg(&g.calc[o]), nc = oc | __ldcg(&rc[w]);
       const u64 om = __ldcg(&g.mymx[o]) | (g.mymx_B ? __ldcg(&g.mymx_B[o]) : 0ull), nm = om | __ldcg(&rm[w]);
@@ -163,6 +165,21 @@ __device__ __forceinline__ void band_exchange_u(const GridView &g, const BandLin
       }
     }
   }
+}
+// the three steps by ALL threads of ONE CTA
+__device__ __forceinline__ void band_exchange_u(const GridView &g, const BandLink &L, const UEntry *table, bool wake, unsigned int *list,
+                                                unsigned int *cnt) {
+  __shared__ unsigned int seq_sh;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) seq_sh = ++L.dev->u_seq;
+  __syncthreads();
+  const unsigned int seq = seq_sh;
+  band_push_u(g, L, seq, tid, nt);
+  __threadfence_system();
+  __syncthreads();
+  band_flags_u(L, seq);
+  __syncthreads();
+  band_merge_u(g, L, table, seq, wake, list, cnt, tid, nt);
   __threadfence();
   __syncthreads();
 }
@@ -241,7 +258,7 @@ k_band_xstate(int pitch, int own0, int own1, U4 *head, u32 *pref, u32 *color, co
 }
 // k_band_xu: one more u exchange without waking anybody (after ring resolution: ring marks on a boundary row must reach
 // the neighbour's ghost row before k_move).  One CTA.
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 k_band_xu(const __grid_constant__ GridView g, const __grid_constant__ BandLink L) {
   band_exchange_u(g, L, nullptr, false, nullptr, nullptr);
 }

@@ -167,6 +167,7 @@ k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *
 
   // iteration `it` visits the entry indices in qlist[it & 1] (length qn[it % 3]) and appends to qlist[(it + 1) & 1]
   unsigned int it = first_it, its_done = 0;
+  unsigned int useq = P2P ? *(volatile unsigned int *)&L.dev->u_seq : 0u;   // number of the last u message sent (k_band_xu counts too)
   if (g.mymx_B) {   // speculative move: the previous tick's deltas (its fix-up is done) are wiped, the list starts empty
     const unsigned int n = *(volatile unsigned int *)g.chg_n;
     for (unsigned int k = (unsigned)b * nt + tid; k < n; k += (unsigned)nb * nt) g.mymx_B[g.chg_list[k]] = 0ull;
@@ -198,18 +199,29 @@ k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *
       else if (!grid_barrier(is, nb)) return;
     }
     if (!P2P) break;
-    // CTA 0 stands at the iteration whose list is empty (slot it % 3 == 0, slot (it + 1) % 3 was cleared one iteration
-    // ago): the merge appends the woken words to ql[it & 1] / qn[it % 3], which is where the next iteration reads.
+    // One convergence round, the whole grid sharing the row work.  CTA 0 stands at the iteration whose list is empty (slot
+    // it % 3 == 0, slot (it + 1) % 3 was cleared one iteration ago): the merge appends the woken words to ql[it & 1] /
+    // qn[it % 3], which is where the next iteration reads.  The other CTAs may have left the loop early (tail): they take `it`
+    // from CTA 0.
+    if (b == 0 && tid == 0) L.dev->round_it = it;
+    if (!grid_barrier(is, nb)) return;                      // the local fixpoint is over: the boundary rows are final for this round
+    it = *(volatile unsigned int *)&L.dev->round_it;
+    useq++;
+    band_push_u(g, L, useq, b * nt + tid, nb * nt);
+    __threadfence_system();
+    if (!grid_barrier(is, nb)) return;                      // every slice is pushed and fenced
+    if (b == 0) { band_flags_u(L, useq); __syncthreads(); }
+    if (!grid_barrier(is, nb)) return;                      // the neighbours' rows have arrived
+    band_merge_u(g, L, table, useq, true, ql[it & 1], &is->qn[it % 3u], b * nt + tid, nb * nt);
+    if (!grid_barrier(is, nb)) return;                      // the woken list is complete
     if (b == 0) {
-      band_exchange_u(g, L, table, true, ql[it & 1], &is->qn[it % 3u]);
       const bool any = band_vote(L, vis->qn[it % 3u] != 0u);
       if (tid == 0) {
-        L.dev->go = any ? 1u : 0u; L.dev->round_it = it; L.dev->rounds++;
+        L.dev->go = any ? 1u : 0u; L.dev->rounds++; L.dev->u_seq = useq;
         is->qn[(it + 1) % 3u] = 0;
       }
     }
     if (!grid_barrier(is, nb)) return;
-    it = *(volatile unsigned int *)&L.dev->round_it;
     if (*(volatile unsigned int *)&L.dev->go == 0u) break;
   }
   {   // visits of this CTA: warp sums, then one shared and one global atomic
