@@ -314,32 +314,37 @@ def main():
         if not args.no_e2e:
             # one grid: the whole value (roads included); row bands: the car state of the owned rows (roads, cycles
             # and halo rows stay resident: flowamok_grid_upload_cars)
-            fields_up = ("uy", "ux", "dy", "dx", "color", "pref", "rng_state") if world == 1 else \
-                        ("dy", "dx", "color", "pref", "rng_state")
-            fields_dn = ("dy", "dx", "color", "pref", "rng_state")
-            host = g.download()                              # whole-grid shaped arrays; only my rows are filled
+            # The per-cell RNG states travel sparsely: only cells with a road on both axes can ever draw (steppers.fut:101-103),
+            # so the host keeps (flat index, state) of those "corner" cells -- 16 bytes per corner instead of 8 per cell.
+            fields_up = ("uy", "ux", "dy", "dx", "color", "pref") if world == 1 else ("dy", "dx", "color", "pref")
+            fields_dn = ("dy", "dx", "color", "pref")
+            host = g.download(fields=tuple(dict.fromkeys(fields_up + fields_dn)))   # whole-grid shaped; only my rows are filled
             lo, hi = rows
             pinned = world == 1                              # several ranks: pageable (bounded host pinning)
             def hostbuf(a):
-                t = torch.from_numpy(np.ascontiguousarray(a[lo:hi]))
+                t = torch.from_numpy(np.ascontiguousarray(a))
                 return (t.pin_memory() if pinned else t).numpy()
-            up = {k: hostbuf(host[k]) for k in fields_up}
+            up = {k: hostbuf(host[k][lo:hi]) for k in fields_up}
             del host
             dn = {k: up[k] for k in fields_dn}               # the result lands in the buffers the input came from
-            h2d = sum(v.nbytes for v in up.values())
-            d2h = sum(v.nbytes for v in dn.values()) + 8
+            ci, cs = g.rng_corners()
+            ci, cs = hostbuf(ci), hostbuf(cs)
+            h2d = sum(v.nbytes for v in up.values()) + ci.nbytes + cs.nbytes
+            d2h = sum(v.nbytes for v in dn.values()) + ci.nbytes + cs.nbytes + 8
 
             def band_ptr(a):                                 # the ABI takes whole-grid base pointers
                 return a.ctypes.data - lo * a.strides[0]
             barrier()
             t0 = time.perf_counter()
             if world == 1:
-                ctx.check(ctx.L.flowamok_grid_upload(ctx.h, g.h, *[band_ptr(up[k]) for k in fields_up], fa.PCG_INC))
+                ctx.check(ctx.L.flowamok_grid_upload(ctx.h, g.h, *[band_ptr(up[k]) for k in fields_up], None, fa.PCG_INC))
             else:
-                band.upload_cars(*[band_ptr(up[k]) for k in fields_up])
+                band.upload_cars(*[band_ptr(up[k]) for k in fields_up], None)
+            g.rng_scatter(ci, cs)
             leaks = run_ticks(args.steps, leaks=True)
             inc = C.c_uint64()
-            ctx.check(ctx.L.flowamok_grid_download(ctx.h, g.h, None, None, *[band_ptr(dn[k]) for k in fields_dn], C.byref(inc)))
+            ctx.check(ctx.L.flowamok_grid_download(ctx.h, g.h, None, None, *[band_ptr(dn[k]) for k in fields_dn], None, C.byref(inc)))
+            g.rng_corners(ci, cs)
             barrier()
             dt = maxr(time.perf_counter() - t0)
             if dist is not None:
@@ -349,10 +354,12 @@ def main():
             e2e = {"value": cells * args.steps / dt / 1e9, "unit": "GCUPS",
                    "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                    "seconds": dt, "leaks": int(leaks), "host_memory": "pinned" if pinned else "pageable",
-                   "what": ("flowamok_grid_upload (host record-of-arrays)" if world == 1 else
+                   "rng_corner_cells": int(len(ci)),
+                   "what": ("flowamok_grid_upload (host record-of-arrays: roads, headings, colours, preferences)" if world == 1 else
                             "flowamok_grid_upload_cars (car state of every band's rows)") +
-                           " + steps ticks through the C ABI + leak count + flowamok_grid_download, wall clock, max over ranks"}
-            del up, dn
+                           " + flowamok_grid_rng_scatter (states of the corner cells, the only ones that can draw) + steps ticks through "
+                           "the C ABI + leak count + flowamok_grid_download + flowamok_grid_rng_corners, wall clock, max over ranks"}
+            del up, dn, ci, cs
 
     peak, peak_src = measured_peak()
     per_gpu_gcups = value / world

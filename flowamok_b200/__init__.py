@@ -165,6 +165,19 @@ class Grid:
         out["rng_inc"] = inc.value
         return out
 
+    def rng_corners(self, idx=None, state=None):
+        """(flat index, pcg32 state) of the cells with a road on both axes -- the only ones whose state can change.
+        idx / state: preallocated (e.g. pinned) arrays to fill; otherwise fresh ones are returned."""
+        n = C.c_int64()
+        if idx is None:
+            self.ctx.check(self.L.flowamok_grid_rng_corners(self.ctx.h, self.h, 0, None, None, C.byref(n)))
+            idx, state = np.zeros(n.value, np.int64), np.zeros(n.value, np.uint64)
+        self.ctx.check(self.L.flowamok_grid_rng_corners(self.ctx.h, self.h, len(idx), _ptr(idx), _ptr(state), C.byref(n)))
+        return idx[:n.value], state[:n.value]
+
+    def rng_scatter(self, idx, state):
+        self.ctx.check(self.L.flowamok_grid_rng_scatter(self.ctx.h, self.h, len(idx), _ptr(idx), _ptr(state)))
+
     # --- chooser / cycles ---
     def set_chooser(self, mode, tape=None):
         t = None if tape is None else np.ascontiguousarray(tape, np.uint8)

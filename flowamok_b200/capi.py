@@ -43,10 +43,13 @@ def lib():
         "flowamok_context_device": (C.c_int, [P]),
         "flowamok_grid_new": (C.c_int, [P, C.POINTER(P), I64, I64]),
         "flowamok_grid_free": (C.c_int, [P, P]),
+        "flowamok_grid_recycle": (C.c_int, [P, P]),
         "flowamok_grid_shape": (C.c_int, [P, P, C.POINTER(I64), C.POINTER(I64)]),
         "flowamok_create_grid": (C.c_int, [P, P, I32, C.POINTER(U64), C.POINTER(U64)]),
         "flowamok_grid_upload": (C.c_int, [P, P, P, P, P, P, P, P, P, U64]),
         "flowamok_grid_download": (C.c_int, [P, P, P, P, P, P, P, P, P, C.POINTER(U64)]),
+        "flowamok_grid_rng_corners": (C.c_int, [P, P, I64, P, P, C.POINTER(I64)]),
+        "flowamok_grid_rng_scatter": (C.c_int, [P, P, I64, P, P]),
         "flowamok_add_line_vertical": (C.c_int, [P, P, I64, I64, I64, I8]),
         "flowamok_add_line_horizontal": (C.c_int, [P, P, I64, I64, I64, I8]),
         "flowamok_add_cell": (C.c_int, [P, P, I64, I64, U32, I8, I8]),
@@ -94,6 +97,9 @@ def lib():
         "flowamok_band_ring_words": (C.c_int, [P, P, C.POINTER(I64)]),
         "flowamok_band_ring_verdicts": (C.c_int, [P, P, P]),
         "flowamok_band_rings_apply": (C.c_int, [P, P, P]),
+        "flowamok_scenario_init": (C.c_int, [P, P, C.c_int]),
+        "flowamok_explorer_step": (C.c_int, [P, P, C.c_int, C.c_int, I64, C.POINTER(I64), C.POINTER(U64), C.POINTER(U64), C.POINTER(I64)]),
+        "flowamok_designer_step": (C.c_int, [P, P, I64, C.POINTER(I64), C.POINTER(U64), C.POINTER(U64), C.POINTER(I32)]),
         "flowamok_version": (C.c_char_p, []),
         # Futhark-generated-library surface (include/flowamok_futhark.h)
         "futhark_context_config_new": (P, []),

@@ -67,6 +67,7 @@ struct flowamok_context {
   size_t smem_optin = 0;   // largest dynamic shared memory a CTA may ask for
   std::string err;
   std::vector<struct flowamok_grid *> grids;   // live grids: flowamok_context_sync reads their watchdog flags
+  std::vector<struct flowamok_grid *> pool;    // recycled grids (flowamok_grid_recycle): flowamok_grid_clone reuses their planes
 };
 
 struct flowamok_grid {
@@ -128,6 +129,8 @@ struct flowamok_grid {
   void *ipc_opened[BAND_MAXW] = {};
   unsigned int s_seq = 0;           // state messages sent so far (= ticks stepped over P2P)
   int p2p_blocks = 0;               // cooperative grid of k_u_iter<true>
+  int8_t *stage = nullptr;          // staging buffer of upload / download (grows, never shrinks; no cudaMalloc per call)
+  size_t stage_bytes = 0;
   const char *poisoned = nullptr;   // a device-side watchdog tripped: the planes are not trustworthy any more
   char poison_text[160];
 };
@@ -147,6 +150,23 @@ static int fail(flowamok_context *ctx, const char *fmt, ...) {
     if (e_ != cudaSuccess) return fail(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
+// scratch device memory / events of one call: released on every return path
+struct DevBuf {
+  void *p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  template <class T> T *as() const { return (T *)p; }
+};
+struct EventSet {
+  std::vector<cudaEvent_t> ev;
+  ~EventSet() { for (auto e : ev) if (e) cudaEventDestroy(e); }
+  cudaError_t create(size_t n) {
+    ev.assign(n, nullptr);
+    for (auto &e : ev) { cudaError_t r = cudaEventCreate(&e); if (r != cudaSuccess) return r; }
+    return cudaSuccess;
+  }
+};
+
 static inline unsigned int nblk(long long n, int b) { return (unsigned int)((n + b - 1) / b); }
 // rows per k_u_local strip: long strips amortise the 2K+3 pipeline-fill rows every strip pays, but there must be
 // enough strips (warps) to occupy every SM.  FLOWAMOK_STRIP_ROWS overrides (tuning).
@@ -160,6 +180,7 @@ static int strip_rows(const flowamok_context *ctx, int owned_rows, int pitch) {
 }
 struct flowamok_grid;
 static int sync_color_buffers(flowamok_context *ctx, flowamok_grid *g);
+static int ensure_stage(flowamok_context *ctx, flowamok_grid *g, size_t bytes);
 extern "C" { static int check_device_errors(flowamok_context *ctx, flowamok_grid *g); }
 
 // FLOWAMOK_DEBUG_SYNC=1: synchronise after every kernel so that a fault is reported at its launch site
@@ -238,6 +259,7 @@ int flowamok_context_new(flowamok_context **out, int device, void *stream) {
 
 int flowamok_context_free(flowamok_context *ctx) {
   if (!ctx) return 0;
+  while (!ctx->pool.empty()) { flowamok_grid *g = ctx->pool.back(); ctx->pool.pop_back(); flowamok_grid_free(ctx, g); }
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   if (ctx->device >= 0) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
@@ -268,8 +290,25 @@ int flowamok_context_device(flowamok_context *ctx) { return ctx ? ctx->device : 
 // ---------------------------------------------------------------------------------------------
 }  // extern "C"
 
+static int grid_alloc(flowamok_context *ctx, flowamok_grid **out, int64_t gh_global, int64_t gw, int64_t row_begin, int64_t row_end, int halo);
+// a grid that could not be allocated completely is freed again: *out is either a whole grid or null
 static int grid_new_impl(flowamok_context *ctx, flowamok_grid **out, int64_t gh_global, int64_t gw, int64_t row_begin,
                          int64_t row_end, int halo) {
+  *out = nullptr;
+  flowamok_grid *g = nullptr;
+  if (grid_alloc(ctx, &g, gh_global, gw, row_begin, row_end, halo)) {
+    if (g) {
+      std::string keep = ctx->err;
+      flowamok_grid_free(ctx, g);
+      ctx->err = keep;
+    }
+    return 1;
+  }
+  *out = g;
+  return 0;
+}
+static int grid_alloc(flowamok_context *ctx, flowamok_grid **out, int64_t gh_global, int64_t gw, int64_t row_begin,
+                      int64_t row_end, int halo) {
   if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
   if (gh_global < 1 || gw < 1 || gh_global > (1 << 20) || gw > (1 << 20)) return fail(ctx, "grid shape out of range");
   if (row_begin < 0 || row_end > gh_global || row_end <= row_begin) return fail(ctx, "bad row band");
@@ -342,6 +381,16 @@ static int grid_new_impl(flowamok_context *ctx, flowamok_grid **out, int64_t gh_
   return 0;
 }
 
+static int ensure_stage(flowamok_context *ctx, flowamok_grid *g, size_t bytes) {
+  if (bytes <= g->stage_bytes) return 0;
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaFree(g->stage));
+  g->stage = nullptr; g->stage_bytes = 0;
+  CU(cudaMalloc(&g->stage, bytes));
+  g->stage_bytes = bytes;
+  return 0;
+}
+
 // After the colour plane of the current buffer was (re)written from outside, make the other buffer identical and
 // forget the dirty sectors: the lazy double buffer's invariant (k_move only rewrites the 32-byte sectors that received a
 // car in this tick or the previous one).
@@ -378,9 +427,21 @@ int flowamok_grid_free(flowamok_context *ctx, flowamok_grid *g) {
   for (int r = 0; r < BAND_MAXW; r++) if (g->ipc_opened[r]) cudaIpcCloseMemHandle(g->ipc_opened[r]);
   cudaFree(g->mailbox); cudaFree(g->band_dev); cudaFree(g->ring_sid); cudaFree(g->ring_partial); cudaFree(g->ring_pass);
   cudaFree(g->table); cudaFree(g->qlist[0]); cudaFree(g->qlist[1]); cudaFree(g->ustate); cudaFree(g->mymx_B); cudaFree(g->chg_list); cudaFree(g->fix_claim);
-  cudaFree(g->ring_words); cudaFree(g->ring_off); cudaFree(g->leak_plane);
+  cudaFree(g->ring_words); cudaFree(g->ring_off); cudaFree(g->leak_plane); cudaFree(g->stage);
   cudaFreeHost(g->h_diag);
   delete g;
+  return 0;
+}
+
+/* Like flowamok_grid_free, but the planes are kept for the next flowamok_grid_clone of a grid of the same shape (animation.fut:23
+ * copies the grid every frame: the generated-library surface would otherwise allocate and clear 19 bytes per cell per frame). */
+int flowamok_grid_recycle(flowamok_context *ctx, flowamok_grid *g) {
+  if (!g) return 0;
+  if (!ctx || ctx->device < 0 || g->poisoned || g->mailbox || ctx->pool.size() >= 2) return flowamok_grid_free(ctx, g);
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->grids.erase(std::remove(ctx->grids.begin(), ctx->grids.end(), g), ctx->grids.end());
+  ctx->pool.push_back(g);
   return 0;
 }
 
@@ -427,8 +488,8 @@ int flowamok_grid_upload(flowamok_context *ctx, flowamok_grid *g, const int8_t *
   // host arrays are [gh_global][gw]; this device takes the rows its planes hold (band + halo rows)
   const int lo = std::max(0, g->row0), hi = std::min(g->gh_global, g->row0 + g->gh);   // global rows present
   const size_t nrow = (size_t)(hi - lo), n = nrow * g->gw;
-  int8_t *tmp = nullptr;
-  CU(cudaMalloc(&tmp, n * 5));
+  if (ensure_stage(ctx, g, n * 5)) return 1;
+  int8_t *tmp = g->stage;
   const void *src[5] = {uy, ux, dy, dx, pref};
   int8_t *dptr[5];
   for (int k = 0; k < 5; k++) {
@@ -443,7 +504,7 @@ int flowamok_grid_upload(flowamok_context *ctx, flowamok_grid *g, const int8_t *
   size_t cp = (size_t)g->pitch * 32;
   const int l0 = lo - g->row0;   // local row of global row lo
   CU(cudaMemsetAsync(g->color[g->cur], color ? 0 : 0xFF, g->ncells_p * 4, st));
-  CU(cudaMemsetAsync(g->rng, 0, g->ncells_p * 8, st));
+  if (rng_state) CU(cudaMemsetAsync(g->rng, 0, g->ncells_p * 8, st));   // NULL: the resident states stay (see flowamok_grid_rng_*)
   if (color)
     CU(cudaMemcpy2DAsync(g->color[g->cur] + (size_t)l0 * cp, cp * 4, color + (size_t)lo * g->gw, (size_t)g->gw * 4,
                          (size_t)g->gw * 4, nrow, cudaMemcpyHostToDevice, st));
@@ -453,7 +514,6 @@ int flowamok_grid_upload(flowamok_context *ctx, flowamok_grid *g, const int8_t *
   g->rng_inc = rng_inc;
   if (sync_color_buffers(ctx, g)) return 1;
   CU(cudaStreamSynchronize(st));
-  CU(cudaFree(tmp));
   return 0;
 }
 
@@ -470,7 +530,8 @@ int flowamok_grid_download(flowamok_context *ctx, const flowamok_grid *g, int8_t
   for (int k = 0; k < 5; k++) any |= dst[k] != nullptr;
   int8_t *tmp = nullptr;
   if (any) {
-    CU(cudaMalloc(&tmp, n * 5));
+    if (ensure_stage(ctx, const_cast<flowamok_grid *>(g), n * 5)) return 1;
+    tmp = g->stage;
     k_unpack<<<nblk((long long)n, 256), 256, 0, st>>>(g->own0, g->own1, g->gw, g->pitch, g->road, g->head[g->cur], g->pref[g->cur],
                                                       uy ? tmp : nullptr, ux ? tmp + n : nullptr, dy ? tmp + 2 * n : nullptr,
                                                       dx ? tmp + 3 * n : nullptr, pref ? (uint8_t *)(tmp + 4 * n) : nullptr);
@@ -487,7 +548,6 @@ int flowamok_grid_download(flowamok_context *ctx, const flowamok_grid *g, int8_t
                          (size_t)g->gw * 8, owned, cudaMemcpyDeviceToHost, st));
   if (rng_inc) *rng_inc = g->rng_inc;
   CU(cudaStreamSynchronize(st));
-  if (tmp) CU(cudaFree(tmp));
   return check_device_errors(ctx, const_cast<flowamok_grid *>(g));   // a synchronisation point: watchdog flags are fatal
 }
 
@@ -932,8 +992,9 @@ int flowamok_step_profile(flowamok_context *ctx, flowamok_grid *g, int perfect, 
   if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
   if (!g || !ms || n_ticks < 1 || n_ticks > 4096) return fail(ctx, "bad profile arguments");
   CU(cudaSetDevice(ctx->device));
-  std::vector<cudaEvent_t> ev((size_t)n_ticks * 5);
-  for (auto &e : ev) CU(cudaEventCreate(&e));
+  EventSet es;
+  CU(es.create((size_t)n_ticks * 5));
+  std::vector<cudaEvent_t> &ev = es.ev;
   for (int64_t t = 0; t < n_ticks; t++)
     if (enqueue_tick(ctx, g, perfect != 0, nullptr, &ev[(size_t)t * 5])) return 1;
   CU(cudaStreamSynchronize(ctx->stream));
@@ -944,8 +1005,7 @@ int flowamok_step_profile(flowamok_context *ctx, flowamok_grid *g, int perfect, 
       CU(cudaEventElapsedTime(&f, ev[(size_t)t * 5 + k], ev[(size_t)t * 5 + k + 1]));
       ms[k] += f;
     }
-  for (auto &e : ev) cudaEventDestroy(e);
-  return 0;
+  return check_device_errors(ctx, g);
 }
 
 /* The production tick (speculative move, three streams) on a time line, summed over n_ticks <= 1024, in ms:
@@ -955,8 +1015,9 @@ int flowamok_step_timeline(flowamok_context *ctx, flowamok_grid *g, int perfect,
   if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
   if (!g || !ms5 || n_ticks < 1 || n_ticks > 1024 || !ctx->split) return fail(ctx, "bad timeline arguments");
   CU(cudaSetDevice(ctx->device));
-  std::vector<cudaEvent_t> ev((size_t)n_ticks * 5);
-  for (auto &e : ev) CU(cudaEventCreate(&e));
+  EventSet es;
+  CU(es.create((size_t)n_ticks * 5));
+  std::vector<cudaEvent_t> &ev = es.ev;
   int rc = 0;
   for (int64_t t = 0; t < n_ticks && !rc; t++) rc = enqueue_tick(ctx, g, perfect != 0, nullptr, nullptr, &ev[(size_t)t * 5]);
   cudaError_t se = cudaStreamSynchronize(ctx->stream);
@@ -969,7 +1030,6 @@ int flowamok_step_timeline(flowamok_context *ctx, flowamok_grid *g, int perfect,
       cudaEventElapsedTime(&d1, e[2], e[4]); cudaEventElapsedTime(&d2, e[3], e[4]); cudaEventElapsedTime(&tot, e[0], e[4]);
       ms5[0] += a; ms5[1] += b; ms5[2] += c; ms5[3] += d1 < d2 ? d1 : d2; ms5[4] += tot;
     }
-  for (auto &e : ev) cudaEventDestroy(e);
   if (se != cudaSuccess) return fail(ctx, "timeline: %s", cudaGetErrorString(se));
   return rc ? 1 : check_device_errors(ctx, g);
 }
@@ -982,24 +1042,24 @@ int flowamok_step_leaks(flowamok_context *ctx, flowamok_grid *g, int perfect, in
   if (!g->leak_plane) CU(cudaMalloc(&g->leak_plane, g->nwords * 4));
   int old = g->cur;
   if (enqueue_tick(ctx, g, perfect != 0, g->leak_plane)) return 1;
-  unsigned int *counts = nullptr, *offs = nullptr;
-  CU(cudaMalloc(&counts, (g->nwords + 1) * 4));
-  CU(cudaMalloc(&offs, (g->nwords + 1) * 4));
+  DevBuf cbuf, obuf, tbuf, dbuf;
+  CU(cbuf.alloc((g->nwords + 1) * 4));
+  CU(obuf.alloc((g->nwords + 1) * 4));
+  unsigned int *counts = cbuf.as<unsigned int>(), *offs = obuf.as<unsigned int>();
   CU(cudaMemsetAsync(counts, 0, (g->nwords + 1) * 4, st));
   k_leak_counts<<<nblk((long long)g->nwords, 256), 256, 0, st>>>((long long)g->nwords, g->leak_plane, counts);
   CU(cudaGetLastError());
-  void *tmp = nullptr;
   size_t tmpb = 0;
   CU(cub::DeviceScan::ExclusiveSum(nullptr, tmpb, counts, offs, (int)(g->nwords + 1), st));
-  CU(cudaMalloc(&tmp, tmpb));
-  CU(cub::DeviceScan::ExclusiveSum(tmp, tmpb, counts, offs, (int)(g->nwords + 1), st));
+  CU(tbuf.alloc(tmpb));
+  CU(cub::DeviceScan::ExclusiveSum(tbuf.p, tmpb, counts, offs, (int)(g->nwords + 1), st));
   unsigned int total = 0;
   CU(cudaMemcpyAsync(&total, offs + g->nwords, 4, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   long long emit = std::min<long long>(total, cap);
   if (emit > 0 && leaks) {
-    long long *dout = nullptr;
-    CU(cudaMalloc(&dout, (size_t)emit * 64));
+    CU(dbuf.alloc((size_t)emit * 64));
+    long long *dout = dbuf.as<long long>();
     // the tuple copies the cell as move_cell saw it (steppers.fut:122): heading/colour of the old state,
     // next_preference_flow_x already updated by the fixpoint (written by U into the new buffer)
     k_leak_emit<<<nblk((long long)g->nwords, 256), 256, 0, st>>>(g->gh, g->gw, g->pitch, g->row0, g->leak_plane, offs, g->head[old],
@@ -1007,11 +1067,9 @@ int flowamok_step_leaks(flowamok_context *ctx, flowamok_grid *g, int perfect, in
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(leaks, dout, (size_t)emit * 64, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    CU(cudaFree(dout));
   }
   if (n_leaks) *n_leaks = total;
-  CU(cudaFree(tmp)); CU(cudaFree(counts)); CU(cudaFree(offs));
-  return 0;
+  return check_device_errors(ctx, g);
 }
 
 int flowamok_render(flowamok_context *ctx, const flowamok_grid *g, int64_t scale, uint32_t *pixels) {
@@ -1020,14 +1078,14 @@ int flowamok_render(flowamok_context *ctx, const flowamok_grid *g, int64_t scale
   if (g->halo != 0) return fail(ctx, "render needs the whole grid (not available on a row band)");
   CU(cudaSetDevice(ctx->device));
   long long n = (long long)g->gh * scale * g->gw * scale;
-  u32 *d = nullptr;
-  CU(cudaMalloc(&d, (size_t)n * 4));
+  DevBuf buf;
+  CU(buf.alloc((size_t)n * 4));
+  u32 *d = buf.as<u32>();
   k_render<<<nblk(n, 256), 256, 0, ctx->stream>>>(g->gh, g->gw, g->pitch, scale, g->road, g->head[g->cur], g->color[g->cur], d);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(pixels, d, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
-  CU(cudaFree(d));
-  return 0;
+  return check_device_errors(ctx, const_cast<flowamok_grid *>(g));
 }
 
 int flowamok_render_device(flowamok_context *ctx, const flowamok_grid *g, int64_t scale, void **pixels_dev) {
@@ -1035,11 +1093,12 @@ int flowamok_render_device(flowamok_context *ctx, const flowamok_grid *g, int64_
   if (!g || scale < 1 || !pixels_dev) return fail(ctx, "bad render arguments");
   CU(cudaSetDevice(ctx->device));
   long long n = (long long)g->gh * scale * g->gw * scale;
-  u32 *d = nullptr;
-  CU(cudaMalloc(&d, (size_t)n * 4));
-  k_render<<<nblk(n, 256), 256, 0, ctx->stream>>>(g->gh, g->gw, g->pitch, scale, g->road, g->head[g->cur], g->color[g->cur], d);
+  DevBuf buf;
+  CU(buf.alloc((size_t)n * 4));
+  k_render<<<nblk(n, 256), 256, 0, ctx->stream>>>(g->gh, g->gw, g->pitch, scale, g->road, g->head[g->cur], g->color[g->cur], buf.as<u32>());
   CU(cudaGetLastError());
-  *pixels_dev = d;
+  *pixels_dev = buf.p;
+  buf.p = nullptr;   // the caller owns the pixels now
   return 0;
 }
 
@@ -1047,7 +1106,20 @@ int flowamok_grid_clone(flowamok_context *ctx, const flowamok_grid *src, flowamo
   if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
   if (!src || !out) return fail(ctx, "null grid");
   flowamok_grid *g = nullptr;
-  if (grid_new_impl(ctx, &g, src->gh_global, src->gw, src->row0 + src->own0, src->row0 + src->own1, src->halo)) return 1;
+  for (size_t i = 0; i < ctx->pool.size() && !g; i++) {   // a recycled grid of the same shape: no allocation, no memsets
+    flowamok_grid *q = ctx->pool[i];
+    if (q->gh_global == src->gh_global && q->gw == src->gw && q->row0 == src->row0 && q->own0 == src->own0 && q->own1 == src->own1 &&
+        q->halo == src->halo) {
+      g = q;
+      ctx->pool.erase(ctx->pool.begin() + (long)i);
+      ctx->grids.push_back(g);
+      cudaFree(g->ring_words); cudaFree(g->ring_off); cudaFree(g->ring_sid); cudaFree(g->ring_partial); cudaFree(g->ring_pass);
+      g->ring_words = nullptr; g->ring_off = nullptr; g->ring_sid = nullptr; g->ring_partial = nullptr; g->ring_pass = nullptr;
+      g->n_rings = g->n_ring_cells = g->n_ring_words = 0; g->ring_stride = 0; g->n_straddle = 0; g->sbit_words = 0;
+      g->h_off.clear(); g->h_y.clear(); g->h_x.clear(); g->h_cy.clear(); g->h_cx.clear();
+    }
+  }
+  if (!g && grid_new_impl(ctx, &g, src->gh_global, src->gw, src->row0 + src->own0, src->row0 + src->own1, src->halo)) return 1;
   cudaStream_t st = ctx->stream;
   CU(cudaMemcpyAsync(g->road, src->road, src->nwords * sizeof(U4), cudaMemcpyDeviceToDevice, st));
   CU(cudaMemcpyAsync(g->head[0], src->head[src->cur], src->nwords * sizeof(U4), cudaMemcpyDeviceToDevice, st));
@@ -1081,7 +1153,7 @@ int flowamok_grid_clone(flowamok_context *ctx, const flowamok_grid *src, flowamo
 
 // ---------------------------------------------------------------------------------------------
 // Row bands.  side 0 = towards smaller rows, 1 = towards larger rows.
-//   state message: 2 heading rows + 2 preference rows + 1 colour row (what k_u_init / k_move read across the cut)
+//   state message: 2 heading rows + 2 preference rows + 1 colour row (what k_u_local / k_move read across the cut)
 //   u message    : 1 row of calc + 1 row of my|mx (what the fixpoint reads across the cut)
 // ---------------------------------------------------------------------------------------------
 int flowamok_band_msg_bytes(flowamok_context *ctx, const flowamok_grid *g, int64_t *state_bytes, int64_t *u_bytes) {
@@ -1114,7 +1186,7 @@ int flowamok_band_unpack_state(flowamok_context *ctx, flowamok_grid *g, int side
   CU(cudaSetDevice(ctx->device));
   return band_state(ctx, g, side == 0 ? (void *)dev_buf : nullptr, side == 1 ? (void *)dev_buf : nullptr, 0);
 }
-/* u_init: k_u_init only (statics, block-local sweeps, ghost rows seeded with this band's view of the neighbour's
+/* u_init: k_u_local only (statics, local levels, ghost rows seeded with this band's view of the neighbour's
  * boundary row); u_iter: the frontier iterations.  u_begin = both.  Swapping the boundary rows BETWEEN the two lets
  * the frontier run against the neighbour's post-sweep rows, so the first convergence check usually passes. */
 int flowamok_band_u_init(flowamok_context *ctx, flowamok_grid *g) {
@@ -1422,8 +1494,9 @@ int flowamok_band_step_profile(flowamok_context *ctx, flowamok_grid *g, int perf
   if (band_check(ctx, g, 0)) return 1;
   if (!g->p2p || !ms5 || n_ticks < 1 || n_ticks > 1024) return fail(ctx, "bad band profile arguments (P2P transport only)");
   CU(cudaSetDevice(ctx->device));
-  std::vector<cudaEvent_t> ev((size_t)n_ticks * 6);
-  for (auto &e : ev) CU(cudaEventCreate(&e));
+  EventSet es;
+  CU(es.create((size_t)n_ticks * 6));
+  std::vector<cudaEvent_t> &ev = es.ev;
   int rc = band_step_p2p(ctx, g, perfect != 0, n_ticks, nullptr, ev.data());
   cudaError_t se = cudaStreamSynchronize(ctx->stream);
   for (int k = 0; k < 5; k++) ms5[k] = 0.0;
@@ -1434,7 +1507,6 @@ int flowamok_band_step_profile(flowamok_context *ctx, flowamok_grid *g, int perf
         cudaEventElapsedTime(&f, ev[(size_t)t * 6 + k], ev[(size_t)t * 6 + k + 1]);
         ms5[k] += f;
       }
-  for (auto &e : ev) cudaEventDestroy(e);
   if (se != cudaSuccess) return fail(ctx, "band profile: %s", cudaGetErrorString(se));
   return rc ? 1 : check_device_errors(ctx, g);
 }
@@ -1522,13 +1594,13 @@ int flowamok_band_step(flowamok_context *ctx, flowamok_grid *g, int perfect, int
 int flowamok_grid_upload_cars(flowamok_context *ctx, flowamok_grid *g, const int8_t *dy, const int8_t *dx, const uint32_t *color,
                               const uint8_t *pref, const uint64_t *rng_state) {
   if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
-  if (!g || !dy || !dx || !color || !pref || !rng_state) return fail(ctx, "upload_cars needs every field");
+  if (!g || !dy || !dx || !color || !pref) return fail(ctx, "upload_cars needs heading, colour and preference");
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const int lo = g->row0 + g->own0, owned = g->own1 - g->own0;
   const size_t n = (size_t)owned * g->gw, cp = (size_t)g->pitch * 32;
-  int8_t *tmp = nullptr;
-  CU(cudaMalloc(&tmp, n * 3));
+  if (ensure_stage(ctx, g, n * 3)) return 1;
+  int8_t *tmp = g->stage;
   const void *src[3] = {dy, dx, pref};
   for (int k = 0; k < 3; k++) CU(cudaMemcpyAsync(tmp + n * k, (const int8_t *)src[k] + (size_t)lo * g->gw, n, cudaMemcpyHostToDevice, st));
   k_pack<<<nblk((long long)g->nwords * 32, 256), 256, 0, st>>>(g->gh, g->gw, g->pitch, -g->own0, owned, nullptr, nullptr, tmp, tmp + n,
@@ -1536,11 +1608,63 @@ int flowamok_grid_upload_cars(flowamok_context *ctx, flowamok_grid *g, const int
   CU(cudaGetLastError());
   CU(cudaMemcpy2DAsync(g->color[g->cur] + (size_t)g->own0 * cp, cp * 4, color + (size_t)lo * g->gw, (size_t)g->gw * 4,
                        (size_t)g->gw * 4, owned, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpy2DAsync(g->rng + (size_t)g->own0 * cp, cp * 8, rng_state + (size_t)lo * g->gw, (size_t)g->gw * 8,
-                       (size_t)g->gw * 8, owned, cudaMemcpyHostToDevice, st));
+  if (rng_state)   // NULL: the resident states stay
+    CU(cudaMemcpy2DAsync(g->rng + (size_t)g->own0 * cp, cp * 8, rng_state + (size_t)lo * g->gw, (size_t)g->gw * 8,
+                         (size_t)g->gw * 8, owned, cudaMemcpyHostToDevice, st));
   if (sync_color_buffers(ctx, g)) return 1;
   CU(cudaStreamSynchronize(st));
-  CU(cudaFree(tmp));
+  return 0;
+}
+
+/* The cells whose RNG state can ever change are the ones with a road on both axes (k_corner_counts).  corners: (global
+ * flat index, state) of every such OWNED cell, in row-major order, up to cap; *n receives their number (call with cap = 0
+ * to size the arrays).  rng_scatter: write states back (cells outside this band's rows are skipped).  Host arrays. */
+int flowamok_grid_rng_corners(flowamok_context *ctx, flowamok_grid *g, int64_t cap, int64_t *idx, uint64_t *state, int64_t *n) {
+  if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
+  if (!g || !n) return fail(ctx, "null argument");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const long long nw = (long long)(g->own1 - g->own0) * g->pitch;
+  DevBuf counts, offs, tmp, dout;
+  CU(counts.alloc((size_t)(nw + 1) * 4)); CU(offs.alloc((size_t)(nw + 1) * 4));
+  CU(cudaMemsetAsync(counts.p, 0, (size_t)(nw + 1) * 4, st));
+  k_corner_counts<<<nblk(nw, 256), 256, 0, st>>>(g->own0, g->own1, g->pitch, g->road, counts.as<unsigned int>());
+  CU(cudaGetLastError());
+  size_t tmpb = 0;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, tmpb, counts.as<unsigned int>(), offs.as<unsigned int>(), (int)(nw + 1), st));
+  CU(tmp.alloc(tmpb));
+  CU(cub::DeviceScan::ExclusiveSum(tmp.p, tmpb, counts.as<unsigned int>(), offs.as<unsigned int>(), (int)(nw + 1), st));
+  unsigned int total = 0;
+  CU(cudaMemcpyAsync(&total, offs.as<unsigned int>() + nw, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  *n = total;
+  const long long emit = std::min<long long>(total, cap);
+  if (emit > 0 && idx && state) {
+    CU(dout.alloc((size_t)emit * 16));
+    long long *di = dout.as<long long>();
+    u64 *ds = (u64 *)(di + emit);
+    k_corner_emit<<<nblk(nw, 256), 256, 0, st>>>(g->own0, g->own1, g->gw, g->pitch, g->row0, g->road, offs.as<unsigned int>(), g->rng, emit, di, ds);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(idx, di, (size_t)emit * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(state, ds, (size_t)emit * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return check_device_errors(ctx, g);
+}
+int flowamok_grid_rng_scatter(flowamok_context *ctx, flowamok_grid *g, int64_t n, const int64_t *idx, const uint64_t *state) {
+  if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
+  if (!g || n < 0 || (n > 0 && (!idx || !state))) return fail(ctx, "bad rng_scatter arguments");
+  if (n == 0) return 0;
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  if (ensure_stage(ctx, g, (size_t)n * 16)) return 1;
+  long long *di = (long long *)g->stage;
+  u64 *ds = (u64 *)(di + n);
+  CU(cudaMemcpyAsync(di, idx, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ds, state, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  k_rng_scatter<<<nblk(n, 256), 256, 0, st>>>(n, di, ds, g->gw, g->pitch, g->row0, g->gh, g->rng);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(st));
   return 0;
 }
 
@@ -1649,8 +1773,9 @@ int flowamok_generate_synthetic(flowamok_context *ctx, flowamok_grid *g, uint64_
         if (!dup) cutrows.by[cutrows.n++] = by;
       }
     }
-    unsigned int *cnt = nullptr;
-    CU(cudaMalloc(&cnt, 8));
+    DevBuf cntbuf;
+    CU(cntbuf.alloc(8));
+    unsigned int *cnt = cntbuf.as<unsigned int>();
     CU(cudaMemsetAsync(cnt, 0, 8, st));
     const long long my_blocks = ((long long)(hi - lo) / 16 + 3) * nbx;   // ring blocks that can intersect this band
     CU(cudaMalloc(&g->ring_words, (size_t)my_blocks * SYNTH_RING_WORDS * sizeof(RingWord)));
@@ -1662,7 +1787,6 @@ int flowamok_generate_synthetic(flowamok_context *ctx, flowamok_grid *g, uint64_
     unsigned int n[2] = {0, 0};
     CU(cudaMemcpyAsync(n, cnt, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    CU(cudaFree(cnt));
     g->n_rings = n[0]; g->n_ring_cells = (long long)n[0] * 48; g->n_ring_words = (long long)n[0] * SYNTH_RING_WORDS;
     g->ring_stride = SYNTH_RING_WORDS;
     if (cutrows.n > 0) {

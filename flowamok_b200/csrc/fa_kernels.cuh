@@ -1,16 +1,21 @@
 // flowamok_b200 -- CUDA kernels (sm_100a) of the per-tick grid update.
 //
-// Kernel list (one tick = k_u_local, k_u_iter, [k_rings], k_move):
-//   k_u_local : streaming, one warp per strip of 30 plane words x RS rows (fa_stream.h, UStrip): statics
-//               and the first two Jacobi levels of update_can_be_moved_to_from (steppers.fut:9-56) in
-//               registers, worklist entries for the words that still hold a waiting car, frontier.
-//   k_u_iter  : cooperative persistent kernel; relaxes the frontier under a grid-wide barrier and
-//               device-side list lengths until the global fixpoint (steppers.fut:147-164) -- no
-//               host round trip per iteration, and each iteration touches only unresolved words.
-//   k_rings   : resolve_cycles (steppers.fut:189-224) on the sparse ring list, one thread per ring.
-//   k_move    : streaming like k_u_local (MStrip): move_cell + reset_cells (steppers.fut:58-145): new car
-//               planes, colour payload through a lazy double buffer (only 32-byte sectors that hold a car or
-//               an arrival are rewritten), per-cell pcg32 draws at forks, leak count.
+// One tick = k_u_local, [k_rings], then -- side by side -- k_u_iter on a high-priority stream and k_move, then k_move_fix:
+//   k_u_local  : streaming, one warp per strip of 30 plane words x RS rows (fa_stream.h, UStrip): statics and the first
+//                FA_U_LEVELS (3) Jacobi levels of update_can_be_moved_to_from (steppers.fut:9-56) in registers, worklist
+//                entries for the words that still hold an unresolved waiting car, frontier.
+//   k_rings    : resolve_cycles (steppers.fut:189-224) on the sparse ring list.  It does not depend on the fixpoint
+//                (ring_word_ok), so it runs before it and its grants are part of what k_move reads.
+//   k_u_iter   : cooperative persistent kernel, one small CTA per SM; relaxes the frontier under a grid-wide barrier and
+//                device-side list lengths until the global fixpoint (steppers.fut:147-164) -- no host round trip per
+//                iteration, each iteration touches only unresolved words.  Its grants go into a delta plane (mymx_B), so
+//                that k_move can gather from the planes k_u_local published at the same time.  On a row band with mapped
+//                peers (fa_band.cuh) the convergence rounds with the neighbour bands run inside this launch too.
+//   k_move     : streaming like k_u_local (MTile): move_cell + reset_cells (steppers.fut:58-145): new car planes, colour
+//                payload through a lazy double buffer (only the 32-byte sectors that received a car in this tick or the
+//                previous one are rewritten), per-cell pcg32 draws at forks, leak count.
+//   k_move_fix : recomputes the words around every word whose my|mx the fixpoint changed after k_u_local (fa_stream.h,
+//                fix_word); a few thousand words per tick.
 // plus packing / unpacking / generator / render helpers.
 #pragma once
 #include <cuda_runtime.h>
@@ -331,11 +336,13 @@ struct alignas(32) RingWord {
 __device__ __forceinline__ void ring_grant(const GridView &g, const RingWord &w) {
   if (w.gY | w.gX) atomicOr((unsigned long long *)&g.mymx[w.wi], (unsigned long long)w.gY | ((unsigned long long)w.gX << 32));
 }
-// every ring cell of the word is uncalculated and holds a car heading exactly the check direction (:197-200)
+// Every ring cell of the word holds a car heading exactly the check direction (:197-200).  `calculated` is not read: if ALL
+// cells of a ring head along it, each waits for the next (find_cycles steps to pos + check, :247-293), so none of them is ever
+// calculated by the fixpoint -- and if one does not, the ring fails here anyway.  (This is also why ring resolution may run
+// before k_u_iter: see ring_grant.)
 __device__ __forceinline__ bool ring_word_ok(const GridView &g, const RingWord &e) {
   const u32 m = e.mN | e.mS | e.mW | e.mE;
   if (m == 0u) return true;   // padding entry
-  if (g.calc[e.wi] & m) return false;
   const U4 h = g.head_in[e.wi];
   const u32 n = h.x & h.y & ~h.z, s_ = h.x & ~h.y & ~h.z, w = h.z & h.w & ~h.x, ea = h.z & ~h.w & ~h.x;
   return (n & e.mN) == e.mN && (s_ & e.mS) == e.mS && (w & e.mW) == e.mW && (ea & e.mE) == e.mE;
@@ -790,6 +797,39 @@ __global__ void k_digest(int own0, int own1, int gw, int pitch, int row0, const 
     x ^= __shfl_xor_sync(0xFFFFFFFFu, x, d);
   }
   if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], sum); atomicXor(&out[1], x); }
+}
+
+// Sparse view of the per-cell RNG plane.  choose_direction is only ever called for a cell whose road has BOTH axes
+// (steppers.fut:101-103 needs flow_y_ok && flow_x_ok), so only those "corner" cells' states can change: hosts that keep the grid
+// in the reference's layout need not move 8 bytes per cell in and out, only (flat index, state) of the corners.
+__global__ void k_corner_counts(int own0, int own1, int pitch, const U4 *road, unsigned int *counts) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)(own1 - own0) * pitch) return;
+  const U4 r = road[(size_t)own0 * pitch + i];
+  counts[i] = __popc(r.x & r.z);   // pad cells have no road
+}
+__global__ void k_corner_emit(int own0, int own1, int gw, int pitch, int row0, const U4 *road, const unsigned int *offs, const u64 *rng,
+                              long long cap, long long *idx, u64 *state) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)(own1 - own0) * pitch) return;
+  const int y = own0 + (int)(i / pitch), w = (int)(i % pitch);
+  const U4 r = road[(size_t)y * pitch + w];
+  u32 m = r.x & r.z;
+  long long k = offs[i];
+  while (m && k < cap) {
+    const int b = __ffs(m) - 1;
+    m &= m - 1;
+    idx[k] = (long long)(y + row0) * gw + (w * 32 + b);
+    state[k] = rng[((size_t)y * pitch + w) * 32 + b];
+    k++;
+  }
+}
+__global__ void k_rng_scatter(long long n, const long long *idx, const u64 *state, int gw, int pitch, int row0, int gh, u64 *rng) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long y = idx[i] / gw - row0, x = idx[i] % gw;
+  if (y < 0 || y >= gh) return;   // a row this band does not hold
+  rng[(size_t)y * pitch * 32 + x] = state[i];
 }
 
 // leak list compaction helpers (flowamok_step_leaks)

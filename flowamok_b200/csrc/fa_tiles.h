@@ -97,7 +97,7 @@ FA_HD int ffs32(u32 v) {  // index of lowest set bit, v != 0
 // =============================================================================================
 // U phase: least fixpoint of update_can_be_moved_to_from (steppers.fut:9-56, :147-164)
 //
-//   UStrip (fa_stream.h, k_u_local): every word once: statics, terminals, two Jacobi levels, and a worklist entry for
+//   UStrip (fa_stream.h, k_u_local): every word once: statics, terminals, K Jacobi levels, and a worklist entry for
 //                 each word that still holds an unresolved waiting car ("link" cell: occupied, successor in
 //                 bounds and on a road).
 //   u_iter_entry: one monotone relaxation of a worklist entry against the CURRENT global planes

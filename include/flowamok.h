@@ -63,6 +63,13 @@ int flowamok_grid_upload(flowamok_context *ctx, flowamok_grid *g, const int8_t *
 int flowamok_grid_download(flowamok_context *ctx, const flowamok_grid *g, int8_t *uy, int8_t *ux, int8_t *dy,
                            int8_t *dx, uint32_t *color, uint8_t *pref, uint64_t *rng_state, uint64_t *rng_inc);
 
+/* Sparse access to underlying.rng.  choose_direction (flowamok.fut:10-14) is only called for a cell whose road has both axes
+ * (steppers.fut:101-103), so only those cells' states ever change: a host that keeps the grid in the reference's layout can
+ * pass rng_state = NULL to upload / download (the resident states stay) and move (global flat index, state) of the corner
+ * cells instead of 8 bytes per cell.  corners: row-major, up to cap, *n = how many there are (cap = 0 sizes the arrays). */
+int flowamok_grid_rng_corners(flowamok_context *ctx, flowamok_grid *g, int64_t cap, int64_t *idx, uint64_t *state, int64_t *n);
+int flowamok_grid_rng_scatter(flowamok_context *ctx, flowamok_grid *g, int64_t n, const int64_t *idx, const uint64_t *state);
+
 /* point edits between ticks: src/utils.fut:19-25, :27-33, :35-38 */
 int flowamok_add_line_vertical(flowamok_context *ctx, flowamok_grid *g, int64_t y_start, int64_t y_end, int64_t x, int8_t flow);
 int flowamok_add_line_horizontal(flowamok_context *ctx, flowamok_grid *g, int64_t y, int64_t x_start, int64_t x_end, int8_t flow);
@@ -114,6 +121,9 @@ int flowamok_render_device(flowamok_context *ctx, const flowamok_grid *g, int64_
 
 /* `copy s.grid` (animation.fut:23): a fresh grid value with the same cells, cycle_checks and chooser. */
 int flowamok_grid_clone(flowamok_context *ctx, const flowamok_grid *src, flowamok_grid **out);
+
+/* flowamok_grid_free that keeps the planes for the next flowamok_grid_clone of a grid of the same shape (at most two are kept) */
+int flowamok_grid_recycle(flowamok_context *ctx, flowamok_grid *g);
 
 /* diagnostics of the ticks since the last call: ticks, fixpoint iterations, worklist entries relaxed */
 int flowamok_stats(flowamok_context *ctx, flowamok_grid *g, int64_t *ticks, int64_t *passes, int64_t *sweeps);
@@ -190,6 +200,17 @@ int flowamok_band_rings_apply(flowamok_context *ctx, flowamok_grid *g, const voi
  * and halo rows are left alone.  Synchronous. */
 int flowamok_grid_upload_cars(flowamok_context *ctx, flowamok_grid *g, const int8_t *dy, const int8_t *dx, const uint32_t *color,
                               const uint8_t *pref, const uint64_t *rng_state);
+
+/* ---- the frontends' `step s n` loops (explorer/explorer.fut:109-130, designer/designer.fut:59-75) and scenario.init, so that a
+ * lys C main (the lys wrapper itself is generated from diku-dk/lys 0.1.24, not vendored) steps through this library:
+ * explorer_step: n_steps x { stepper_{perfect,quick}.step; scenario.step id grid step_cur rng; find_cycles if asked }; in/out
+ * *step_cur and the explorer's rng (state, inc); out the cell leaks of this call.  designer_step: n_steps x { a car of random
+ * colour at (25, 0) every 10th step; stepper_quick.step }.  The scenario rng arithmetic is cpprandom's (unpinned). */
+int flowamok_scenario_init(flowamok_context *ctx, flowamok_grid *g, int scenario_id);
+int flowamok_explorer_step(flowamok_context *ctx, flowamok_grid *g, int scenario_id, int perfect, int64_t n_steps, int64_t *step_cur,
+                           uint64_t *rng_state, uint64_t *rng_inc, int64_t *n_cell_leaks);
+int flowamok_designer_step(flowamok_context *ctx, flowamok_grid *g, int64_t n_steps, int64_t *n_steps_total, uint64_t *rng_state,
+                           uint64_t *rng_inc, int32_t *n_leaks);
 
 /* library identification */
 const char *flowamok_version(void);

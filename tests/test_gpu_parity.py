@@ -134,6 +134,52 @@ def test_explorer_scenarios_perfect(ctx, sid):
     assert np.array_equal(dx.grid.cycles_dense(), ox.cycles)
 
 
+@pytest.mark.parametrize("sid,perfect", [(1, True), (5, False), (10, True), (11, True), (4, False)])
+def test_explorer_step_c_entry(ctx, sid, perfect):
+    """explorer/explorer.fut:109-130 `step s n` as ONE C entry (flowamok_explorer_step: ticks + scenario.step + cycle
+    recomputation + leak sum inside the library), in batches of 7 steps, against the oracle's Explorer."""
+    import ctypes as C
+    from flowamok_b200 import scenarios as S
+    ox = O.Explorer(123, sid, perfect=perfect)
+    dx = S.Explorer(ctx, 123, sid, perfect=perfect)          # init only; the stepping below is the C entry
+    step_cur, st, inc, nl = C.c_int64(0), C.c_uint64(dx.rng.state), C.c_uint64(dx.rng.inc), C.c_int64()
+    for batch in range(12):
+        want = ox.step(7)
+        ctx.check(ctx.L.flowamok_explorer_step(ctx.h, dx.grid.h, sid, int(perfect), 7, C.byref(step_cur), C.byref(st), C.byref(inc),
+                                               C.byref(nl)))
+        assert nl.value == want and step_cur.value == ox.step_cur, f"sid {sid} batch {batch}"
+        assert (st.value, inc.value) == (ox.rng.state, ox.rng.inc)
+        assert_state_equal(state_of(ox.grid), dev_state(dx.grid), f"sid {sid} batch {batch}")
+
+
+def test_designer_step_c_entry(ctx):
+    """designer/designer.fut:59-75 `step s n`: a car of random colour enters at (25, 0) every 10th step, stepper_quick.step;
+    the C entry against the same loop spelled out with the oracle."""
+    import ctypes as C
+    gh, gw = 60, 80
+    og = O.Grid(gh, gw)
+    og.create(O.Rng.from_seed([9]))
+    g = ctx.create_grid(gh, gw, 9)
+    for obj in (og, g):
+        obj.add_line_horizontal(25, 0, 60, 1)
+        obj.add_line_vertical(25, 50, 60, 1)
+    rng = O.Rng.from_seed([77])
+    total, st, inc, nl = C.c_int64(0), C.c_uint64(rng.state), C.c_uint64(rng.inc), C.c_int32()
+    ch = O.Chooser(O.CHOOSE_RANDOM)
+    n_total = 0
+    for batch in range(6):
+        leaks = 0
+        for _ in range(13):
+            if n_total % 10 == 0:
+                og.add_cell(25, 0, int(O.lib().fo_random_color(C.byref(rng.c))), 0, 1)
+            leaks += og.step_quick(ch)[0]
+            n_total += 1
+        ctx.check(ctx.L.flowamok_designer_step(ctx.h, g.h, 13, C.byref(total), C.byref(st), C.byref(inc), C.byref(nl)))
+        assert (nl.value, total.value) == (leaks, n_total)
+        assert (st.value, inc.value) == (rng.state, rng.inc)
+        assert_state_equal(state_of(og), dev_state(g), f"batch {batch}")
+
+
 def test_find_cycles_matches_oracle(ctx):
     import synth_ref
     arrs, rings = synth_ref.generate(50, 60, seed=4)
@@ -479,6 +525,36 @@ def test_p2p_bands_on_one_gpu_equal_oracle(cuts, perfect, cycles):
         b.p2p_close()
     for b in bands:
         b.grid.free()
+
+
+def test_sparse_rng_transfer(ctx):
+    """flowamok_grid_rng_corners / _rng_scatter: only cells with a road on both axes can draw (steppers.fut:101-103), so their
+    (index, state) pairs are all of underlying.rng a host has to move: a grid rebuilt from the dense fields WITHOUT the rng
+    plane plus the corner list continues bit-identically."""
+    arrs = random_grid(17, 120, 300, car_p=0.6)
+    g = ctx.grid_from_arrays(**arrs)
+    og, ch = oracle_grid(arrs), O.Chooser(O.CHOOSE_RANDOM)
+    for _ in range(5):
+        og.step_quick(ch)
+    g.step(False, 5)
+    idx, st = g.rng_corners()
+    corners = (arrs["uy"] != 0) & (arrs["ux"] != 0)
+    assert np.array_equal(idx, np.flatnonzero(corners.ravel()))
+    d = g.download()
+    assert np.array_equal(st, d["rng_state"].ravel()[idx])
+    changed = d["rng_state"] != arrs["rng_state"]
+    assert changed.any() and not (changed & ~corners).any()          # draws happened, and only on corner cells
+    h = ctx.grid(120, 300)
+    dense = {k: d[k] for k in ("uy", "ux", "dy", "dx", "color", "pref")}
+    h.upload(**dense, rng_state=None)                                 # rng plane stays as it is (zeros in a fresh grid)
+    h.rng_scatter(idx, st)
+    for _ in range(5):
+        og.step_quick(ch)
+    h.step(False, 5)
+    want, got = state_of(og), dev_state(h)
+    for k in ("dy", "dx", "color", "pref"):
+        assert np.array_equal(want[k], got[k]), k
+    assert np.array_equal(want["rng_state"].ravel()[idx], h.rng_corners()[1])
 
 
 def test_device_digest_matches_numpy(ctx):
