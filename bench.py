@@ -389,14 +389,14 @@ def main():
                          "dominant": {"kernel": dom, "ms": dom_ms, "traffic": dom_bytes,
                                       "dram_gbs": dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_bytes else None,
                                       "frac": dom_bytes / (dom_ms * 1e-3) / 1e9 / peak if dom_bytes else None}})
-    # launches of OUR kernels inside the timed region
-    launches_per_tick = 3 + (1 if perfect and n_rings else 0)
+    # launches of OUR kernels inside the timed region: k_u_local, [k_rings], k_u_iter || k_move, k_move_fix per tick;
+    # row bands over P2P add k_band_xstate and k_band_xu (+ k_band_xring and k_rings_mark when rings straddle the cuts)
+    launches_per_tick = 4 + (1 if perfect and n_rings else 0)
     if runner is not None and args.transport == "p2p":
-        launches_per_tick += 1 + ((2 if args.cuts == "straddle" else 0) + (1 if args.cuts == "straddle" else 0) if perfect else 0)
+        launches_per_tick += 2 + (2 if perfect and args.cuts == "straddle" else 0)
     gpu_launches = launches_per_tick * args.steps
-    if runner is not None and args.transport == "nccl":   # + per convergence round: pack, merge, k_u_iter resume
-        sides = (1 if rank > 0 else 0) + (1 if rank < world - 1 else 0)
-        gpu_launches += rounds * (2 + 1) + args.steps * 4
+    if runner is not None and args.transport == "nccl":   # kernels one after the other + pack / merge / resume per swap and round
+        gpu_launches = (3 + (1 if perfect and n_rings else 0) + 4) * args.steps + rounds * 3
     hist = g.stats_hist()
     if runner is None:
         par = "1 grid"
@@ -430,7 +430,7 @@ def main():
     if rank == 0 and not args.no_cpu:
         try:
             g1, dt1, thr = cpu_oracle_run(S, 64, 2, 1, perfect=perfect)
-            rows_c = int(15.0 / (dt1 / (64 * S * 2) * S * 6))
+            rows_c = int(30.0 / (dt1 / (64 * S * 2) * S * 6))
             rows_c = max(32, min(S, (rows_c // 16) * 16))
             gc, dt, thr = cpu_oracle_run(S, rows_c, 5, 1, perfect=perfect)
             line["cpu_baseline"] = {"value": gc, "unit": "GCUPS", "cores": thr, "kind": "port", "nproc": os.cpu_count(),

@@ -230,6 +230,13 @@ class Grid:
         self.ctx.check(self.L.flowamok_step_leaks(self.ctx.h, self.h, int(perfect), cap, buf.ctypes.data, C.byref(n)))
         return n.value, buf[:min(n.value, cap)]
 
+    def step_leaks_cells(self, perfect: bool, cap=1 << 20):
+        """one tick; the leaks with the whole source cell: rows of 14 int64 (include/flowamok.h)"""
+        buf = np.zeros((cap, 14), np.int64)
+        n = C.c_int64()
+        self.ctx.check(self.L.flowamok_step_leaks_cells(self.ctx.h, self.h, int(perfect), cap, buf.ctypes.data, C.byref(n)))
+        return n.value, buf[:min(n.value, cap)]
+
     def render(self, scale):
         px = np.zeros((self.gh * scale, self.gw * scale), np.uint32)
         self.ctx.check(self.L.flowamok_render(self.ctx.h, self.h, scale, px.ctypes.data))

@@ -63,6 +63,7 @@ def lib():
         "flowamok_step_profile": (C.c_int, [P, P, C.c_int, I64, C.POINTER(C.c_double)]),
         "flowamok_step_timeline": (C.c_int, [P, P, C.c_int, I64, C.POINTER(C.c_double)]),
         "flowamok_step_leaks": (C.c_int, [P, P, C.c_int, I64, P, C.POINTER(I64)]),
+        "flowamok_step_leaks_cells": (C.c_int, [P, P, C.c_int, I64, P, C.POINTER(I64)]),
         "flowamok_render": (C.c_int, [P, P, I64, P]),
         "flowamok_render_device": (C.c_int, [P, P, I64, C.POINTER(P)]),
         "flowamok_grid_clone": (C.c_int, [P, P, C.POINTER(P)]),

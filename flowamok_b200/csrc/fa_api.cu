@@ -1034,12 +1034,13 @@ int flowamok_step_timeline(flowamok_context *ctx, flowamok_grid *g, int perfect,
   return rc ? 1 : check_device_errors(ctx, g);
 }
 
-int flowamok_step_leaks(flowamok_context *ctx, flowamok_grid *g, int perfect, int64_t cap, int64_t *leaks, int64_t *n_leaks) {
+static int step_leaks_impl(flowamok_context *ctx, flowamok_grid *g, int perfect, int64_t cap, int64_t *leaks, int64_t *n_leaks, int nf) {
   if (!ctx || ctx->device < 0) return fail(ctx, "no CUDA device");
   if (!g) return fail(ctx, "null grid");
+  if (g->poisoned) return fail(ctx, "grid is poisoned: %s", g->poisoned);
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  if (!g->leak_plane) CU(cudaMalloc(&g->leak_plane, g->nwords * 4));
+  if (!g->leak_plane) CU(cudaMalloc(&g->leak_plane, g->nwords * 8));   // leak mask plane + "drew in this tick" plane
   int old = g->cur;
   if (enqueue_tick(ctx, g, perfect != 0, g->leak_plane)) return 1;
   DevBuf cbuf, obuf, tbuf, dbuf;
@@ -1058,18 +1059,26 @@ int flowamok_step_leaks(flowamok_context *ctx, flowamok_grid *g, int perfect, in
   CU(cudaStreamSynchronize(st));
   long long emit = std::min<long long>(total, cap);
   if (emit > 0 && leaks) {
-    CU(dbuf.alloc((size_t)emit * 64));
+    CU(dbuf.alloc((size_t)emit * 8 * nf));
     long long *dout = dbuf.as<long long>();
     // the tuple copies the cell as move_cell saw it (steppers.fut:122): heading/colour of the old state,
     // next_preference_flow_x already updated by the fixpoint (written by U into the new buffer)
     k_leak_emit<<<nblk((long long)g->nwords, 256), 256, 0, st>>>(g->gh, g->gw, g->pitch, g->row0, g->leak_plane, offs, g->head[old],
-                                                                g->pref[old ^ 1], g->color[old], emit, dout);
+                                                                g->pref[old ^ 1], g->color[old], g->road, g->calc, g->mymx, g->rng,
+                                                                g->rng_inc, emit, nf, dout);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(leaks, dout, (size_t)emit * 64, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(leaks, dout, (size_t)emit * 8 * nf, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
   }
   if (n_leaks) *n_leaks = total;
   return check_device_errors(ctx, g);
+}
+
+int flowamok_step_leaks(flowamok_context *ctx, flowamok_grid *g, int perfect, int64_t cap, int64_t *leaks, int64_t *n_leaks) {
+  return step_leaks_impl(ctx, g, perfect, cap, leaks, n_leaks, 8);
+}
+int flowamok_step_leaks_cells(flowamok_context *ctx, flowamok_grid *g, int perfect, int64_t cap, int64_t *leaks, int64_t *n_leaks) {
+  return step_leaks_impl(ctx, g, perfect, cap, leaks, n_leaks, 14);
 }
 
 int flowamok_render(flowamok_context *ctx, const flowamok_grid *g, int64_t scale, uint32_t *pixels) {

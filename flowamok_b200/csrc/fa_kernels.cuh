@@ -837,25 +837,55 @@ __global__ void k_leak_counts(long long nwords, const u32 *leak_plane, unsigned 
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nwords) counts[i] = __popc(leak_plane[i]);
 }
+// nf = 8 (flowamok_step_leaks) or 14 (flowamok_step_leaks_cells) int64 per leak; the record is the SOURCE cell as move_cell saw it
+// (steppers.fut:122 copies `cell` of the old grid): old heading and colour, calculated / direction / preference as the fixpoint
+// left them, and the cell's rng state BEFORE this tick -- if the cell itself drew in this tick (a car entered it while its own
+// left: fork plane), the draw is undone (pcg32's state update is invertible; a redrawn rejection, probability 2^-31 per draw, is
+// undone too).
+__device__ __forceinline__ u64 pcg32_undo_draw(u64 s, u64 inc) {
+  const u64 MINV = 13877824140714322085ULL;   // 6364136223846793005^-1 mod 2^64
+  for (int k = 0; k < 4; k++) {
+    s = (s - (inc | 1ULL)) * MINV;
+    const u64 before = (s - (inc | 1ULL)) * MINV;   // was the draw before this one a rejected one of the same call?
+    u64 t = before;
+    if (pcg32_next(t, inc) < 0xFFFFFFFEu) break;
+  }
+  return s;
+}
 __global__ void k_leak_emit(int gh, int gw, int pitch, int row0, const u32 *leak_plane, const unsigned int *offs,
-                            const U4 *head_old, const u32 *pref_old, const u32 *color_old, long long cap,
-                            long long *out) {
+                            const U4 *head_old, const u32 *pref_new, const u32 *color_old, const U4 *road, const u32 *calc, const u64 *mymx,
+                            const u64 *rng, u64 rng_inc, long long cap, int nf, long long *out) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)gh * pitch) return;
   u32 m = leak_plane[i];
+  if (!m) return;
   long long k = offs[i];
   int y = (int)(i / pitch), w = (int)(i % pitch);
   U4 h = head_old[i];
-  u32 pr = pref_old[i];
+  u32 pr = pref_new[i];
+  const u32 drew = leak_plane[i + (size_t)gh * pitch];
   while (m && k < cap) {
     int b = __ffs(m) - 1;
     m &= m - 1;
     u32 bit = 1u << b;
     int x = w * 32 + b;
     int dy = (h.x & bit) ? ((h.y & bit) ? -1 : 1) : 0, dx = (h.z & bit) ? ((h.w & bit) ? -1 : 1) : 0;
-    long long *o = out + k * 8;
-    o[0] = y + row0 + dy; o[1] = x + dx; o[2] = y + row0; o[3] = x; o[4] = dy; o[5] = dx;
-    o[6] = color_old[(size_t)y * pitch * 32 + x]; o[7] = (pr & bit) ? 1 : 0;
+    long long *o = out + k * nf;
+    const size_t c = (size_t)y * pitch * 32 + x;
+    if (nf == 8) {
+      o[0] = y + row0 + dy; o[1] = x + dx; o[2] = y + row0; o[3] = x; o[4] = dy; o[5] = dx;
+      o[6] = color_old[c]; o[7] = (pr & bit) ? 1 : 0;
+    } else {
+      const U4 r = road[i];
+      const u64 mm = mymx[i];
+      u64 st = rng[c];
+      if (drew & bit) st = pcg32_undo_draw(st, rng_inc);
+      o[0] = y + row0 + dy; o[1] = x + dx; o[2] = y + row0; o[3] = x;
+      o[4] = (r.x & bit) ? ((r.y & bit) ? -1 : 1) : 0; o[5] = (r.z & bit) ? ((r.w & bit) ? -1 : 1) : 0;
+      o[6] = dy; o[7] = dx; o[8] = color_old[c];
+      o[9] = (calc[i] & bit) ? 1 : 0; o[10] = ((u32)mm & bit) ? 1 : 0; o[11] = ((u32)(mm >> 32) & bit) ? 1 : 0;
+      o[12] = (pr & bit) ? 1 : 0; o[13] = (long long)st;
+    }
     k++;
   }
 }

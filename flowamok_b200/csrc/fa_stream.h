@@ -387,7 +387,10 @@ struct MTile {
       const MOut out = m_post(p, CH);
       const U4 hd = {out.DYN, out.DYS, out.DXN, out.DXS};
       g.head_out[o] = hd;
-      if (E.leak_plane) E.leak_plane[o] = out.leak;
+      if (E.leak_plane) {   // flowamok_step_leaks: the leak mask, and (second plane) the cells that drew from their rng in this tick
+        E.leak_plane[o] = out.leak;
+        E.leak_plane[o + (size_t)g.gh * g.pitch] = g.chooser == CHOOSE_RANDOM ? out.fork : 0u;
+      }
       nleak += (unsigned int)popc32(out.leak);
       d.y = out.AY | out.AX;
       u32 arrS = 0u;   // the word's 32-byte colour sectors that receive a car (bit k = cells 8k .. 8k+7)

@@ -111,6 +111,11 @@ int flowamok_step_timeline(flowamok_context *ctx, flowamok_grid *g, int perfect,
  * to cap leaks in row-major order of the source cell as 8 int64 per leak:
  * {y_next, x_next, y_src, x_src, dy, dx, color, pref}.  Synchronous. */
 int flowamok_step_leaks(flowamok_context *ctx, flowamok_grid *g, int perfect, int64_t cap, int64_t *leaks, int64_t *n_leaks);
+/* The same with the WHOLE source cell of the reference's tuple (y_next, x_next, cell) (src/model.fut:26, steppers.fut:122), as
+ * move_cell saw it: 14 int64 per leak {y_next, x_next, y_src, x_src, underlying.direction.y, .x, direction.y, .x, color,
+ * can_be_moved_to_from.calculated, .direction.y, .direction.x, .next_preference_flow_x, underlying.rng.state (bit pattern; inc is
+ * the grid's)}.  aux = () has no storage. */
+int flowamok_step_leaks_cells(flowamok_context *ctx, flowamok_grid *g, int perfect, int64_t cap, int64_t *leaks, int64_t *n_leaks);
 
 /* render (flowamok.fut:16-64) into a host buffer [gh*scale][gw*scale] of argb.  Synchronous. */
 int flowamok_render(flowamok_context *ctx, const flowamok_grid *g, int64_t scale, uint32_t *pixels);

@@ -1,7 +1,12 @@
 #!/usr/bin/env python
 """Turn an ncu report (--set full, --import-source on) into the text summary committed under profiles/.
-usage: python profiles/summarize.py gpurun_out/r01_kernels.ncu-rep k_move > profiles/r01_k_move.txt
-(the second argument picks one kernel of a report that holds several)"""
+usage: python profiles/summarize.py gpurun_out/r02_quick.ncu-rep k_move > profiles/r02_k_move.txt
+(the second argument picks one kernel of a report that holds several)
+
+       python profiles/summarize.py --traffic WORKLOAD OUT.json REPORT [REPORT ...]
+writes the DRAM bytes per launch of every kernel in the reports (dram__bytes_read.sum + dram__bytes_write.sum; first launch
+of each kernel name) together with the sha256 of the kernel sources they were captured on: bench.py reports
+`roofline.traffic` / `roofline.physical` from that file, and only while the sources are still the same."""
 import csv
 import subprocess
 import sys
@@ -67,5 +72,39 @@ def main(rep, kern=None):
         print("\nTMA / mbarrier SASS present:", sorted(set(x.split()[0] if not x.startswith('@') else x.split()[1] for x in tma)))
 
 
+def traffic(workload, out, reps):
+    import hashlib
+    import json
+    import re
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    h = hashlib.sha256()
+    for f in sorted((root / "flowamok_b200" / "csrc").iterdir()):
+        if f.suffix in (".h", ".cuh", ".cu", ".inc"):
+            h.update(f.name.encode())
+            h.update(f.read_bytes())
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tunit = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "usecond": 1.0, "nsecond": 1e-3, "msecond": 1e3, "second": 1e6}
+    dram, dur = {}, {}
+    for rep in reps:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        hdr, units = rows[0], rows[1]
+        ki, ir, iw, it = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+        for r in rows[2:]:
+            name = re.sub(r"<.*", "", r[ki].replace("void ", "").split("(")[0]).replace("fa::", "").strip()
+            if name in dram:
+                continue
+            dram[name] = float(r[ir].replace(",", "")) * unit[units[ir]] + float(r[iw].replace(",", "")) * unit[units[iw]]
+            dur[name] = float(r[it].replace(",", "")) * tunit[units[it]]
+    Path(out).write_text(json.dumps({"workload": workload, "csrc_sha256": h.hexdigest()[:16], "dram_bytes": dram,
+                                     "ncu_duration_us": dur, "source": "ncu --set full --clock-control none, one launch per kernel: " +
+                                     ", ".join(Path(r).name for r in reps)}, indent=1) + "\n")
+    print(Path(out).read_text())
+
+
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)
+    if sys.argv[1] == "--traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4:])
+    else:
+        main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)

@@ -234,6 +234,30 @@ def test_leak_list_order_and_content(ctx):
     assert total > 0
 
 
+def test_leak_list_whole_source_cell(ctx):
+    """cell_leak = (y_next, x_next, cell) (model.fut:26): the whole source cell as move_cell saw it (steppers.fut:122) --
+    roads, heading, colour, calculated / direction / preference after the fixpoint, and the rng state BEFORE the tick, also
+    when the leaking cell drew in the same tick."""
+    total = drew = 0
+    for seed in (21, 22, 23):
+        arrs = random_grid(seed, 90, 130, n_lines=90, car_p=0.7, weird_p=0.08, offroad_p=0.04)
+        og, ch = oracle_grid(arrs), O.Chooser(O.CHOOSE_RANDOM)
+        g = ctx.grid_from_arrays(**arrs)
+        for t in range(8):
+            before = og.arrays()["rng_state"].copy()
+            nl, leaks = og.step_quick(ch, leaks=True)
+            n, rec = g.step_leaks_cells(False)
+            assert n == nl
+            exp = [[l["y_next"], l["x_next"], l["y_src"], l["x_src"], l["uy"], l["ux"], l["dy"], l["dx"], l["color"], l["calc"],
+                    l["my"], l["mx"], l["pref"], int(np.uint64(l["rng_state"]).astype(np.int64))] for l in leaks]
+            assert rec.tolist() == exp, f"seed {seed} tick {t}"
+            after = og.arrays()["rng_state"]
+            drew += sum(before[l["y_src"], l["x_src"]] != after[l["y_src"], l["x_src"]] for l in leaks)
+            total += n
+            assert_state_equal(state_of(og), dev_state(g), f"seed {seed} tick {t}")
+    assert total > 20
+
+
 def test_render_matches_oracle(ctx):
     for scale in (1, 4, 5, 10):
         arrs = random_grid(31, 30, 45, car_p=0.5)
