@@ -38,7 +38,10 @@ def main(rep, kern=None):
     cmd = ["ncu", "-i", rep, "--page", "source", "--csv"] + (["-k", "regex:" + kern] if kern else [])
     src = subprocess.run(cmd, capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
-    hi = next(i for i, r in enumerate(rows) if "Source" in r)
+    hi = next((i for i, r in enumerate(rows) if "Source" in r), None)
+    if hi is None:
+        print("\n(no source page in this report)")
+        return
     hdr = rows[hi]
     rows = rows[hi - 1:]
     st = [i for i, h in enumerate(hdr) if h.startswith("stall_")]
