@@ -900,7 +900,11 @@ static int fork_fix_and_move(flowamok_context *ctx, flowamok_grid *g, bool p2p, 
   KCHECK("k_move");
   if (tev) CU(cudaEventRecord(tev[3], st));
   CU(cudaStreamWaitEvent(st, ctx->ev_fix, 0));
-  k_move_fix<<<ctx->num_sms * 2, 256, 0, st>>>(vf, g->fix_claim, ++g->fix_epoch, g->is, g->diag);
+  if (++g->fix_epoch == 0u) {   // the tag wrapped (after 2^32 ticks): forget the old claims
+    CU(cudaMemsetAsync(g->fix_claim, 0, g->nwords * 4, st));
+    g->fix_epoch = 1u;
+  }
+  k_move_fix<<<ctx->num_sms * 2, 256, 0, st>>>(vf, g->fix_claim, g->fix_epoch, g->is, g->diag);
   KCHECK("k_move_fix");
   if (tev) CU(cudaEventRecord(tev[4], st));
   g->cur ^= 1;

@@ -42,7 +42,10 @@ constexpr int STRIP_THREADS = 128;         // k_u_local / k_move block: 4 warps 
 #ifndef FA_UIT_THREADS
 #define FA_UIT_THREADS 128
 #endif
-constexpr int UIT_THREADS = FA_UIT_THREADS;   // k_u_iter block; ONE per SM: the clean k_move tiles run beside the fixpoint
+#ifndef FA_UIT_MINB
+#define FA_UIT_MINB 8                      // register budget of k_u_iter: 64 K / (threads * this) per thread
+#endif
+constexpr int UIT_THREADS = FA_UIT_THREADS;   // k_u_iter block; ONE small CTA per SM: k_move runs beside the fixpoint
 
 struct IterState {
   unsigned int qn[3];       // frontier lengths: iteration it >= 1 reads slot it % 3 and writes (it + 1) % 3
@@ -127,7 +130,7 @@ constexpr int UIT_CHASE = FA_UIT_CHASE;   // links of a waiting queue one visit 
 // become the next frontier, and all bands vote -- device to device -- whether anybody woke anything.  No NCCL call, no
 // kernel boundary and no host round trip per convergence round; the other CTAs wait at the grid barrier.
 template <bool P2P>
-__global__ void __launch_bounds__(UIT_THREADS, 8)   // <= 64 registers: 8 K of an SM's 64 K, so that k_move keeps 4 of its 5 CTAs beside it
+__global__ void __launch_bounds__(UIT_THREADS, FA_UIT_MINB)   // <= 64 registers: 8 K of an SM's 64 K, so that k_move keeps 4 of its 5 CTAs beside it
 k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *qlist0, unsigned int *qlist1,
          unsigned int first_it, IterState *is, Diag *diag, const __grid_constant__ BandLink L) {
   const int tid = threadIdx.x, nt = blockDim.x, b = blockIdx.x, nb = gridDim.x, lane = tid & 31;
