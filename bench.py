@@ -398,6 +398,11 @@ def main():
     if runner is not None and args.transport == "nccl":   # kernels one after the other + pack / merge / resume per swap and round
         gpu_launches = (3 + (1 if perfect and n_rings else 0) + 4) * args.steps + rounds * 3
     hist = g.stats_hist()
+
+    def jam_ticks():
+        n = C.c_int64()
+        ctx.check(ctx.L.flowamok_jam_ticks(ctx.h, g.h, C.byref(n)))
+        return n.value
     if runner is None:
         par = "1 grid"
     elif args.transport == "p2p":
@@ -420,6 +425,7 @@ def main():
                          "iterations_histogram": {"what": "ticks by number of frontier iterations of k_u_iter on rank 0 "
                                                           "(all ticks since the grid was made; bucket 31 = 31 and more)",
                                                   "ticks": {str(k): v for k, v in enumerate(hist) if v}},
+                         "ticks_in_jam_order": jam_ticks(),
                          "band_convergence_rounds_per_tick": rounds / args.steps if runner else None,
                          "band_wait_ms_per_tick_rank0": ((p2p1["wait_ns"] - p2p0["wait_ns"]) / 1e6 / args.steps) if p2p1 else None},
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(gpu_launches), "e2e": e2e,

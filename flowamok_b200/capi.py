@@ -41,6 +41,8 @@ def lib():
         "flowamok_context_sync": (C.c_int, [P]),
         "flowamok_context_get_error": (P, [P]),
         "flowamok_context_device": (C.c_int, [P]),
+        "flowamok_set_jam_threshold": (C.c_int, [P, C.c_double]),
+        "flowamok_jam_ticks": (C.c_int, [P, P, C.POINTER(I64)]),
         "flowamok_grid_new": (C.c_int, [P, C.POINTER(P), I64, I64]),
         "flowamok_grid_free": (C.c_int, [P, P]),
         "flowamok_grid_recycle": (C.c_int, [P, P]),

@@ -64,6 +64,8 @@ struct flowamok_context {
   int num_sms;
   int iter_blocks; // co-resident CTAs of k_u_iter
   int iter_blocks_p2p = 0;   // the same for a band with mapped peers (smaller when several bands share one device)
+  int iter_blocks_big = 0;   // every CTA of k_u_iter an SM can hold: jammed networks (the fixpoint alone on the device)
+  double jam_visits = 40000.0;   // visits per fixpoint iteration above which a tick runs in jam order (flowamok_set_jam_threshold)
   size_t smem_optin = 0;   // largest dynamic shared memory a CTA may ask for
   std::string err;
   std::vector<struct flowamok_grid *> grids;   // live grids: flowamok_context_sync reads their watchdog flags
@@ -129,6 +131,12 @@ struct flowamok_grid {
   void *ipc_opened[BAND_MAXW] = {};
   unsigned int s_seq = 0;           // state messages sent so far (= ticks stepped over P2P)
   int p2p_blocks = 0;               // cooperative grid of k_u_iter<true>
+  // Jam detection: {iterations, visits} of the fixpoint, copied to pinned memory after every k_u_iter WITHOUT a synchronisation
+  // (the host reads whatever has arrived: a few ticks late is fine).  A frontier of tens of thousands of words per iteration
+  // needs the whole device: the tick then runs k_u_iter at full size before k_move instead of a small one beside it.
+  unsigned long long *h_fix = nullptr, fix_seen[2] = {0, 0};
+  bool jam = false;
+  long long jam_ticks = 0;          // ticks stepped in jam order
   int8_t *stage = nullptr;          // staging buffer of upload / download (grows, never shrinks; no cudaMalloc per call)
   size_t stage_bytes = 0;
   const char *poisoned = nullptr;   // a device-side watchdog tripped: the planes are not trustworthy any more
@@ -236,7 +244,8 @@ int flowamok_context_new(flowamok_context **out, int device, void *stream) {
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_u_iter<false>, UIT_THREADS, 0));
   if (per_sm < 1) return fail(ctx, "k_u_iter does not fit on an SM");
-  ctx->iter_blocks = ctx->num_sms;   // ONE small CTA per SM: the clean k_move tiles run beside the fixpoint
+  ctx->iter_blocks = ctx->num_sms;   // ONE small CTA per SM: k_move runs beside the fixpoint
+  ctx->iter_blocks_big = std::min(per_sm, 4) * ctx->num_sms;   // 4 x 128 threads per SM: more CTAs only make the grid barrier dearer
   {   // Load every kernel of the stepping path NOW.  With CUDA's lazy module loading the first launch of a kernel may have to
       // wait for running kernels to finish -- and the band kernels wait for each other on the device, so a load in the middle
       // of a tick could wait forever for a kernel whose neighbour has not been enqueued yet.
@@ -286,6 +295,18 @@ char *flowamok_context_get_error(flowamok_context *ctx) {
   return s;
 }
 int flowamok_context_device(flowamok_context *ctx) { return ctx ? ctx->device : -1; }
+/* tuning knob: a tick whose recent fixpoint iterations visited more than this many words each runs k_u_iter at full size before
+ * k_move instead of a small one beside a speculative k_move (default 40000; results are identical either way) */
+int flowamok_jam_ticks(flowamok_context *ctx, const flowamok_grid *g, int64_t *n) {
+  if (!g || !n) return fail(ctx, "null argument");
+  *n = g->jam_ticks;
+  return 0;
+}
+int flowamok_set_jam_threshold(flowamok_context *ctx, double visits_per_iteration) {
+  if (!ctx || !(visits_per_iteration > 0.0)) return 1;
+  ctx->jam_visits = visits_per_iteration;
+  return 0;
+}
 
 // ---------------------------------------------------------------------------------------------
 }  // extern "C"
@@ -361,6 +382,8 @@ static int grid_alloc(flowamok_context *ctx, flowamok_grid **out, int64_t gh_glo
   CU(cudaMalloc(&g->is, sizeof(IterState)));
   CU(cudaMalloc(&g->diag, sizeof(Diag)));
   CU(cudaMallocHost(&g->h_diag, sizeof(Diag)));
+  CU(cudaMallocHost(&g->h_fix, 16));
+  g->h_fix[0] = g->h_fix[1] = 0;
   memset(&g->base, 0, sizeof(Diag));
   cudaStream_t st = ctx->stream;
   CU(cudaMemsetAsync(g->road, 0, g->nwords * sizeof(U4), st));
@@ -429,6 +452,7 @@ int flowamok_grid_free(flowamok_context *ctx, flowamok_grid *g) {
   cudaFree(g->table); cudaFree(g->qlist[0]); cudaFree(g->qlist[1]); cudaFree(g->ustate); cudaFree(g->mymx_B); cudaFree(g->chg_list); cudaFree(g->fix_claim);
   cudaFree(g->ring_words); cudaFree(g->ring_off); cudaFree(g->leak_plane); cudaFree(g->stage);
   cudaFreeHost(g->h_diag);
+  if (g->h_fix) cudaFreeHost(g->h_fix);
   delete g;
   return 0;
 }
@@ -851,12 +875,13 @@ static int launch_u_init(flowamok_context *ctx, flowamok_grid *g, const GridView
 }
 // first_it = 0: start from the frontier k_u_local left in qlist[0]; 1: resume from qlist[1] (band merge)
 static int launch_u_iter(flowamok_context *ctx, flowamok_grid *g, GridView &v, unsigned int first_it, bool p2p = false,
-                         cudaStream_t st = nullptr) {
+                         cudaStream_t st = nullptr, int blocks = 0) {
   if (!st) st = ctx->stream;
+  if (!blocks) blocks = ctx->iter_blocks;
   void *args[] = {(void *)&v, (void *)&g->table, (void *)&g->qlist[0], (void *)&g->qlist[1],
                   (void *)&first_it, (void *)&g->is, (void *)&g->diag, (void *)&g->link};
   if (p2p) CU(cudaLaunchCooperativeKernel((void *)k_u_iter<true>, dim3(g->p2p_blocks), dim3(UIT_THREADS), args, 0, st));
-  else CU(cudaLaunchCooperativeKernel((void *)k_u_iter<false>, dim3(ctx->iter_blocks), dim3(UIT_THREADS), args, 0, st));
+  else CU(cudaLaunchCooperativeKernel((void *)k_u_iter<false>, dim3(blocks), dim3(UIT_THREADS), args, 0, st));
   KCHECK("k_u_iter");
   return 0;
 }
@@ -895,6 +920,7 @@ static int fork_fix_and_move(flowamok_context *ctx, flowamok_grid *g, bool p2p, 
   if (launch_u_iter(ctx, g, vf, 0u, p2p, ctx->hi)) return 1;
   if (tev) CU(cudaEventRecord(tev[2], ctx->hi));
   CU(cudaEventRecord(ctx->ev_fix, ctx->hi));
+  CU(cudaMemcpyAsync(g->h_fix, &g->diag->passes, 16, cudaMemcpyDeviceToHost, ctx->hi));   // jam detection; nobody waits for it
   GridView vs = make_view(g);
   k_move<M_WARPS><<<g->mtx * g->mty, M_WARPS * 32, MTL::Smem::bytes(g->rs_m), st>>>(vs, g->nsx, g->mtx, g->rs_m, g->diag, nullptr);
   KCHECK("k_move");
@@ -918,6 +944,24 @@ static int enqueue_tick(flowamok_context *ctx, flowamok_grid *g, bool perfect, u
   if (g->halo != 0) return fail(ctx, "a row band is stepped with the flowamok_band_* calls");
   cudaStream_t st = ctx->stream;
   if (ctx->split && !ev && !leak_plane) {
+    {   // jam detection on what the last ticks reported: visits per fixpoint iteration, with hysteresis
+      const unsigned long long p = ((volatile unsigned long long *)g->h_fix)[0], w = ((volatile unsigned long long *)g->h_fix)[1];
+      if (p > g->fix_seen[0] && w >= g->fix_seen[1]) {
+        const double per_it = (double)(w - g->fix_seen[1]) / (double)(p - g->fix_seen[0]);
+        if (per_it > ctx->jam_visits) g->jam = true;
+        else if (per_it < 0.4 * ctx->jam_visits) g->jam = false;
+        g->fix_seen[0] = p; g->fix_seen[1] = w;
+      }
+    }
+    if (g->jam && !tev) {   // the frontier is large: the fixpoint gets the whole device, then the move (no speculation)
+      g->jam_ticks++;
+      GridView v = make_view(g);
+      if (launch_u_init(ctx, g, v)) return 1;
+      if (launch_u_iter(ctx, g, v, 0u, false, st, ctx->iter_blocks_big)) return 1;
+      CU(cudaMemcpyAsync(g->h_fix, &g->diag->passes, 16, cudaMemcpyDeviceToHost, st));
+      if (perfect && launch_rings(ctx, g, v)) return 1;
+      return launch_move(ctx, g, v, nullptr);
+    }
     if (tev) CU(cudaEventRecord(tev[0], st));
     GridView v = make_view(g);
     if (launch_u_init(ctx, g, v)) return 1;

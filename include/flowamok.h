@@ -130,6 +130,12 @@ int flowamok_grid_clone(flowamok_context *ctx, const flowamok_grid *src, flowamo
 /* flowamok_grid_free that keeps the planes for the next flowamok_grid_clone of a grid of the same shape (at most two are kept) */
 int flowamok_grid_recycle(flowamok_context *ctx, flowamok_grid *g);
 
+/* Tuning knob.  Normally the global fixpoint runs as a small kernel BESIDE the move; on a jammed network -- recent
+ * fixpoint iterations visited more than `visits_per_iteration` words each (default 40000) -- a tick runs it at full size before the
+ * move instead.  The results are identical either way. */
+int flowamok_set_jam_threshold(flowamok_context *ctx, double visits_per_iteration);
+int flowamok_jam_ticks(flowamok_context *ctx, const flowamok_grid *g, int64_t *n);   /* ticks this grid stepped in jam order */
+
 /* diagnostics of the ticks since the last call: ticks, fixpoint iterations, worklist entries relaxed */
 int flowamok_stats(flowamok_context *ctx, flowamok_grid *g, int64_t *ticks, int64_t *passes, int64_t *sweeps);
 

@@ -60,6 +60,34 @@ def test_dense_jam_multi_pass(ctx):
     assert st["ticks"] == 6 and st["passes"] > 6, st
 
 
+def test_jam_mode_switch_is_exact():
+    """A jammed network (many visits per fixpoint iteration) makes the tick switch from "small k_u_iter beside a speculative
+    k_move" to "full-size k_u_iter, then k_move" a few ticks later (jam detection reads device counters without synchronising)
+    and back when the threshold is raised: every tick of both schedules must equal the oracle.  The threshold is lowered so
+    that a grid the oracle steps in seconds trips it."""
+    import flowamok_b200 as fa
+    c = fa.Context()
+    gh, gw = 1024, 4096
+    arrs, rings = synth_ref.generate(gh, gw, seed=5, density16=60000)
+    g = c.grid_from_arrays(**arrs)
+    og, ch = oracle_grid(arrs), O.Chooser(O.CHOOSE_RANDOM)
+    g.stats()
+    assert c.L.flowamok_set_jam_threshold(c.h, 500.0) == 0
+    for t in range(16):
+        if t == 10:
+            assert c.L.flowamok_set_jam_threshold(c.h, 1e9) == 0     # back to the speculative order
+        nl, _ = og.step_quick(ch)
+        assert g.step(False, 1) == nl, f"tick {t}"
+        if t in (0, 1, 5, 9, 10, 12, 15):
+            assert_state_equal(state_of(og), dev_state(g), f"tick {t}")
+    st = g.stats()
+    assert st["sweeps"] / max(1, st["passes"]) > 500, st      # the workload really was above the lowered threshold
+    import ctypes as C
+    n = C.c_int64()
+    assert c.L.flowamok_jam_ticks(c.h, g.h, C.byref(n)) == 0
+    assert 3 <= n.value <= 10, n.value                         # both orders ran
+
+
 def test_dense_free_flow_overflows_the_arrival_list(ctx):
     """every row an avenue, every other cell a car: half of all cells receive a car each tick, far more than the
     shared-memory arrival list of a k_move tile holds (the direct pass from the descriptors runs); the grid is wider
