@@ -131,8 +131,9 @@ struct flowamok_grid {
   void *ipc_opened[BAND_MAXW] = {};
   unsigned int s_seq = 0;           // state messages sent so far (= ticks stepped over P2P)
   int p2p_blocks = 0;               // cooperative grid of k_u_iter<true>
-  // Jam detection: {iterations, visits} of the fixpoint, copied to pinned memory after every k_u_iter WITHOUT a synchronisation
-  // (the host reads whatever has arrived: a few ticks late is fine).  A frontier of tens of thousands of words per iteration
+  // Jam detection: k_u_iter stores its cumulative {iterations, visits} into pinned host memory when it ends (posted stores, no
+  // copy, no synchronisation: an asynchronous 16-byte copy on the fixpoint's stream cost 34 us per tick); the host reads
+  // whatever has arrived when it enqueues a tick -- a few ticks late is fine.  A frontier of tens of thousands of words per iteration
   // needs the whole device: the tick then runs k_u_iter at full size before k_move instead of a small one beside it.
   unsigned long long *h_fix = nullptr, fix_seen[2] = {0, 0};
   bool jam = false;
@@ -879,7 +880,7 @@ static int launch_u_iter(flowamok_context *ctx, flowamok_grid *g, GridView &v, u
   if (!st) st = ctx->stream;
   if (!blocks) blocks = ctx->iter_blocks;
   void *args[] = {(void *)&v, (void *)&g->table, (void *)&g->qlist[0], (void *)&g->qlist[1],
-                  (void *)&first_it, (void *)&g->is, (void *)&g->diag, (void *)&g->link};
+                  (void *)&first_it, (void *)&g->is, (void *)&g->diag, (void *)&g->link, (void *)&g->h_fix};
   if (p2p) CU(cudaLaunchCooperativeKernel((void *)k_u_iter<true>, dim3(g->p2p_blocks), dim3(UIT_THREADS), args, 0, st));
   else CU(cudaLaunchCooperativeKernel((void *)k_u_iter<false>, dim3(blocks), dim3(UIT_THREADS), args, 0, st));
   KCHECK("k_u_iter");
@@ -920,7 +921,6 @@ static int fork_fix_and_move(flowamok_context *ctx, flowamok_grid *g, bool p2p, 
   if (launch_u_iter(ctx, g, vf, 0u, p2p, ctx->hi)) return 1;
   if (tev) CU(cudaEventRecord(tev[2], ctx->hi));
   CU(cudaEventRecord(ctx->ev_fix, ctx->hi));
-  CU(cudaMemcpyAsync(g->h_fix, &g->diag->passes, 16, cudaMemcpyDeviceToHost, ctx->hi));   // jam detection; nobody waits for it
   GridView vs = make_view(g);
   k_move<M_WARPS><<<g->mtx * g->mty, M_WARPS * 32, MTL::Smem::bytes(g->rs_m), st>>>(vs, g->nsx, g->mtx, g->rs_m, g->diag, nullptr);
   KCHECK("k_move");
@@ -958,7 +958,6 @@ static int enqueue_tick(flowamok_context *ctx, flowamok_grid *g, bool perfect, u
       GridView v = make_view(g);
       if (launch_u_init(ctx, g, v)) return 1;
       if (launch_u_iter(ctx, g, v, 0u, false, st, ctx->iter_blocks_big)) return 1;
-      CU(cudaMemcpyAsync(g->h_fix, &g->diag->passes, 16, cudaMemcpyDeviceToHost, st));
       if (perfect && launch_rings(ctx, g, v)) return 1;
       return launch_move(ctx, g, v, nullptr);
     }

@@ -53,6 +53,7 @@ struct IterState {
   unsigned int error;       // barrier watchdog tripped
   unsigned int chg_n;       // words listed for the fix-up of the speculative move (k_u_iter wipes the previous tick's first)
   unsigned int pad[1];
+  unsigned long long cum_it, cum_visits;   // iterations / visited words of all k_u_iter launches so far (jam detection)
 };
 
 struct Diag {
@@ -132,7 +133,7 @@ constexpr int UIT_CHASE = FA_UIT_CHASE;   // links of a waiting queue one visit 
 template <bool P2P>
 __global__ void __launch_bounds__(UIT_THREADS, FA_UIT_MINB)   // <= 64 registers: 8 K of an SM's 64 K, so that k_move keeps 4 of its 5 CTAs beside it
 k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *qlist0, unsigned int *qlist1,
-         unsigned int first_it, IterState *is, Diag *diag, const __grid_constant__ BandLink L) {
+         unsigned int first_it, IterState *is, Diag *diag, const __grid_constant__ BandLink L, unsigned long long *host_stats) {
   const int tid = threadIdx.x, nt = blockDim.x, b = blockIdx.x, nb = gridDim.x, lane = tid & 31;
   volatile IterState *vis = is;
   unsigned int *ql[2] = {qlist0, qlist1};
@@ -175,6 +176,7 @@ k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *
 
   // iteration `it` visits the entry indices in qlist[it & 1] (length qn[it % 3]) and appends to qlist[(it + 1) & 1]
   unsigned int it = first_it, its_done = 0;
+  unsigned long long visits = 0;   // sum of the frontier lengths (the same number in every CTA that takes part)
   unsigned int useq = P2P ? *(volatile unsigned int *)&L.dev->u_seq : 0u;   // number of the last u message sent (k_band_xu counts too)
   if (g.mymx_B) {   // speculative move: the previous tick's deltas (its fix-up is done) are wiped, the list starts empty
     const unsigned int n = *(volatile unsigned int *)g.chg_n;
@@ -203,6 +205,7 @@ k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *
         else visit_and_flush(std::false_type(), k < n, k < n ? src[k] : 0u, dst, out_cnt);
       }
       its_done++;
+      visits += n;
       if (tail) { __threadfence(); __syncthreads(); }
       else if (!grid_barrier(is, nb)) return;
     }
@@ -247,6 +250,10 @@ k_u_iter(const __grid_constant__ GridView g, const UEntry *table, unsigned int *
       is->qn[0] = 0; is->qn[1] = 0; is->qn[2] = 0;   // the slot everyone just read is 0 already
       atomicAdd(&diag->passes, (unsigned long long)its_done);
       atomicAdd(&diag->hist[its_done < 31u ? its_done : 31u], 1ull);
+      is->cum_it += its_done; is->cum_visits += visits;
+      if (host_stats) {   // pinned host memory: posted stores, nobody waits (the host's jam detection reads them whenever)
+        host_stats[0] = is->cum_it; host_stats[1] = is->cum_visits;
+      }
     }
   }
 }
