@@ -895,8 +895,15 @@ static int launch_rings(flowamok_context *ctx, flowamok_grid *g, const GridView 
   }
   return 0;
 }
+static size_t move_smem_bytes(const flowamok_grid *g) {
+#ifdef FA_B1_TMA   // A/B variant: staging buffer + mbarrier behind the tile's lists
+  return ((MTL::Smem::bytes(g->rs_m) + 127) & ~(size_t)127) + B1_TMA_CHUNK * 32 + 16;
+#else
+  return MTL::Smem::bytes(g->rs_m);
+#endif
+}
 static int launch_move(flowamok_context *ctx, flowamok_grid *g, const GridView &v, u32 *leak_plane) {
-  k_move<M_WARPS><<<g->mtx * g->mty, M_WARPS * 32, MTL::Smem::bytes(g->rs_m), ctx->stream>>>(v, g->nsx, g->mtx, g->rs_m, g->diag, leak_plane);
+  k_move<M_WARPS><<<g->mtx * g->mty, M_WARPS * 32, move_smem_bytes(g), ctx->stream>>>(v, g->nsx, g->mtx, g->rs_m, g->diag, leak_plane);
   KCHECK("k_move");
   g->cur ^= 1;
   g->tick++;
@@ -922,7 +929,7 @@ static int fork_fix_and_move(flowamok_context *ctx, flowamok_grid *g, bool p2p, 
   if (tev) CU(cudaEventRecord(tev[2], ctx->hi));
   CU(cudaEventRecord(ctx->ev_fix, ctx->hi));
   GridView vs = make_view(g);
-  k_move<M_WARPS><<<g->mtx * g->mty, M_WARPS * 32, MTL::Smem::bytes(g->rs_m), st>>>(vs, g->nsx, g->mtx, g->rs_m, g->diag, nullptr);
+  k_move<M_WARPS><<<g->mtx * g->mty, M_WARPS * 32, move_smem_bytes(g), st>>>(vs, g->nsx, g->mtx, g->rs_m, g->diag, nullptr);
   KCHECK("k_move");
   if (tev) CU(cudaEventRecord(tev[3], st));
   CU(cudaStreamWaitEvent(st, ctx->ev_fix, 0));

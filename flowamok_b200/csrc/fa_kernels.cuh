@@ -467,6 +467,67 @@ __global__ void k_rings_mark(const __grid_constant__ GridView g, const RingWord 
   }
 }
 
+#ifdef FA_B1_TMA
+// ---------------------------------------------------------------------------------------------
+// A/B VARIANT, not the production path (tools/tune_variants.py build tma=-DFA_B1_TMA): phase B1 of k_move -- the copy of the
+// listed 32-byte colour sectors -- through the bulk-async copy engine (cp.async.bulk global -> shared with an mbarrier,
+// shared -> global with a bulk group) instead of LDG.128 / STG.128 through registers.  Measured and rejected: DESIGN 6b.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done = 0;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(dst_gmem), "r"(smem_addr(src_smem)), "r"(bytes) : "memory");
+}
+constexpr int B1_TMA_CHUNK = 256;   // sectors staged per round: 8 KB of shared memory
+// all threads of the CTA; stage: B1_TMA_CHUNK * 32 bytes, 128-byte aligned; bar: one mbarrier (initialised, count 1)
+template <class MT>
+__device__ __forceinline__ void phaseB1_tma(const GridView &g, typename MT::Smem sm, int tsx, int ya, int tid, int nt, char *stage, uint64_t *bar) {
+  const unsigned short *sect = sm.sect();
+  const int ns = (int)sm.cnt()[0];
+  uint32_t parity = 0;
+  for (int c0 = 0; c0 < ns; c0 += B1_TMA_CHUNK) {
+    const int n = min(B1_TMA_CHUNK, ns - c0);
+    if (tid == 0) mbar_expect_tx(bar, (uint32_t)n * 32u);
+    __syncthreads();
+    for (int k = tid; k < n; k += nt) {
+      const int id = sect[c0 + k], row = id / (MT::TW * 4), sc = id - row * (MT::TW * 4);
+      const size_t off = ((size_t)(ya + row) * g.pitch + (size_t)tsx * STRIP_W) * 32 + (size_t)sc * 8;
+      bulk_g2s(stage + (size_t)k * 32, g.color_in + off, 32u, bar);
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int k = tid; k < n; k += nt) {
+      const int id = sect[c0 + k], row = id / (MT::TW * 4), sc = id - row * (MT::TW * 4);
+      const size_t off = ((size_t)(ya + row) * g.pitch + (size_t)tsx * STRIP_W) * 32 + (size_t)sc * 8;
+      bulk_s2g(g.color_out + off, stage + (size_t)k * 32, 32u);
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the staging buffer may be overwritten
+    __syncthreads();
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");          // the writes are done before the arrival patches
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // move + reset
 // ---------------------------------------------------------------------------------------------
@@ -491,7 +552,18 @@ k_move(const __grid_constant__ GridView g, int nsx, int ntx, int rs, Diag *diag,
   __syncthreads();
   MTL::phaseB0(sm, yb - ya, tid, nt);
   __syncthreads();
+#ifdef FA_B1_TMA
+  {
+    const size_t lists = ((size_t)rs * MTL::TW * 6 + MTL::ARR_CAP + 4) * 4;   // MTile::Smem::bytes(rs)
+    char *stage = reinterpret_cast<char *>(smem_raw) + ((lists + 127) & ~(size_t)127);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(stage + B1_TMA_CHUNK * 32);
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    phaseB1_tma<MTL>(g, sm, tx * NW, ya, tid, nt, stage, bar);
+  }
+#else
   MTL::phaseB1(g, sm, tx * NW, ya, tid, nt);
+#endif
   __syncthreads();   // the sector copies are ordered before the arrival patches
   MTL::phaseB2(g, sm, tx * NW, ya, yb - ya, tid, nt);
 }
