@@ -680,6 +680,16 @@ static int install_rings(flowamok_context *ctx, flowamok_grid *g, int64_t n, con
       if (have_cuts)
         for (size_t c = 1; c + 1 < g->cuts.size(); c++) touch_global |= (y[t] == g->cuts[c] - 1 || y[t] == g->cuts[c]);
     }
+    {   // A cycle must be CLOSED: every cell's check direction leads to another cell of the same cycle (what find_cycles
+        // produces, steppers.fut:247-293).  k_rings relies on it: such a ring's cells are never calculated by the fixpoint
+        // when they all head along it, so `calculated` need not be read (ring_word_ok).
+      std::unordered_set<int64_t> cells;
+      for (int64_t t = off[k]; t < off[k + 1]; t++) cells.insert(y[t] * (int64_t)g->gw + x[t]);
+      for (int64_t t = off[k]; t < off[k + 1]; t++)
+        if (!cells.count((y[t] + cy[t]) * (int64_t)g->gw + (x[t] + cx[t])) || x[t] + cx[t] < 0 || x[t] + cx[t] >= g->gw)
+          return fail(ctx, "cycle %lld is not closed: the check direction of cell (%lld, %lld) leaves it", (long long)k, (long long)y[t],
+                      (long long)x[t]);
+    }
     int sid = -1;
     if (band && have_cuts) {
       if (ymin <= ymax && band_of_row(g->cuts, ymin) != band_of_row(g->cuts, ymax)) sid = (int)n_straddle++;

@@ -80,7 +80,10 @@ int flowamok_set_chooser(flowamok_context *ctx, flowamok_grid *g, int mode, cons
 
 /* cycle_checks of stepper_perfect.step (src/steppers.fut:305) in sparse form: ring k is the cells
  * [off[k], off[k+1]) with position (y,x), check direction (cy,cx) and grant (1: direction.y, 2: direction.x,
- * i.e. the outcome of steppers.fut:206-211 for that cell).  Host arrays, copied.  n = 0 clears. */
+ * i.e. the outcome of steppers.fut:206-211 for that cell).  Host arrays, copied.  n = 0 clears.  Every cycle must be closed --
+ * each cell's check direction leads to another cell of the same cycle, as find_cycles produces them (steppers.fut:247-293) --
+ * or the call fails: ring resolution relies on it (a ring whose cells all head along it is never touched by the fixpoint).
+ * On a row band (after flowamok_band_set_cuts) pass the GLOBAL list: cycles may straddle the cuts. */
 int flowamok_set_cycles(flowamok_context *ctx, flowamok_grid *g, int64_t n, const int64_t *off, const int64_t *y,
                         const int64_t *x, const int8_t *cy, const int8_t *cx, const uint8_t *grant);
 /* stepper_perfect.find_cycles (src/steppers.fut:233-300) on the grid's roads; stores the result as

@@ -13,14 +13,21 @@ from flowamok_b200.bands import LocalBands  # noqa: E402
 
 
 def one_synth(seed, r):
-    """perfect mode on the synthetic network: cuts on multiples of 16 (rings never straddle a cut)"""
+    """perfect mode on the synthetic network: cuts on multiples of 16 (no ring is cut) or ANYWHERE (rings straddle the cuts:
+    every band judges its part, the verdict bits are AND-ed over the bands, then the ring is marked)"""
     import synth_ref
     nb16 = int(r.integers(3, 8))
     gh, gw = 16 * nb16 + int(r.integers(0, 16)), int(r.integers(40, 400))
     n_bands = int(r.integers(2, min(4, nb16) + 1))
-    cuts = sorted((16 * r.choice(np.arange(1, nb16), n_bands - 1, replace=False)).tolist())
+    if r.random() < 0.5:
+        cuts = sorted((16 * r.choice(np.arange(1, nb16), n_bands - 1, replace=False)).tolist())
+    else:
+        while True:
+            cuts = sorted(r.choice(np.arange(2, gh - 2), n_bands - 1, replace=False).tolist())
+            if all(b - a >= 2 for a, b in zip([0] + cuts, cuts + [gh])):
+                break
     rows = list(zip([0] + cuts, cuts + [gh]))
-    arrs, rings = synth_ref.generate(gh, gw, seed=seed)
+    arrs, rings = synth_ref.generate(gh, gw, seed=seed, ring_full16=int(r.integers(0, 17)))
     variant = int(r.integers(0, 3))
     bands = [EmulBand(arrs, lo, hi, variant, rings=rings) for lo, hi in rows]
     run = LocalBands(bands)

@@ -462,6 +462,32 @@ def test_grid_clone_is_independent(ctx):
     assert_state_equal(state_of(og), dev_state(g), "original after 3 ticks")
 
 
+def test_host_driven_band_protocol_with_rings_across_the_cuts(ctx):
+    """The phase-by-phase protocol (flowamok_band_rings / _ring_verdicts / _rings_apply, driven by LocalBands) with cuts that
+    run THROUGH ring tiles: every band gets the GLOBAL cycle list after flowamok_band_set_cuts."""
+    from flowamok_b200.bands import DeviceBand, LocalBands
+    gh, gw = 200, 700
+    arrs, rings = synth_ref.generate(gh, gw, seed=8, ring_full16=9)
+    off, idx, cy, cx, grant = rings
+    cuts = [0, 55, 121, 200]
+    bands = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        b = DeviceBand(ctx, gh, gw, lo, hi)
+        b.set_cuts(cuts)
+        b.grid.upload(**arrs)
+        b.grid.set_cycles(off, idx // gw, idx % gw, cy, cx, grant)
+        bands.append(b)
+    assert bands[0].ring_words() > 0
+    run = LocalBands(bands)
+    og, ch = oracle_grid(arrs), O.Chooser(O.CHOOSE_RANDOM)
+    for t in range(9):
+        og.step_perfect_sparse(ch, rings)
+        run.tick(True)
+        if t % 4 == 0:
+            want = state_of(og)
+            assert_state_equal(want, _gather_bands(bands, gh, gw, want), f"tick {t}")
+
+
 @pytest.mark.parametrize("n_bands,perfect", [(2, False), (3, False), (4, True)])
 def test_row_bands_on_one_gpu_equal_single_grid(ctx, n_bands, perfect):
     """BASELINE config 5 shape at a size the oracle finishes in seconds: the grid split into row bands (the
