@@ -105,9 +105,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """t0, t1: wall-clock bounds of the timed region; the sampler itself is started earlier (nvidia-smi needs a moment to
+        come up), and only the rows sampled inside the region -- or, for a very short region, the first one after it began --
+        are used."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -116,8 +119,13 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        rows = [r for _t, r in self.rows]
+        if t0 is not None:
+            inside = [r for t, r in self.rows if t0 <= t <= t1 + 0.12]
+            after = [r for t, r in self.rows if t >= t0]
+            rows = inside or after[:1] or rows[-1:]
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except Exception:
@@ -230,6 +238,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (flowamok_b200 has no CPU path)")
     torch.cuda.set_device(local_rank)
     old_affinity = bind_near_gpu(local_rank)
+    sampler = ClockSampler(local_rank)   # started NOW: nvidia-smi takes a few hundred ms to deliver its first row; only the rows
+    sampler.start()                      # sampled during the timed region are used (ClockSampler.stop)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -306,16 +316,16 @@ def main():
         p2p0 = band.p2p_stats() if use_p2p else None
 
         # ---- device-resident throughput: K ticks, inputs already in HBM, CUDA events on the launching stream
-        sampler = ClockSampler(local_rank)
-        sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        wall0 = time.time()
         e0.record(stream)
         run_ticks(args.steps)
         e1.record(stream)
         barrier()
+        wall1 = time.time()
         ms = maxr(e0.elapsed_time(e1))
-        clocks = sampler.stop()
+        clocks = sampler.stop(wall0, wall1)
         st = g.stats()
         rounds = (runner.rounds - rounds0) if runner else 0
         p2p1 = band.p2p_stats() if use_p2p else None
