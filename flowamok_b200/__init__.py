@@ -74,10 +74,17 @@ class Context:
     def device(self):
         return self.L.flowamok_context_device(self.h)
 
+    @classmethod
+    def _borrowed(cls, handle) -> "Context":
+        """a view of a flowamok_context somebody else owns (flowamok_lys_context); never freed from here"""
+        c = cls.__new__(cls)
+        c.L, c.h, c.stream_ptr, c._owned = lib(), C.c_void_p(handle), -1, False
+        return c
+
     def close(self):
-        if self.h:
+        if self.h and getattr(self, "_owned", True):
             self.L.flowamok_context_free(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -112,8 +119,18 @@ class Grid:
         ctx.check(self.L.flowamok_grid_new(ctx.h, C.byref(self.h), self.gh, self.gw))
         self.joined_rng = None
 
+    @classmethod
+    def _borrowed(cls, ctx: Context, handle) -> "Grid":
+        """a view of a grid value somebody else owns (flowamok_lys_state_grid); never freed from here"""
+        g = cls.__new__(cls)
+        g.ctx, g.L, g.h, g.joined_rng, g._owned = ctx, ctx.L, C.c_void_p(handle), None, False
+        gh, gw = C.c_int64(), C.c_int64()
+        ctx.check(g.L.flowamok_grid_shape(ctx.h, g.h, C.byref(gh), C.byref(gw)))
+        g.gh, g.gw = gh.value, gw.value
+        return g
+
     def free(self):
-        if self.h and self.ctx.h:
+        if self.h and self.ctx.h and getattr(self, "_owned", True):
             self.L.flowamok_grid_free(self.ctx.h, self.h)
         self.h = None
 

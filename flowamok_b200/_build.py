@@ -18,6 +18,14 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-shared", "-ldl"]
 
 
+# the lys frontends: host code above the C ABI (g++, no CUDA), one library per program like the generated ones
+LYS = PKG / "lys"
+LYS_SO = {"explorer": PKG / "libflowamok_explorer.so", "designer": PKG / "libflowamok_designer.so"}
+LYS_DEPS = [LYS / "fa_lys.h", LYS / "fa_lys_api.inc", CSRC / "fa_bits.h", PKG.parent / "include" / "flowamok.h",
+            PKG.parent / "include" / "flowamok_lys.h"]
+CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-Wl,-Bsymbolic", "-Wl,--exclude-libs,ALL"]
+
+
 def nvcc_path() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and Path(cand).exists():
@@ -46,5 +54,29 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return SO
 
 
+def lys_needs_build(name: str) -> bool:
+    so = LYS_SO[name]
+    if not so.exists():
+        return True
+    t = so.stat().st_mtime
+    return any(d.exists() and d.stat().st_mtime > t for d in LYS_DEPS + [LYS / f"{name}_lys.cpp"])
+
+
+def build_lys(name: str, force: bool = False) -> Path:
+    """libflowamok_<name>.so: links against libflowamok_b200.so next to it ($ORIGIN rpath)"""
+    so = LYS_SO[name]
+    build()
+    if not force and not lys_needs_build(name):
+        return so
+    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    cmd = [cxx, *CXX_FLAGS, "-o", str(so), str(LYS / f"{name}_lys.cpp"), f"-L{PKG}", "-lflowamok_b200", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"{cxx} failed:\n" + r.stdout + r.stderr)
+    return so
+
+
 if __name__ == "__main__":
+    for _n in LYS_SO:
+        print(build_lys(_n, force=True))
     print(build(force=True, verbose=True))
