@@ -3,6 +3,7 @@ of the CUDA tile programs (tests/emul) and field-by-field comparison."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 import sys
 from pathlib import Path
@@ -117,12 +118,18 @@ def emul_lib():
         return _emul
     deps = [_EMUL_SRC, ROOT / "tests/emul/simt_host.h"] + [ROOT / "flowamok_b200/csrc" / f
                                                          for f in ("fa_tiles.h", "fa_bits.h", "fa_stream.h", "fa_simt.h")]
-    if not _EMUL_SO.exists() or any(d.stat().st_mtime > _EMUL_SO.stat().st_mtime for d in deps):
-        _EMUL_SO.parent.mkdir(parents=True, exist_ok=True)
+    # FLOWAMOK_EMUL_SANITIZE=1: the kernel programs under AddressSanitizer + UBSan (the stand-in for compute-sanitizer's
+    # memcheck, which is closed on the GPU pool).  Run as
+    #   FLOWAMOK_EMUL_SANITIZE=1 LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 pytest tests/test_emul.py tests/test_bands_cpu.py
+    san = os.environ.get("FLOWAMOK_EMUL_SANITIZE") == "1"
+    so = _EMUL_SO.with_name("libemul_asan.so") if san else _EMUL_SO
+    if not so.exists() or any(d.stat().st_mtime > so.stat().st_mtime for d in deps):
+        so.parent.mkdir(parents=True, exist_ok=True)
         cxx = "/usr/bin/g++" if Path("/usr/bin/g++").exists() else "g++"
-        subprocess.run([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-o", str(_EMUL_SO), str(_EMUL_SRC)],
-                       check=True)
-    L = C.CDLL(str(_EMUL_SO))
+        flags = (["-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-fno-sanitize-recover=undefined"]
+                 if san else ["-O2"])
+        subprocess.run([cxx, *flags, "-std=c++17", "-fPIC", "-shared", "-o", str(so), str(_EMUL_SRC)], check=True)
+    L = C.CDLL(str(so))
     L.emul_new.restype = C.c_void_p
     L.emul_new.argtypes = [C.c_int, C.c_int]
     L.emul_free.argtypes = [C.c_void_p]
