@@ -386,18 +386,37 @@ def main():
 
             def band_ptr(a):                                 # the ABI takes whole-grid base pointers
                 return a.ctypes.data - lo * a.strides[0]
-            def e2e_pass(n_ticks):
+            legs = {}
+            def e2e_pass(n_ticks):                           # every call below is synchronous: the legs add up to the pass
+                ta = time.perf_counter()
                 if world == 1:
                     ctx.check(ctx.L.flowamok_grid_upload(ctx.h, g.h, *[band_ptr(up[k]) for k in fields_up], None, fa.PCG_INC))
                 else:
                     band.upload_cars(*[band_ptr(up[k]) for k in fields_up], None)
                 g.rng_scatter(ci, cs)
+                tb = time.perf_counter()
                 n_leaks = run_ticks(n_ticks, leaks=True)
+                tc = time.perf_counter()
                 inc = C.c_uint64()
                 ctx.check(ctx.L.flowamok_grid_download(ctx.h, g.h, None, None, *[band_ptr(dn[k]) for k in fields_dn], None, C.byref(inc)))
                 g.rng_corners(ci, cs)
+                td = time.perf_counter()
+                legs.update(upload_s=tb - ta, ticks_s=tc - tb, download_s=td - tc)
                 return n_leaks
 
+            def pcie_probe():                                # what a plain pinned copy of 1 GiB gets on this box, each way
+                n = 1 << 30
+                hbuf, dbuf = torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8, device="cuda")
+                out = {}
+                for name, (dst, src) in (("h2d_gbs", (dbuf, hbuf)), ("d2h_gbs", (hbuf, dbuf))):
+                    dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
+                    t = time.perf_counter()
+                    dst.copy_(src, non_blocking=True); torch.cuda.synchronize()
+                    out[name] = n / (time.perf_counter() - t) / 1e9
+                return out
+
+            my_h2d, my_d2h = h2d, d2h
+            probe = pcie_probe() if rank == 0 else None
             e2e_pass(1)                                      # untimed warm-up of the whole round trip (staging buffers, first touch)
             barrier()
             t0 = time.perf_counter()
@@ -417,6 +436,9 @@ def main():
                    "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                    "seconds": dt, "leaks": int(leaks), "host_memory": host_memory,
                    "rng_corner_cells": int(len(ci)),
+                   # rank 0's legs of the timed pass, and the box's own pinned-copy bandwidth (one rank copying alone)
+                   "legs": {**legs, "upload_gbs": my_h2d / legs["upload_s"] / 1e9, "download_gbs": my_d2h / legs["download_s"] / 1e9},
+                   "pcie_probe": probe,
                    "what": ("flowamok_grid_upload (host record-of-arrays: roads, headings, colours, preferences)" if world == 1 else
                             "flowamok_grid_upload_cars (car state of every band's rows)") +
                            " + flowamok_grid_rng_scatter (states of the corner cells, the only ones that can draw) + steps ticks through "
