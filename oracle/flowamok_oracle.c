@@ -4,6 +4,11 @@
  * Literal restatement of /root/reference/src/{steppers,model,helpers,utils,random,option,reduce1}.fut,
  * flowamok.fut, explorer/scenarios.fut.  Written from the behaviour of those files; nothing is
  * copied (the reference is Futhark, this is C).  Citations are file:line of the reference.
+ *
+ * Pinned by: the README GIF (tests/golden/readme_gif_classes.npz), the scenario tables evaluated from
+ * explorer/scenarios.fut (tests/golden/scenario_inits.npz) and -- cell for cell, tick for tick, leak lists and
+ * find_cycles included -- vectors made by executing src/steppers.fut itself under a Futhark-subset interpreter
+ * (tests/golden/stepper_vectors.npz, tests/test_stepper_vectors.py).  NOT pinned: the RNG arithmetic below.
  */
 #include "flowamok_oracle.h"
 #include <math.h>
