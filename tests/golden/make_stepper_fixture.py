@@ -31,14 +31,23 @@ CHOOSE_RANDOM, CHOOSE_Y, CHOOSE_X, CHOOSE_TAPE = 0, 1, 2, 3
 PCG_INC = ((0xda3e39cb94b95bdb << 1) | 1) & (2**64 - 1)
 
 
-def load_steppers():
+def load_reference():
+    """flowamok.fut (which opens src/steppers, src/utils, ...) under the interpreter.  Not in the reference tree and therefore
+    stubbed: athas/matte (argb.gray / argb.mix return symbolic values, so that `render` yields WHICH pixels are grey or mixed
+    and from which colour), diku-dk/lys, diku-dk/cpprandom (dist_i8.rand is the repository's restated pcg32 draw)."""
     unavailable = F.builtin("unavailable", 1, lambda *_: (_ for _ in ()).throw(F.FutharkError("not in the reference tree")))
-    rnge = F.Module({"rng_from_seed": F.builtin("rng_from_seed", 1, lambda xs: 0),
-                     "split_rng": unavailable, "join_rng": unavailable})
-    random_stub = {"rnge": rnge, "dist_i8": F.Module({}), "dist_f32": F.Module({}), "random_color": unavailable}
-    stubs = {"matte/colour": {"argb": F.Module({"white": 0xFFFFFFFF, "black": 0xFF000000})},
-             "lys/lys": {}, "random": random_stub}
-    return F.Program(stubs).load(REF / "steppers.fut")
+
+    def dist_i8_rand(bounds, rng):
+        r = O.Rng(rng, PCG_INC)
+        v = r.dist_i8(bounds[0], bounds[1])
+        return (r.state, v)
+    rnge = F.Module({"rng_from_seed": F.builtin("rng_from_seed", 1, lambda xs: 0), "split_rng": unavailable, "join_rng": unavailable})
+    random_stub = {"rnge": rnge, "dist_i8": F.Module({"rand": F.builtin("dist_i8.rand", 2, dist_i8_rand)}), "dist_f32": F.Module({}),
+                   "random_color": unavailable}
+    argb = F.Module({"white": 0xFFFFFFFF, "black": 0xFF000000, "gray": F.builtin("gray", 1, lambda v: ("gray", v)),
+                     "mix": F.builtin("mix", 4, lambda a, c1, b, c2: ("mix", a, c1, b, c2))})
+    stubs = {"matte/colour": {"argb": argb}, "lys/lys": {}, "random": random_stub}
+    return F.Program(stubs).load(REF.parent / "flowamok.fut")
 
 
 def to_cells(a):
@@ -84,17 +93,14 @@ def leak_rows(leaks):
 class Chooser:
     """choose_direction y x cell -> (rng, direction flow)  (steppers.fut:60, flowamok.fut:10-14 for RANDOM)"""
 
-    def __init__(self, mode, tape=None):
+    def __init__(self, mode, tape=None, reference_random=None):
         self.mode, self.tape, self.tick = mode, tape, 0
-        self.fn = F.builtin("choose_direction", 3, self.choose)
+        # RANDOM: the reference's own choose_direction_random (flowamok.fut:10-14); only dist_i8.rand underneath is restated
+        self.fn = reference_random if mode == CHOOSE_RANDOM else F.builtin("choose_direction", 3, self.choose)
 
     def choose(self, _y, _x, cell):
         u, rng = cell["underlying"]["direction"], cell["underlying"]["rng"]
-        if self.mode == CHOOSE_RANDOM:          # the repository's restatement of dist_i8.rand (0, 1) on pcg32 (unpinned arithmetic)
-            r = O.Rng(rng, PCG_INC)
-            choice = r.dist_i8(0, 1)
-            rng = r.state
-        elif self.mode == CHOOSE_Y:
+        if self.mode == CHOOSE_Y:
             choice = 0
         elif self.mode == CHOOSE_X:
             choice = 1
@@ -251,8 +257,77 @@ def find_perfect_seeds(find_cycles, want=8):
     return seeds
 
 
+def render_vectors(ref, data):
+    """render h w gh gw scale grid (flowamok.fut:16-64) with symbolic grey / mix: per pixel its kind (0 a plain colour, 1 grey,
+    2 grey mixed with a car's colour) and the colour involved"""
+    n = 0
+    for seed, (gh, gw), scale, (dh, dw) in [(1, (6, 9), 1, (0, 0)), (2, (6, 9), 2, (1, -1)), (3, (5, 8), 3, (0, 0)), (4, (7, 7), 4, (3, -2)),
+                                            (5, (6, 10), 5, (0, 0)), (6, (4, 6), 8, (-5, 7)), (7, (5, 5), 10, (0, 0)), (8, (3, 4), 13, (2, 2)),
+                                            (9, (8, 11), 7, (-9, -20))]:
+        a = palette(random_grid(900 + seed, gh, gw, n_lines=6, car_p=0.5, weird_p=0.1, offroad_p=0.05))
+        h, w = gh * scale + dh, gw * scale + dw
+        px = F.call(ref["render"], h, w, gh, gw, scale, to_cells(a))
+        kind, base = np.zeros((h, w), np.uint8), np.zeros((h, w), np.uint32)
+        for y in range(h):
+            for x in range(w):
+                v = px[y][x]
+                if isinstance(v, int):
+                    base[y, x] = v
+                elif v[0] == "gray":
+                    assert v == ("gray", 0.3)
+                    kind[y, x] = 1
+                else:
+                    assert v[:4] == ("mix", 0.5, ("gray", 0.3), 0.5) and isinstance(v[4], int)
+                    kind[y, x], base[y, x] = 2, v[4]
+        key = f"render/{n}"
+        data[f"{key}/meta"] = np.array([gh, gw, scale, h, w], np.int64)
+        for k in ("uy", "ux", "dy", "dx", "color"):
+            data[f"{key}/{k}"] = a[k]
+        data[f"{key}/kind"], data[f"{key}/base"] = kind, base
+        print(f"{key}: {gh} x {gw} cells, scale {scale}, window {h} x {w}: {int((kind == 1).sum())} grey, {int((kind == 2).sum())} mixed pixels")
+        n += 1
+    data["render/n"] = np.array(n)
+
+
+def edit_vectors(ref, data):
+    """add_line_vertical / add_line_horizontal / add_cell (utils.fut:19-38) applied in random order to an empty grid"""
+    n = 0
+    for seed, (gh, gw) in [(1, (12, 15)), (2, (9, 31)), (3, (20, 20))]:
+        r = np.random.default_rng(700 + seed)
+        a = palette(random_grid(seed, gh, gw, n_lines=0, car_p=0.0, weird_p=0.0, offroad_p=0.0))
+        for k in ("uy", "ux", "dy", "dx"):
+            a[k][...] = 0
+        a["color"][...] = 0xFFFFFFFF
+        cells, edits = to_cells(a), []
+        for _ in range(40):
+            kind = int(r.integers(0, 3))
+            if kind == 0:
+                y0, y1 = sorted(r.integers(0, gh, 2).tolist())
+                x, flow = int(r.integers(0, gw)), int(r.choice([-1, 1]))
+                cells = F.call(ref["add_line_vertical"], y0, y1, x, flow, cells)
+                edits.append([0, y0, y1, x, flow, 0, 0])
+            elif kind == 1:
+                x0, x1 = sorted(r.integers(0, gw, 2).tolist())
+                y, flow = int(r.integers(0, gh)), int(r.choice([-1, 1]))
+                cells = F.call(ref["add_line_horizontal"], y, x0, x1, flow, cells)
+                edits.append([1, y, x0, x1, flow, 0, 0])
+            else:
+                y, x, col = int(r.integers(0, gh)), int(r.integers(0, gw)), int(PALETTE[int(r.integers(0, len(PALETTE)))])
+                dy, dx = int(r.integers(-1, 2)), int(r.integers(-1, 2))
+                cells = F.call(ref["add_cell"], y, x, col, {"y": dy, "x": dx}, cells)
+                edits.append([2, y, x, col, dy, dx, 0])
+        st = from_cells(cells)
+        key = f"edits/{n}"
+        data[f"{key}/meta"] = np.array([gh, gw], np.int64)
+        data[f"{key}/edits"] = np.array(edits, np.int64)
+        for k in ("uy", "ux", "dy", "dx", "color"):
+            data[f"{key}/{k}"] = st[k]
+        n += 1
+    data["edits/n"] = np.array(n)
+
+
 def main():
-    ref = load_steppers()
+    ref = load_reference()
     quick, perfect = ref["stepper_quick"].names["step"], ref["stepper_perfect"].names["step"]
     find_cycles = ref["stepper_perfect"].names["find_cycles"]
     data, names = {}, []
@@ -265,7 +340,7 @@ def main():
         a = palette(c["arrs"])
         gh, gw = a["uy"].shape
         tape = np.random.default_rng(zlib.crc32(c["name"].encode())).integers(0, 2, 7).astype(np.uint8)
-        ch = Chooser(c["mode"], tape)
+        ch = Chooser(c["mode"], tape, ref["choose_direction_random"])
         cells = to_cells(a)
         key = c["name"]
         names.append(key)
@@ -302,6 +377,8 @@ def main():
         n_leaks = sum(len(data[f"{key}/t{t}/leaks"]) for t in range(1, c["ticks"] + 1))
         print(f"{key:36s} {gh:3d} x {gw:3d}  ticks {c['ticks']:3d}  cycles {len(cycles):3d}  leaks {n_leaks:4d}  {time.time() - t0:6.1f} s", flush=True)
     data["names"] = np.array(names)
+    render_vectors(ref, data)
+    edit_vectors(ref, data)
     np.savez_compressed(HERE / "stepper_vectors.npz", **data)
     print(f"wrote {HERE / 'stepper_vectors.npz'} ({(HERE / 'stepper_vectors.npz').stat().st_size} bytes) in {time.time() - t00:.0f} s")
 

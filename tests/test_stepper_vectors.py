@@ -72,3 +72,85 @@ def test_cuda_equals_the_reference_source(ctx, name):
         assert_state_equal(want, {k: d[k] for k in STATE_FIELDS}, f"{name} tick {t}")
         assert n == len(leaks) and np.delete(rec, [2, 3], axis=1).tolist() == leaks.tolist(), f"{name} tick {t}: cell_leak list"
     g.free()
+
+
+# ---- render (flowamok.fut:16-64) and the point edits (utils.fut:19-38), executed from the reference source the same way ----
+def check_render(name, px):
+    """px: a rendered window.  The vector says, per pixel, whether the reference takes a plain colour (and which), argb.gray 0.3,
+    or argb.mix 0.5 grey 0.5 colour (athas/matte is not in the reference tree: grey and mix must be FUNCTIONS of their
+    arguments -- one grey everywhere, one result per mixed colour -- and geometry must agree exactly)."""
+    kind, base = V[f"{name}/kind"], V[f"{name}/base"]
+    assert px.shape == kind.shape
+    plain = kind == 0
+    assert np.array_equal(px[plain], base[plain]), f"{name}: plain pixels"
+    greys = np.unique(px[kind == 1])
+    assert len(greys) <= 1, f"{name}: grey pixels differ among themselves"
+    for b in np.unique(base[kind == 2]):
+        assert len(np.unique(px[(kind == 2) & (base == b)])) == 1, f"{name}: mix of colour {b:#x} is not a function of it"
+    if len(greys):
+        assert greys[0] not in (0xFFFFFFFF, 0xFF000000)
+
+
+def render_case(i):
+    name = f"render/{i}"
+    gh, gw, scale, h, w = (int(v) for v in V[f"{name}/meta"])
+    arrs = {k: V[f"{name}/{k}"] for k in ("uy", "ux", "dy", "dx", "color")}
+    arrs["pref"] = np.zeros((gh, gw), np.uint8)
+    arrs["rng_state"] = np.zeros((gh, gw), np.uint64)
+    arrs["rng_inc"] = np.full((gh, gw), PCG_INC, np.uint64)
+    return name, gh, gw, scale, h, w, arrs
+
+
+@pytest.mark.parametrize("i", range(int(V["render/n"])))
+def test_oracle_render_equals_the_reference_source(i):
+    name, gh, gw, scale, h, w, arrs = render_case(i)
+    og = oracle_grid(arrs)
+    px = np.zeros((h, w), np.uint32)
+    O.lib().fo_render(og.p, h, w, scale, px.ctypes.data)
+    check_render(name, px)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("i", range(int(V["render/n"])))
+def test_cuda_render_equals_the_reference_source(ctx, i):
+    name, gh, gw, scale, h, w, arrs = render_case(i)
+    g = ctx.grid_from_arrays(**arrs)
+    img = g.render(scale)                                  # [gh*scale][gw*scale]; the window cuts or pads it with black
+    px = np.full((h, w), 0xFF000000, np.uint32)
+    ch, cw = min(h, img.shape[0]), min(w, img.shape[1])
+    px[:ch, :cw] = img[:ch, :cw]
+    check_render(name, px)
+    g.free()
+
+
+def apply_edits(obj, edits):
+    for e in edits.tolist():
+        if e[0] == 0:
+            obj.add_line_vertical(e[1], e[2], e[3], e[4])
+        elif e[0] == 1:
+            obj.add_line_horizontal(e[1], e[2], e[3], e[4])
+        else:
+            obj.add_cell(e[1], e[2], e[3], e[4], e[5])
+
+
+@pytest.mark.parametrize("i", range(int(V["edits/n"])))
+def test_oracle_edits_equal_the_reference_source(i):
+    gh, gw = (int(v) for v in V[f"edits/{i}/meta"])
+    og = O.Grid(gh, gw)
+    og.create(O.Rng.from_seed([1]))
+    apply_edits(og, V[f"edits/{i}/edits"])
+    a = og.arrays()
+    for k in ("uy", "ux", "dy", "dx", "color"):
+        assert np.array_equal(a[k], V[f"edits/{i}/{k}"]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("i", range(int(V["edits/n"])))
+def test_cuda_edits_equal_the_reference_source(ctx, i):
+    gh, gw = (int(v) for v in V[f"edits/{i}/meta"])
+    g = ctx.create_grid(gh, gw, 1)
+    apply_edits(g, V[f"edits/{i}/edits"])
+    d = g.download()
+    for k in ("uy", "ux", "dy", "dx", "color"):
+        assert np.array_equal(d[k], V[f"edits/{i}/{k}"]), k
+    g.free()
