@@ -21,7 +21,10 @@ import re
 import sys
 from pathlib import Path
 
+import numpy as np
+
 sys.setrecursionlimit(20000)
+F32 = np.float32      # every floating-point value of the sources is f32
 
 KEYWORDS = {"let", "in", "if", "then", "else", "match", "case", "loop", "for", "while", "do", "with", "def", "local",
             "module", "import", "open", "type", "entry", "true", "false", "assert", "val"}
@@ -30,7 +33,8 @@ DECL_START = {"def", "local", "module", "import", "open", "type", "entry"}
 TOKEN_RE = re.compile(r"""
     (?P<ws>\s+)
   | (?P<comment>--[^\n]*)
-  | (?P<num>\d+(\.\d+)?(i8|i16|i32|i64|u8|u16|u32|u64|f32|f64)?)
+  | (?P<char>'[^'\\]')
+  | (?P<num>0b[01]+|0x[0-9a-fA-F]+|\d+(\.\d+)?(i8|i16|i32|i64|u8|u16|u32|u64|f32|f64)?)
   | (?P<str>"[^"]*")
   | (?P<tag>\#[A-Za-z_][A-Za-z_0-9']*)
   | (?P<id>[A-Za-z_][A-Za-z_0-9']*)
@@ -304,8 +308,14 @@ class Parser:
             left = ("bin", op, left, right)
         return left
 
+    COERCION_STOP = {"let", "in", "then", "else", "do", "case", ")", ",", "]", "}", "with", "def", "local", "module", "import", "open",
+                     "type", "entry"}
+
     def with_expr(self):
         e = self.unary()
+        if self.at(":>"):                              # size coercion: a no-op here
+            self.eat()
+            self.skip_type(self.COERCION_STOP)
         while self.at("with"):
             self.eat("with")
             if self.at("["):
@@ -350,7 +360,7 @@ class Parser:
 
     def atom_starts(self):
         tok = self.peek()
-        if tok.kind in ("num", "tag", "str"):
+        if tok.kind in ("num", "tag", "str", "char"):
             return True
         if tok.kind == "id":
             return tok.text not in KEYWORDS or tok.text in ("true", "false")
@@ -397,7 +407,10 @@ class Parser:
             e = ("lit", number(tok.text))
         elif tok.kind == "str":
             self.eat()
-            e = ("lit", tok.text[1:-1])
+            e = ("lit", tok.text[1:-1].replace("\\n", "\n"))
+        elif tok.kind == "char":
+            self.eat()
+            e = ("lit", ord(tok.text[1]))
         elif tok.text in ("true", "false"):
             self.eat()
             e = ("lit", tok.text == "true")
@@ -510,23 +523,19 @@ class Parser:
                     self.skip_braces()
                     continue
                 name = self.eat().text
-                if self.at(":"):
+                fparams = []
+                while self.at("("):                      # parametric module: (p: signature)
+                    self.eat("(")
+                    fparams.append(self.eat().text)
                     self.eat(":")
-                    self.skip_type({"="})
+                    self.skip_type({")"})
+                    self.eat(")")
+                if self.at(":"):                         # signature ascription, possibly `sig with t = u`
+                    self.eat(":")
+                    self.skip_module_sig()
                 self.eat("=")
-                if self.at("{"):
-                    self.eat("{")
-                    body = self.decls(until="}")
-                    self.eat("}")
-                    out.append(("module", name, body, local))
-                elif self.at("import"):
-                    self.eat()
-                    out.append(("module_import", name, self.eat().text[1:-1]))
-                else:                                    # module alias / functor application: `module rnge = pcg32`
-                    words = []
-                    while self.peek().kind != "eof" and self.peek().text not in DECL_START and not self.at("}"):
-                        words.append(self.eat().text)
-                    out.append(("module_alias", name, words))
+                mexp = self.module_expr()
+                out.append(("module", name, fparams, mexp, local))
             elif tok.text == "type":
                 self.eat()
                 while self.peek().kind != "eof" and self.peek().text not in DECL_START and not (until and self.peek().text == until
@@ -541,6 +550,50 @@ class Parser:
     def depth0(self):
         return True
 
+    def skip_module_sig(self):
+        """skip `sig` or `sig with t = u ...` up to the `=` that introduces the module's body"""
+        depth = 0
+        while True:
+            tok = self.peek()
+            if tok.kind == "eof":
+                return
+            if tok.text in ("(", "{", "["):
+                depth += 1
+            elif tok.text in (")", "}", "]"):
+                depth -= 1
+            elif tok.text == "=" and depth == 0:
+                nxt = self.peek(1)
+                if nxt.text in ("{", "import") or (nxt.kind == "id" and self.peek(2).text != "="):
+                    return
+            self.i += 1
+
+    def module_expr(self):
+        """{ decls } | import "f" | name | name.name | application of a parametric module to module expressions"""
+        def atom():
+            if self.at("{"):
+                self.eat("{")
+                body = self.decls(until="}")
+                self.eat("}")
+                return ("mbody", body)
+            if self.at("import"):
+                self.eat()
+                return ("mimport", self.eat().text[1:-1])
+            if self.at("("):
+                self.eat("(")
+                m = self.module_expr()
+                self.eat(")")
+                return m
+            path = [self.eat().text]
+            while self.at(".") and not self.peek().space_before:
+                self.eat(".")
+                path.append(self.eat().text)
+            return ("mname", path)
+        m = atom()
+        while self.peek().kind != "eof" and self.peek().text not in DECL_START and not self.at("}") and not self.at(")") and \
+                (self.at("{") or self.at("(") or (self.peek().kind == "id" and self.peek().text not in KEYWORDS)):
+            m = ("mapp", m, atom())
+        return m
+
     def skip_braces(self):
         self.eat("{")
         depth = 1
@@ -550,8 +603,14 @@ class Parser:
 
 
 def number(text):
+    if text.startswith("0b"):
+        return int(text[2:], 2)
+    if text.startswith("0x"):
+        return int(text[2:], 16)
     m = re.match(r"(\d+(\.\d+)?)", text)
-    return float(m.group(1)) if "." in m.group(1) else int(m.group(1))
+    if "." in m.group(1) or text.endswith(("f32", "f64")):
+        return F32(m.group(1))
+    return int(m.group(1))
 
 
 def pattern_as_expr(p):
@@ -601,6 +660,17 @@ def builtin(name, arity, py):
 
 class FutharkError(Exception):
     pass
+
+
+class Poison:
+    """the value of a tuple component whose evaluation failed; fails again when it is looked at"""
+
+    def __init__(self, exc):
+        self.exc = exc
+
+    def _fail(self, *_a, **_k):
+        raise FutharkError(f"use of a failed value: {self.exc}")
+    __getitem__ = __len__ = __iter__ = __add__ = __radd__ = __eq__ = __ne__ = __lt__ = __bool__ = __call__ = _fail
 
 
 def apply(f, arg):
@@ -731,10 +801,16 @@ def ev(e, env):
         if op == "*":
             return a * b
         if op == "/":
+            if isinstance(a, (float, np.floating)) or isinstance(b, (float, np.floating)):
+                return F32(a) / F32(b)
             return a // b      # Futhark's integer division rounds towards negative infinity, like Python's
         if op == "%":
             return a % b
         if op == "++":
+            if isinstance(a, str) or isinstance(b, str):      # strings are arrays of u8
+                def as_str(v):
+                    return v if isinstance(v, str) else "".join(chr(c) for c in v)
+                return as_str(a) + as_str(b)
             return a + b
         if op == "..<":
             return list(range(a, b))
@@ -754,7 +830,16 @@ def ev(e, env):
     if k == "lam":
         return Fn("<lambda>", (), e[1], e[2], env)
     if k == "tuple":
-        return tuple(ev(x, env) for x in e[1])
+        # A component that fails is poisoned instead of failing the tuple: the reference computes e.g. a scenario's NAME from
+        # (scenario.init dummy_1x1_grid, ..., scenario.name ()) (explorer_scenario_helper.fut:26-31, :43-44) and relies on the
+        # compiler to drop the unused components, out-of-bounds edits included.
+        out = []
+        for x in e[1]:
+            try:
+                out.append(ev(x, env))
+            except FutharkError as exc:
+                out.append(Poison(exc))
+        return tuple(out)
     if k == "record":
         return {name: ev(x, env) for name, x in e[1]}
     if k == "array":
@@ -814,6 +899,7 @@ def reduce_(f, ne, xs):
 def prelude():
     ident = builtin("id", 1, lambda x: x)
     ints = Module({"i8": ident, "i16": ident, "i32": ident, "i64": ident, "u8": ident, "u32": ident, "u64": ident,
+                   "f32": builtin("int.f32", 1, lambda v: int(v)), "f64": builtin("int.f64", 1, lambda v: int(v)),
                    "bool": builtin("bool", 1, lambda b: int(bool(b))),
                    "sum": builtin("sum", 1, lambda xs: sum(xs)),
                    "abs": builtin("abs", 1, abs), "sgn": builtin("sgn", 1, lambda v: (v > 0) - (v < 0)),
@@ -836,6 +922,9 @@ def prelude():
         "length": builtin("length", 1, len),
         "copy": ident,
         "iota": builtin("iota", 1, lambda n: list(range(n))),
+        "const": builtin("const", 2, lambda x, _y: x),
+        "t32": builtin("t32", 1, lambda v: int(v)),
+        "f32": Module({"i32": builtin("f32.i32", 1, F32), "i64": builtin("f32.i64", 1, F32), "f64": builtin("f32.f64", 1, F32)}),
     }
 
 
@@ -866,37 +955,70 @@ class Program:
         return self.load(target)
 
     def run_decls(self, decls, env, exported, here):
+        """Definitions are not recursive and may shadow earlier ones (designer.fut defines `step` twice): every declaration
+        opens a new scope on top of the previous ones, and a function closes over the scope BEFORE its own name."""
         for d in decls:
             k = d[0]
             if k == "def":
                 _k, name, sizes, params, body, local = d
                 val = Fn(name, sizes, params, body, env) if params else ev(body, env)
-                env.vars[name] = val
+                env = Env(env, {name: val})
                 if not local:
                     exported[name] = val
             elif k == "import":
                 table = self.resolve_import(d[1], here)
-                env.vars.update(table)
+                env = Env(env, dict(table))
                 if d[2]:                                 # `open import`: re-exported
                     exported.update(table)
             elif k == "open":
                 mod = env.lookup(d[1])
-                env.vars.update(mod.names)
+                env = Env(env, dict(mod.names))
                 exported.update(mod.names)
             elif k == "module":
-                _k, name, body, local = d
-                inner_env, inner_exp = Env(env), {}
-                self.run_decls(body, inner_env, inner_exp, here)
-                env.vars[name] = Module(inner_exp)
+                _k, name, fparams, mexp, local = d
+                if fparams:
+                    val = Functor(fparams, mexp, env, here, self)
+                else:
+                    val = self.eval_module(mexp, env, here)
+                env = Env(env, {name: val})
                 if not local:
-                    exported[name] = env.vars[name]
-            elif k == "module_import":
-                env.vars[d[1]] = Module(self.resolve_import(d[2], here))
-                exported[d[1]] = env.vars[d[1]]
-            elif k == "module_alias":
-                words = d[2]
-                try:
-                    env.vars[d[1]] = env.lookup(words[0]) if len(words) == 1 else Module({})
-                except NameError:
-                    env.vars[d[1]] = Module({})
-                exported[d[1]] = env.vars[d[1]]
+                    exported[name] = val
+        return env
+
+    def eval_module(self, mexp, env, here):
+        k = mexp[0]
+        if k == "mbody":
+            inner_env, inner_exp = Env(env), {}
+            self.run_decls(mexp[1], inner_env, inner_exp, here)
+            return Module(inner_exp)
+        if k == "mimport":
+            return Module(self.resolve_import(mexp[1], here))
+        if k == "mname":
+            try:
+                m = env.lookup(mexp[1][0])
+                for part in mexp[1][1:]:
+                    m = m.names[part]
+                return m
+            except (NameError, KeyError):
+                return Module({})                      # a module of a library that is not in the reference tree
+        if k == "mapp":
+            f = self.eval_module(mexp[1], env, here)
+            arg = self.eval_module(mexp[2], env, here)
+            if not isinstance(f, Functor):
+                return Module({})                      # e.g. uniform_int_distribution i8 rnge (cpprandom): stubbed elsewhere
+            return f.apply(arg)
+        raise FutharkError(f"module expression {k}")
+
+
+class Functor:
+    def __init__(self, params, body, env, here, program):
+        self.params, self.body, self.env, self.here, self.program, self.args = params, body, env, here, program, []
+
+    def apply(self, arg):
+        args = self.args + [arg]
+        if len(args) < len(self.params):
+            f = Functor(self.params, self.body, self.env, self.here, self.program)
+            f.args = args
+            return f
+        env = Env(self.env, dict(zip(self.params, args)))
+        return self.program.eval_module(self.body, env, self.here)

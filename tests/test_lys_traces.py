@@ -1,0 +1,130 @@
+"""Golden traces of the lys frontends made by EXECUTING explorer/explorer.fut and designer/designer.fut themselves under
+tests/golden/futhark_mini.py (generator: tests/golden/make_lys_fixture.py): every scalar field of the state, text_content and
+the grid the state shows, after lys.init and after every event of a scripted session.
+
+CPU suite: the oracle-side models (tests/lys_model.py, which the event-by-event GPU tests of test_lys_frontends.py use as
+their checker) reproduce the traces.  GPU suite: libflowamok_explorer.so / libflowamok_designer.so do, through the entry points
+of include/flowamok_lys.h."""
+import numpy as np
+import pytest
+
+import lys_model as M
+from util import ROOT, STATE_FIELDS, state_digest, state_of
+
+T = np.load(ROOT / "tests" / "golden" / "lys_traces.npz")
+KINDS = ["key", "keyup", "step", "mouse", "wheel", "resize"]
+EXPLORER_SCALARS = ["h", "w", "scale", "auto", "steps_auto_per_second", "scenario_id", "steps", "perfect_simulation", "n_cycles",
+                    "n_cell_leaks", "rng_state", "time_unused"]
+DESIGNER_SCALARS = ["h", "w", "gh", "gw", "scale", "running", "steps_per_second", "n_steps_total", "n_leaks", "cursor_some", "cursor_y",
+                    "cursor_x", "rng_state", "time_unused"]
+
+
+def events(prog):
+    out = []
+    for row in T[f"{prog}/events"]:
+        kind = KINDS[int(row[0])]
+        if kind == "step":
+            out.append((kind, np.float32(row[1])))
+        elif kind in ("key", "keyup"):
+            out.append((kind, int(row[1])))
+        elif kind == "mouse":
+            out.append((kind, int(row[1]), int(row[2]), int(row[3])))
+        else:
+            out.append((kind, int(row[1]), int(row[2])))
+    return out
+
+
+def want_scalars(prog, i):
+    names = EXPLORER_SCALARS if prog == "explorer" else DESIGNER_SCALARS
+    d = dict(zip(names, (int(v) for v in T[f"{prog}/{i}/scalars"])))
+    d["rng_state"] &= (1 << 64) - 1
+    d["time_unused"] = np.uint32(d["time_unused"]).view(np.float32)
+    return d
+
+
+def check(prog, i, fields, state, text, what):
+    want = want_scalars(prog, i)
+    for k, v in want.items():
+        got = fields[k]
+        if k == "time_unused":
+            assert np.float32(got).tobytes() == np.float32(v).tobytes(), f"{what}: time_unused {got!r}, the reference has {v!r}"
+        elif k in ("cursor_y", "cursor_x") and not want["cursor_some"]:
+            continue
+        else:
+            assert (got or 0) == v, f"{what}: {k} = {got}, the reference has {v}"
+    for k in ("dy", "dx", "color", "pref"):
+        assert np.array_equal(state[k], T[f"{prog}/{i}/{k}"]), f"{what}: grid field {k}"
+    assert state_digest(state) == tuple(int(v) for v in T[f"{prog}/{i}/digest"]), f"{what}: digest of the grid (rng states included)"
+    assert tuple(text) == tuple(int(v) for v in T[f"{prog}/{i}/text"]), f"{what}: text_content"
+
+
+def model_apply(m, ev):
+    if ev[0] == "key":
+        m.keydown(ev[1])
+    elif ev[0] == "step":
+        m.event_step(ev[1])
+    elif ev[0] == "mouse":
+        m.mouse(*ev[1:])
+    elif ev[0] == "resize":
+        m.resize(*ev[1:])
+
+
+@pytest.mark.parametrize("prog", ["explorer", "designer"])
+def test_models_reproduce_the_reference_source_traces(prog):
+    seed, h, w = (int(v) for v in T[f"{prog}/meta"])
+    m = (M.ExplorerModel if prog == "explorer" else M.DesignerModel)(seed, h, w)
+    if prog == "explorer":
+        for k in range(14):                                    # lys.init builds all fourteen grids (explorer.fut:89-101)
+            a = m.grids[k].arrays()
+            assert np.array_equal(np.stack([a["uy"], a["ux"]]), T[f"explorer/init/{k}/roads"]), f"scenario {k}: roads"
+            assert np.array_equal(np.stack([a["dy"], a["dx"]]), T[f"explorer/init/{k}/cars"]), f"scenario {k}: cars"
+            assert state_digest(state_of(m.grids[k])) == tuple(int(v) for v in T[f"explorer/init/{k}/digest"])
+        assert M.explorer_text_format() == bytes(T["explorer/text_format"]).decode()
+    check(prog, 0, m.fields(), state_of(m.grid), m.text_content(59.94), "init")
+    for i, ev in enumerate(events(prog), 1):
+        model_apply(m, ev)
+        check(prog, i, m.fields(), state_of(m.grid), m.text_content(59.94), f"event {i} {ev}")
+        a = m.grid.arrays()
+        assert np.array_equal(np.stack([a["uy"], a["ux"]]), T[f"{prog}/{i}/roads"]), f"event {i} {ev}: roads"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prog", ["explorer", "designer"])
+def test_libraries_reproduce_the_reference_source_traces(prog):
+    import flowamok_b200.lys as lys
+    seed, h, w = (int(v) for v in T[f"{prog}/meta"])
+    p = lys.Program(prog, device=0)
+    octx = p.operator_context()
+    assert p.text_format() == bytes(T[f"{prog}/text_format"]).decode()
+    s = p.init(seed, h, w)
+
+    def look(i, what):
+        g = p.grid(s, octx)
+        d = g.download()
+        check(prog, i, p.fields(s), {k: d[k] for k in STATE_FIELDS}, p.text_content(s, 59.94), what)
+        assert np.array_equal(np.stack([d["uy"], d["ux"]]), T[f"{prog}/{i}/roads"]), f"{what}: roads"
+    look(0, "init")
+    if prog == "explorer":                                     # the other thirteen grids of lys.init: walk through them and back
+        for k in range(1, 14):
+            s = p.key(s, lys.SDLK_RIGHT)
+            d = p.grid(s, octx).download()
+            assert np.array_equal(np.stack([d["uy"], d["ux"]]), T[f"explorer/init/{k}/roads"]), f"scenario {k}: roads"
+            assert state_digest({f: d[f] for f in STATE_FIELDS}) == tuple(int(v) for v in T[f"explorer/init/{k}/digest"])
+        s = p.key(s, lys.SDLK_RIGHT)
+        assert p.fields(s)["scenario_id"] == 0
+    for i, ev in enumerate(events(prog), 1):
+        if ev[0] == "key":
+            s = p.key(s, ev[1])
+        elif ev[0] == "keyup":
+            s = p.key(s, ev[1], up=True)
+        elif ev[0] == "step":
+            s = p.step(s, float(ev[1]))
+        elif ev[0] == "mouse":
+            s = p.mouse(s, *ev[1:])
+        elif ev[0] == "wheel":
+            s = p.wheel(s, *ev[1:])
+        else:
+            s = p.resize(s, *ev[1:])
+        look(i, f"event {i} {ev}")
+    p.free(s)
+    p.close()
