@@ -101,6 +101,20 @@ class Parser:
     def skip_type(self, stop):
         """skip a type up to (not including) one of the `stop` tokens at nesting depth 0; returns the leading dims"""
         dims, depth, leading = [], 0, True
+        self.last_tyapp = None
+        first = self.peek()
+        if first.kind == "id" and first.text not in KEYWORDS and self.peek(1).text == "[":     # `state [] [gh] [gw]`
+            j, args = 1, []
+            while self.peek(j).text == "[":
+                if self.peek(j + 1).text == "]":
+                    args.append(None)
+                    j += 2
+                elif self.peek(j + 2).text == "]":
+                    args.append(self.peek(j + 1).text)
+                    j += 3
+                else:
+                    break
+            self.last_tyapp = (first.text, args)
         while True:
             tok = self.peek()
             if tok.kind == "eof":
@@ -182,7 +196,7 @@ class Parser:
         if self.at(":"):
             self.eat(":")
             dims = self.skip_type({",", ")", "="})
-            p = ("ptyped", p, dims)
+            p = ("ptyped", p, dims, self.last_tyapp)
         return p
 
     # -- expressions
@@ -538,6 +552,9 @@ class Parser:
                 out.append(("module", name, fparams, mexp, local))
             elif tok.text == "type":
                 self.eat()
+                td = self.typedef()
+                if td:
+                    out.append(td)
                 while self.peek().kind != "eof" and self.peek().text not in DECL_START and not (until and self.peek().text == until
                                                                                               and self.depth0()):
                     if self.at("{"):
@@ -549,6 +566,33 @@ class Parser:
 
     def depth0(self):
         return True
+
+    def typedef(self):
+        """`type name [p] [q] = {field: [p][q]elem, ...}`: which field and axis carries each size parameter (look-ahead only)"""
+        j = 0
+        if self.peek(j).text in ("~", "^"):
+            j += 1
+        name = self.peek(j).text
+        j += 1
+        params = []
+        while self.peek(j).text == "[" and self.peek(j + 2).text == "]":
+            params.append(self.peek(j + 1).text)
+            j += 3
+        if not params or self.peek(j).text != "=" or self.peek(j + 1).text != "{":
+            return None
+        j += 2
+        where, depth = {}, 1
+        while depth and self.peek(j).kind != "eof":
+            tok = self.peek(j)
+            if depth == 1 and tok.kind == "id" and self.peek(j + 1).text == ":":
+                field, k, axis = tok.text, j + 2, 0
+                while self.peek(k).text == "[" and self.peek(k + 2).text == "]":
+                    where.setdefault(self.peek(k + 1).text, (field, axis))
+                    axis += 1
+                    k += 3
+            depth += (tok.text == "{") - (tok.text == "}")
+            j += 1
+        return ("typedef", name, params, where)
 
     def skip_module_sig(self):
         """skip `sig` or `sig with t = u ...` up to the `=` that introduces the module's body"""
@@ -658,6 +702,9 @@ def builtin(name, arity, py):
     return Fn(name, (), [None] * arity, None, None, (), py)
 
 
+TYPEDEFS = {}      # record types with size parameters: name -> (parameters, {parameter: (field, axis)})
+
+
 class FutharkError(Exception):
     pass
 
@@ -710,6 +757,15 @@ def bind(p, v, env, sizes=()):
                         raise FutharkError(f"size parameter {d}: {env.vars[d]} vs {len(x)}")
                     env.vars.setdefault(d, len(x))
                 x = x[0] if isinstance(x, list) and x else None
+        if sizes and len(p) > 3 and p[3] and p[3][0] in TYPEDEFS and isinstance(v, dict):
+            params, where = TYPEDEFS[p[3][0]]
+            for formal, actual in zip(params, p[3][1]):
+                if actual in sizes and formal in where:
+                    field, axis = where[formal]
+                    x = v[field]
+                    for _ in range(axis):
+                        x = x[0] if x else []
+                    env.vars.setdefault(actual, len(x))
         return bind(p[1], v, env, sizes)
     if k == "ptuple":
         if not isinstance(v, tuple) or len(v) != len(p[1]):
@@ -965,6 +1021,8 @@ class Program:
                 env = Env(env, {name: val})
                 if not local:
                     exported[name] = val
+            elif k == "typedef":
+                TYPEDEFS[d[1]] = (d[2], d[3])
             elif k == "import":
                 table = self.resolve_import(d[1], here)
                 env = Env(env, dict(table))

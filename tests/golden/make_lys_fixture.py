@@ -192,11 +192,45 @@ def designer_session(data):
     data["designer/text_format"] = np.frombuffer(F.call(lys["text_format"], ()).encode(), np.uint8)
 
 
+def readme_session(data):
+    """README.fut: `init 30 30 10 123` and `step` (animation.fut:14-32), what `futhark literate` runs 400 times for the GIF"""
+    ref = F.Program(stubs()).load(REF / "README.fut")
+    n_frames = 40
+    s = F.call(ref["init"], 30, 30, 10, 123)
+    data["readme/meta"] = np.array([30, 30, 10, 123, n_frames, len(s["cycles"])], np.int64)
+    for k in range(n_frames):
+        t0 = time.time()
+        px, s = F.call(ref["step"], s)                      # the frame shows the grid BEFORE the tick (animation.fut:22-24)
+        h, w = len(px), len(px[0])
+        kind, base = np.zeros((h, w), np.uint8), np.zeros((h, w), np.uint32)
+        for y in range(h):
+            for x in range(w):
+                v = px[y][x]
+                if isinstance(v, int):
+                    base[y, x] = v
+                elif v[0] == "gray":
+                    kind[y, x] = 1
+                else:
+                    kind[y, x], base[y, x] = 2, v[4]
+        data[f"readme/{k}/kind"], data[f"readme/{k}/base"] = kind, base
+        st = from_cells(s["grid"])
+        for f in ("dy", "dx", "color", "pref"):
+            data[f"readme/{k}/{f}"] = st[f]
+        data[f"readme/{k}/digest"] = np.array(state_digest(st), np.uint64)
+        print(f"readme frame {k:3d}  {time.time() - t0:5.1f} s", flush=True)
+    data["readme/rng"] = np.array([s["rng"] - (1 << 64) if s["rng"] >= 1 << 63 else s["rng"], s["steps"]], np.int64)
+
+
 def main():
     data = {}
     t0 = time.time()
-    designer_session(data)
-    explorer_session(data)
+    if len(sys.argv) > 1:                                    # python make_lys_fixture.py readme: only that session, the rest is kept
+        data = dict(np.load(HERE / "lys_traces.npz"))
+        {"readme": readme_session, "designer": designer_session, "explorer": explorer_session}[sys.argv[1]](data)
+    else:
+        readme_session(data)
+        designer_session(data)
+        explorer_session(data)
     out = HERE / "lys_traces.npz"
     np.savez_compressed(out, **data)
     print(f"wrote {out} ({out.stat().st_size} bytes) in {time.time() - t0:.0f} s")

@@ -128,3 +128,53 @@ def test_libraries_reproduce_the_reference_source_traces(prog):
         look(i, f"event {i} {ev}")
     p.free(s)
     p.close()
+
+
+# ---- README.fut: init 30 30 10 123 and step (animation.fut:14-32), the program of the README GIF ----
+def check_frame(k, px):
+    kind, base = T[f"readme/{k}/kind"], T[f"readme/{k}/base"]
+    plain = kind == 0
+    assert np.array_equal(px[plain], base[plain]), f"frame {k}: plain pixels"
+    assert len(np.unique(px[kind == 1])) <= 1, f"frame {k}: grey"
+    for b in np.unique(base[kind == 2]):
+        assert len(np.unique(px[(kind == 2) & (base == b)])) == 1, f"frame {k}: mix of {b:#x}"
+
+
+def test_oracle_anim_reproduces_the_readme_program():
+    from util import O
+    gh, gw, scale, seed, n_frames, n_cycles = (int(v) for v in T["readme/meta"])
+    oa = O.Anim(8, gh, gw, scale, seed)
+    assert len(oa.cycles) == n_cycles
+    for k in range(n_frames):
+        check_frame(k, oa.step(render=True))
+        st = state_of(oa.grid)
+        for f in ("dy", "dx", "color", "pref"):
+            assert np.array_equal(st[f], T[f"readme/{k}/{f}"]), f"after step {k}: {f}"
+        assert state_digest(st) == tuple(int(v) for v in T[f"readme/{k}/digest"]), f"after step {k}: digest (rng states included)"
+    assert (np.int64(np.uint64(oa.rng.state)), oa.steps) == tuple(T["readme/rng"])
+
+
+@pytest.mark.gpu
+def test_generated_library_surface_reproduces_the_readme_program():
+    """futhark_entry_init / futhark_entry_step of libflowamok_b200.so (include/flowamok_futhark.h): every frame"""
+    import ctypes as C
+    import flowamok_b200.capi as capi
+    L = capi.lib()
+    gh, gw, scale, seed, n_frames, _n = (int(v) for v in T["readme/meta"])
+    cfg = L.futhark_context_config_new()
+    fctx = L.futhark_context_new(cfg)
+    st = C.c_void_p()
+    assert L.futhark_entry_init(fctx, C.byref(st), gh, gw, scale, seed) == 0
+    for k in range(n_frames):
+        px, st2 = C.c_void_p(), C.c_void_p()
+        assert L.futhark_entry_step(fctx, C.byref(px), C.byref(st2), st) == 0
+        frame = np.zeros((gh * scale, gw * scale), np.uint32)
+        assert L.futhark_values_u32_2d(fctx, px, frame.ctypes.data) == 0
+        assert L.futhark_context_sync(fctx) == 0
+        check_frame(k, frame)
+        L.futhark_free_u32_2d(fctx, px)
+        L.futhark_free_opaque_state(fctx, st)
+        st = st2
+    L.futhark_free_opaque_state(fctx, st)
+    L.futhark_context_free(fctx)
+    L.futhark_context_config_free(cfg)
