@@ -221,14 +221,46 @@ def readme_session(data):
     data["readme/rng"] = np.array([s["rng"] - (1 << 64) if s["rng"] >= 1 << 63 else s["rng"], s["steps"]], np.int64)
 
 
+def hooks_session(data):
+    """scenario.init and 120 consecutive scenario.step calls (steps = 0 .. 119) of every scenario of explorer/scenarios.fut, through
+    explorer.fut's own `scenario` module (explorer.fut:4-44), without ticks in between: which hook injects what, when, what it
+    draws from the rng, and when it asks for new cycle_checks"""
+    from make_stepper_fixture import to_cells
+    scenario = F.Program(stubs()).load(REF / "explorer" / "explorer.fut")["scenario"].names
+    gh, gw, n_steps = 108, 192, 120
+    z = np.zeros((gh, gw), np.int8)
+    empty = dict(uy=z, ux=z, dy=z, dx=z, color=np.full((gh, gw), 0xFFFFFFFF, np.uint32), pref=np.zeros((gh, gw), np.uint8),
+                 rng_state=np.zeros((gh, gw), np.uint64))
+    data["hooks/meta"] = np.array([gh, gw, n_steps, scenario["n_scenarios"]], np.int64)
+    for sid in range(scenario["n_scenarios"]):
+        t0 = time.time()
+        grid = F.call(scenario["init"], sid, to_cells(empty))
+        rng = O.Rng.from_seed([1000 + sid]).state
+        recs, rngs = [], []
+        for steps in range(n_steps):
+            rng, rec, grid = F.call(scenario["step"], sid, grid, steps, rng)
+            recs.append(int(rec))
+            rngs.append(rng - (1 << 64) if rng >= 1 << 63 else rng)
+            if steps in (0, 9, 29, 59, n_steps - 1):
+                st = from_cells(grid)
+                for f in ("uy", "ux", "dy", "dx", "color"):
+                    data[f"hooks/{sid}/{steps}/{f}"] = st[f]
+        data[f"hooks/{sid}/recompute"] = np.array(recs, np.uint8)
+        data[f"hooks/{sid}/rng"] = np.array(rngs, np.int64)
+        data[f"hooks/{sid}/name"] = np.frombuffer(F.call(scenario["name"], sid).encode(), np.uint8)
+        print(f"hooks scenario {sid:2d} {F.call(scenario['name'], sid):28s} recompute at {[i for i, r in enumerate(recs) if r]}  "
+              f"{time.time() - t0:5.1f} s", flush=True)
+
+
 def main():
     data = {}
     t0 = time.time()
     if len(sys.argv) > 1:                                    # python make_lys_fixture.py readme: only that session, the rest is kept
         data = dict(np.load(HERE / "lys_traces.npz"))
-        {"readme": readme_session, "designer": designer_session, "explorer": explorer_session}[sys.argv[1]](data)
+        {"readme": readme_session, "designer": designer_session, "explorer": explorer_session, "hooks": hooks_session}[sys.argv[1]](data)
     else:
         readme_session(data)
+        hooks_session(data)
         designer_session(data)
         explorer_session(data)
     out = HERE / "lys_traces.npz"

@@ -178,3 +178,46 @@ def test_generated_library_surface_reproduces_the_readme_program():
     L.futhark_free_opaque_state(fctx, st)
     L.futhark_context_free(fctx)
     L.futhark_context_config_free(cfg)
+
+
+# ---- the scenario hooks of explorer/scenarios.fut through explorer.fut's `scenario` module: init + 120 step calls each ----
+HOOK_SNAPSHOTS = (0, 9, 29, 59, 119)
+
+
+@pytest.mark.parametrize("sid", range(14))
+def test_oracle_scenario_hooks_equal_the_reference_source(sid):
+    from util import O
+    gh, gw, n_steps, n_scen = (int(v) for v in T["hooks/meta"])
+    assert n_scen == 14 and O.scenario_name(sid) == bytes(T[f"hooks/{sid}/name"]).decode()
+    og = O.Grid(gh, gw)
+    og.create(O.Rng.from_seed([1]))
+    og.scenario_init(sid)
+    rng = O.Rng.from_seed([1000 + sid])
+    for steps in range(n_steps):
+        rec = og.scenario_step(sid, steps, rng)
+        assert int(rec) == int(T[f"hooks/{sid}/recompute"][steps]), f"scenario {sid} step {steps}: recompute_cycles"
+        assert np.int64(np.uint64(rng.state)) == T[f"hooks/{sid}/rng"][steps], f"scenario {sid} step {steps}: rng"
+        if steps in HOOK_SNAPSHOTS:
+            a = og.arrays()
+            for f in ("uy", "ux", "dy", "dx", "color"):
+                assert np.array_equal(a[f], T[f"hooks/{sid}/{steps}/{f}"]), f"scenario {sid} step {steps}: {f}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sid", range(14))
+def test_product_scenario_hooks_equal_the_reference_source(ctx, sid):
+    """flowamok_b200.scenarios (the host-side hooks over the point-edit entries of the C ABI) on a device grid"""
+    from flowamok_b200 import scenarios as S
+    gh, gw, n_steps, _n = (int(v) for v in T["hooks/meta"])
+    g = ctx.create_grid(gh, gw, 1)
+    S.init(sid, g)
+    rng = S.Pcg32.from_seed([1000 + sid])
+    for steps in range(n_steps):
+        rec = S.step(sid, g, steps, rng)
+        assert int(bool(rec)) == int(T[f"hooks/{sid}/recompute"][steps]), f"scenario {sid} step {steps}: recompute_cycles"
+        assert np.int64(np.uint64(rng.state)) == T[f"hooks/{sid}/rng"][steps], f"scenario {sid} step {steps}: rng"
+        if steps in HOOK_SNAPSHOTS:
+            d = g.download()
+            for f in ("uy", "ux", "dy", "dx", "color"):
+                assert np.array_equal(d[f], T[f"hooks/{sid}/{steps}/{f}"]), f"scenario {sid} step {steps}: {f}"
+    g.free()
