@@ -164,7 +164,8 @@ def cases():
     # quick mode on random networks: queues, merges, forks, leaks, off-road cars, diagonal headings
     r = np.random.default_rng(2024)
     shapes = [(9, 13), (12, 16), (7, 33), (20, 9), (14, 14), (16, 20), (1, 24), (18, 1), (10, 35), (24, 31), (30, 40), (33, 33),
-              (5, 64), (40, 12), (2, 2), (3, 70), (26, 26), (17, 45), (31, 32), (32, 33)]
+              (5, 64), (40, 12), (2, 2), (3, 70), (26, 26), (17, 45), (31, 32), (32, 33),
+              (1, 1), (4, 32), (4, 33), (3, 64), (3, 65), (2, 31), (3, 96), (3, 97), (6, 129)]      # plane-word boundaries of the CUDA layout
     for i, (gh, gw) in enumerate(shapes):
         nl = int(r.integers(2, 3 + (gh + gw) // 2))
         car_p, wp, op = float(r.choice([0.3, 0.6, 0.9, 1.0])), float(r.choice([0.0, 0.03, 0.15])), float(r.choice([0.0, 0.01, 0.08]))

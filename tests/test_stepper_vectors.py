@@ -32,7 +32,7 @@ def expected_states(name, arrs, ticks):
 
 
 def test_vector_set_is_what_the_generator_describes():
-    assert len(NAMES) >= 40
+    assert len(NAMES) >= 50
     assert sum(int(V[f"{n}/meta"][2]) for n in NAMES) >= 15                       # perfect-mode cases
     assert sum(len(V[f"{n}/t{t}/leaks"]) for n in NAMES for t in range(1, int(V[f"{n}/meta"][4]) + 1)) > 2000
     assert sum(len(V[f"{n}/t{t}/rng_idx"]) for n in NAMES for t in range(1, int(V[f"{n}/meta"][4]) + 1)) > 300   # fork draws
