@@ -27,7 +27,8 @@ if str(ROOT) not in sys.path:
 B_ALG = 12.0  # algorithmic bytes per cell-update (SURVEY 8d / BASELINE.md): r+w of a u16 control word and a u32 colour
 
 RNG_PARITY = ("unverified: the fork stream of the reference's README GIF is not reproduced (diku-dk/cpprandom 1.3.1 is not "
-              "vendored; DESIGN.md section 4); CUDA == oracle bit for bit, movement semantics pinned by the GIF")
+              "vendored; DESIGN.md section 4); CUDA == oracle bit for bit; everything but the draw arithmetic is pinned by the GIF and by "
+              "vectors made by executing the reference's own steppers.fut (tests/golden/futhark_mini.py)")
 
 
 def csrc_hash():
