@@ -199,6 +199,13 @@ def cases():
     for i, seed in enumerate(PERFECT_RANDOM_SEEDS):
         out.append(dict(name=f"perfect_random_{i}", arrs=random_grid(seed, 12, 14, n_lines=7, car_p=0.9, weird_p=0.02, offroad_p=0.01),
                         perfect=True, mode=[CHOOSE_RANDOM, CHOOSE_TAPE, CHOOSE_RANDOM, CHOOSE_Y][i % 4], ticks=12))
+    # long runs: alternation patterns and ring rotation over a hundred ticks and more
+    out.append(dict(name="long_quick_random", arrs=random_grid(4242, 16, 22, n_lines=11, car_p=0.8, weird_p=0.02, offroad_p=0.01),
+                    perfect=False, mode=CHOOSE_RANDOM, ticks=150))
+    a = grid_from_lines(16, 18, ring(2, 2, 8, -1) + [("h", 6, 2, 14, 1), ("v", 14, 6, 10, 1), ("h", 10, 2, 14, -1)], [], 21)
+    out.append(dict(name="long_perfect_overlapping_cycles", arrs=fill_roads(a, 1.0, 21), perfect=True, mode=CHOOSE_RANDOM, ticks=120))
+    a = grid_from_lines(12, 18, [("h", 6, 0, 16, 1), ("v", 9, 0, 6, 1), ("v", 4, 6, 11, 1)], [], 22)
+    out.append(dict(name="long_quick_merge_and_fork", arrs=fill_roads(a, 1.0, 22), perfect=False, mode=CHOOSE_RANDOM, ticks=100))
     for i, seed in enumerate(RING_NETWORK_SEEDS):
         out.append(dict(name=f"perfect_ring_network_{i}", arrs=ring_network(seed), perfect=True,
                         mode=[CHOOSE_RANDOM, CHOOSE_RANDOM, CHOOSE_TAPE, CHOOSE_X][i % 4], ticks=14))
