@@ -154,3 +154,22 @@ def test_cuda_edits_equal_the_reference_source(ctx, i):
     for k in ("uy", "ux", "dy", "dx", "color"):
         assert np.array_equal(d[k], V[f"edits/{i}/{k}"]), k
     g.free()
+
+
+# ---- the kernel programs themselves (fa_stream.h / fa_tiles.h compiled for the host, warp lanes as coroutines) ----
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_emulated_kernel_programs_equal_the_reference_source(variant):
+    """no GPU needed: the code the CUDA kernels run (strip / tile programs, speculative move + fix-up, sparse ring resolution),
+    in three shapes of strips, tiles and Jacobi levels, against the vectors -- state and leak COUNT (the emulation does not
+    build the leak list)"""
+    from util import EmulGrid
+    for name in NAMES:
+        gh, gw, perfect, mode, ticks, arrs, tape = case(name)
+        eg = EmulGrid(arrs)
+        rings = None
+        if perfect:
+            rings = oracle_grid(arrs).rings_from_masks(V[f"{name}/cycles"])      # dense masks -> the sparse list the kernels take
+        for t, want, leaks in expected_states(name, arrs, min(ticks, 40)):
+            n = eg.step(variant=variant, chooser=mode, tape_bit=int(tape[(t - 1) % len(tape)]), rings=rings)
+            assert n == len(leaks), f"{name} variant {variant} tick {t}: leak count"
+            assert_state_equal(want, eg.state(), f"{name} variant {variant} tick {t}")
