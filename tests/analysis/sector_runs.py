@@ -3,13 +3,14 @@
 question whether bulk-async copies, cp.async.bulk / TMA, could move the colour payload: a bulk copy needs >= 16 contiguous
 bytes, and pays an shared-memory round trip + mbarrier per transfer, so it only has a chance on LONG runs.)
 Oracle run of the synthetic network (statistics do not depend on the grid size); a sector is copied iff a car arrived in
-it in this tick or the previous one.  python tools/sector_runs.py [size] [ticks]"""
+it in this tick or the previous one.  Analysis script under tests/ because it runs the ORACLE (test infrastructure).
+python tests/analysis/sector_runs.py [size] [ticks]"""
 import sys
 from pathlib import Path
 
 import numpy as np
 
-sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent.parent))
 from oracle import oracle as O
 
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
