@@ -25,6 +25,10 @@ P, I32, I64, U32, U64, F32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_u
 EXPORTS = ["futhark_context_config_new", "futhark_context_config_free", "futhark_context_config_set_debugging",
            "futhark_context_config_set_profiling", "futhark_context_config_set_logging", "futhark_context_config_set_device",
            "futhark_context_new", "futhark_context_free", "futhark_context_sync", "futhark_context_get_error",
+           "futhark_context_config_set_tuning_param", "futhark_get_tuning_param_count", "futhark_get_tuning_param_name",
+           "futhark_get_tuning_param_class", "futhark_context_config_set_cache_file", "futhark_context_set_logging_file",
+           "futhark_context_pause_profiling", "futhark_context_unpause_profiling", "futhark_context_clear_caches",
+           "futhark_context_report",
            "futhark_entry_init", "futhark_entry_resize", "futhark_entry_key", "futhark_entry_mouse", "futhark_entry_wheel",
            "futhark_entry_step", "futhark_entry_render", "futhark_entry_text_format", "futhark_entry_text_content",
            "futhark_entry_text_colour", "futhark_entry_grab_mouse", "futhark_free_opaque_state", "futhark_free_u32_2d",

@@ -23,7 +23,9 @@
 #ifndef FLOWAMOK_LYS_H
 #define FLOWAMOK_LYS_H
 #include <stdbool.h>
+#include <stddef.h>
 #include <stdint.h>
+#include <stdio.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -44,6 +46,17 @@ struct futhark_context *futhark_context_new(struct futhark_context_config *cfg);
 void futhark_context_free(struct futhark_context *ctx);
 int futhark_context_sync(struct futhark_context *ctx);
 char *futhark_context_get_error(struct futhark_context *ctx);
+/* the rest of the context API of a generated library (accepted; there is nothing to tune, cache or profile here) */
+int futhark_context_config_set_tuning_param(struct futhark_context_config *cfg, const char *param_name, size_t new_value);
+int futhark_get_tuning_param_count(void);
+const char *futhark_get_tuning_param_name(int i);
+const char *futhark_get_tuning_param_class(int i);
+void futhark_context_config_set_cache_file(struct futhark_context_config *cfg, const char *f);
+void futhark_context_set_logging_file(struct futhark_context *ctx, FILE *f);
+void futhark_context_pause_profiling(struct futhark_context *ctx);
+void futhark_context_unpause_profiling(struct futhark_context *ctx);
+int futhark_context_clear_caches(struct futhark_context *ctx);
+char *futhark_context_report(struct futhark_context *ctx);   /* malloc'd */
 
 /* explorer.fut:89-101 / designer.fut:36-45   init (seed: u32) (h: i64) (w: i64) */
 int futhark_entry_init(struct futhark_context *ctx, struct futhark_opaque_state **out0, const uint32_t seed, const int64_t h,
