@@ -3,7 +3,7 @@
 with seed 123, then `lys.step s 1` again and again, perfect simulation) EXECUTED by tests/golden/futhark_mini.py for the first
 N_TICKS ticks -- the interpreter needs about four seconds per tick of a 108 x 192 grid, so not the 1000 ticks of the config.
 Recorded per tick: the digest of the grid (tests/util.state_digest: headings, colours, preferences, rng states), the cell
-leaks of the tick, the explorer's rng, the number of cycle_checks; the full grid every tenth tick.
+leaks of the tick, the explorer's rng, the number of cycle_checks; the full grid at ticks 1, 10, 50, 100, 150, 200.
 
   python tests/golden/make_explorer_runs.py 0 1 2      # these scenario ids -> tests/golden/_parts/explorer_run_<sid>.npz
   python tests/golden/make_explorer_runs.py merge      # -> tests/golden/explorer_runs.npz (committed; derived data only)
@@ -21,7 +21,7 @@ from make_lys_fixture import K, REF, stubs  # noqa: E402
 from make_stepper_fixture import from_cells  # noqa: E402
 from util import state_digest  # noqa: E402
 
-N_TICKS, SEED = 50, 123
+N_TICKS, SEED = 200, 123
 PARTS = HERE / "_parts"
 
 
@@ -41,7 +41,7 @@ def run(sid):
         rng = s["rng"] - (1 << 64) if s["rng"] >= 1 << 63 else s["rng"]
         rows.append([np.uint64(d[0]).astype(np.int64), np.uint64(d[1]).astype(np.int64), s["n_cell_leaks"], rng, len(s["cycle_checks"]),
                      s["steps"][sid]])
-        if t % 10 == 0 or t == 1:
+        if t in (1, 10, 50, 100, 150, 200):
             for f in ("uy", "ux", "dy", "dx", "color", "pref"):
                 data[f"t{t}/{f}"] = st[f]
         print(f"scenario {sid:2d} tick {t:3d}: leaks {s['n_cell_leaks']} cycles {len(s['cycle_checks'])}  {time.time() - t0:4.1f} s", flush=True)

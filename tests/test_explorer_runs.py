@@ -1,7 +1,7 @@
 """BASELINE config 2 against the reference's own source text: every explorer scenario, perfect simulation, stepped exactly as
-explorer/explorer.fut:109-130 does -- EXECUTED from explorer.fut by tests/golden/futhark_mini.py for the first 50 ticks
+explorer/explorer.fut:109-130 does -- EXECUTED from explorer.fut by tests/golden/futhark_mini.py for the first 200 ticks
 (tests/golden/make_explorer_runs.py).  Per tick: the digest of the whole grid (rng states included), the cell leaks, the
-explorer's rng and the number of cycle_checks; the full grid at ticks 1, 10, 20, 30, 40, 50.  The oracle on the CPU, the
+explorer's rng and the number of cycle_checks; the full grid at ticks 1, 10, 50, 100, 150, 200.  The oracle on the CPU, the
 CUDA path on the GPU box (where the 1000-tick runs of tests/test_gpu_parity.py continue from there against the oracle)."""
 import numpy as np
 import pytest
