@@ -1,19 +1,27 @@
-"""TEST INFRASTRUCTURE: a small interpreter for the subset of Futhark that flowamok's hot path is written in, so that
-the reference's OWN source text (/root/reference/src/steppers.fut, helpers.fut, utils.fut, option.fut, reduce1.fut)
-can be executed here -- there is no Futhark compiler in the image -- and its outputs committed as golden vectors
-(tests/golden/make_stepper_fixture.py).  It reads the reference files where they lie; nothing of them is copied.
+"""TEST INFRASTRUCTURE: a small interpreter for the subset of Futhark that flowamok is written in, so that the reference's OWN
+source text can be executed here -- there is no Futhark compiler in the image -- and its outputs committed as golden vectors:
+src/steppers.fut, helpers.fut, utils.fut, option.fut, reduce1.fut, flowamok.fut (make_stepper_fixture.py), README.fut /
+animation.fut, explorer/explorer.fut + explorer_scenario_helper.fut + scenarios.fut, designer/designer.fut (make_lys_fixture.py,
+make_explorer_runs.py).  It reads the reference files where they lie; nothing of them is copied.  Its own semantics are
+held by known-answer programs in tests/test_futhark_mini.py.
 
-Subset: top-level `def` / `local def` / `module X = { ... }` / `import` / `open`; expressions `let` (tuple patterns,
-local functions, `let a[i] = v`), `if`, `match` (tuple / constructor / literal patterns), `loop ... while|for`, lambdas,
-curried application, records with field access and `with` updates (nested fields, array indices), tuples, arrays, slices,
-`#constructors`, the operators of the sources, and the prelude functions they call (tabulate_2d, map, map2, map3, zip,
-unzip, filter, all, reduce, flatten, unflatten, replicate, length, copy, i64.sum, conversions).  Types are parsed only
-far enough to skip them and to bind size parameters (`[gh][gw]`) from the shapes of the arguments.
+Subset: declarations `def` / `local def` / `let` / `type` (skipped, except the size parameters of record abbreviations) /
+`module X = { ... }`, module ascriptions, parametric modules and their application to module expressions, `import`,
+`open`; expressions `let` (tuple / record patterns, local functions, `let a[i] = v`), `if`, `match` (tuple / constructor /
+literal / record patterns), `loop ... while|for`, lambdas and sections, curried application, records with field access and
+`with` updates (nested fields, array indices), tuples, arrays, slices, ranges, `#constructors`, strings and characters, `:>`,
+the operators of the sources, and the prelude functions they call (tabulate_2d, map, map2, map3, zip, unzip, filter, all,
+reduce, flatten, unflatten, replicate, length, copy, const, i64.sum, conversions).  Definitions are not recursive and later
+ones shadow earlier ones (lexical scoping per declaration).  Types are parsed only far enough to skip them and to bind size
+parameters (`[gh][gw]`, also through `state [] [gh] [gw]`) from the shapes of the arguments.
 
-Values: integers and booleans are Python's, records are dicts, tuples are tuples, arrays are lists, `#tag x` is
-('#tag', x...).  Nothing is mutated in place.  Modules the sources import but that are not in the reference tree
-(diku-dk/cpprandom, athas/matte, diku-dk/lys) are replaced by stubs: the steppers take `choose_direction` as a
-parameter, so no random number is ever drawn by the vectors' generator.
+Values: integers and booleans are Python's (`/` and `%` round towards negative infinity, as in Futhark), every
+floating-point value is numpy.float32, records are dicts, tuples are tuples, arrays are lists, strings are str, `#tag x` is
+('#tag', x...).  Nothing is mutated in place.  A tuple component whose evaluation fails is poisoned instead of failing the
+tuple (the reference relies on the compiler dropping unused components, explorer_scenario_helper.fut:26-31).  Modules the
+sources import but that are not in the reference tree (diku-dk/cpprandom, athas/matte, diku-dk/lys) are supplied by the caller
+as stubs: the steppers take `choose_direction` as a parameter, and where the frontends draw random numbers the stubs are the
+repository's restated pcg32 (unpinned arithmetic).
 """
 from __future__ import annotations
 
